@@ -1,0 +1,111 @@
+/* tlab_gpu.h -- C ABI of the B200-native tlab hot path (libtlab_gpu.so).
+ *
+ * Drop-in boundary for tlab's incompressible/Boussinesq right-hand side and Runge-Kutta substep.
+ * Every entry point names the reference (turbulencia/tlab, Fortran) interface it replaces as
+ * file:line under src/.  The Fortran host binds these through iso_c_binding (fortran/tlab_gpu_mod.f90,
+ * INTEGRATION.md).  Conventions:
+ *   - all functions return 0 on success or a tlab error code (src/include/dns_error.h numbering;
+ *     TLAB_ERR_CUDA = 200 for CUDA/cuFFT/NCCL failures, text in tlab_gpu_last_error());
+ *   - unless a name ends in _host, array arguments are DEVICE pointers (tlab_gpu_malloc) holding
+ *     double precision data in the reference's layout a(nx,ny,nz), x fastest;
+ *   - bcs is the Fortran bcs(2,2) in column-major order: {bcs(1,1), bcs(2,1), bcs(1,2), bcs(2,2)};
+ *   - one caller thread per process/GPU (the reference is not re-entrant either, opr_elliptic.f90:64-81);
+ *     calls are stream-ordered on the library stream and synchronous at return unless
+ *     tlab_gpu_set_async(1) was called.
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef TLAB_GPU_H
+#define TLAB_GPU_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TLAB_ERR_DIMGRID 48      /* DNS_ERROR_DIMGRID   */
+#define TLAB_ERR_PARPARTITION 45 /* DNS_ERROR_PARPARTITION */
+#define TLAB_ERR_ALLOC 80        /* DNS_ERROR_ALLOC     */
+#define TLAB_ERR_OPTION 85       /* DNS_ERROR_OPTION    */
+#define TLAB_ERR_UNDEVELOP 104   /* DNS_ERROR_UNDEVELOP */
+#define TLAB_ERR_CUDA 200
+
+/* operator codes, src/operators/opr_partial.f90:19-21 and src/physics/opr_burgers.f90 (OPR_B_SELF/U_IN) */
+#define TLAB_OPR_P1 1
+#define TLAB_OPR_P2 2
+#define TLAB_OPR_P2_P1 3
+#define TLAB_OPR_B_SELF 0
+#define TLAB_OPR_B_U_IN 1
+/* boundary-condition codes, src/base/tlab_constants.f90:62-71 */
+#define TLAB_BCS_DD 0
+#define TLAB_BCS_ND 1
+#define TLAB_BCS_DN 2
+#define TLAB_BCS_NN 3
+/* scheme codes, src/fdm/fdm_derivative.f90:51-58 */
+#define TLAB_FDM_COM4_JACOBIAN 4
+#define TLAB_FDM_COM6_JACOBIAN 6
+#define TLAB_FDM_COM6_JACOBIAN_HYPER 7
+/* DNS_BCS_* of src/tools/dns/boundary_bcs.f90:42-46 */
+#define TLAB_DNS_BCS_DIRICHLET 3
+#define TLAB_DNS_BCS_NEUMANN 4
+/* time.f90 RKM_EXP3 / RKM_EXP4 */
+#define TLAB_RKM_EXP3 3
+#define TLAB_RKM_EXP4 4
+
+typedef struct tlab_plan_s* tlab_plan_t; /* one direction: type(fdm_dt), src/fdm/fdm.f90:14-29 */
+
+/* ---- runtime ------------------------------------------------------------------------------- */
+int tlab_gpu_init(int device);                 /* TLab_Start, src/base/tlab_workflow.f90:36-101 (device part) */
+int tlab_gpu_finalize(void);                   /* TLab_Stop */
+const char* tlab_gpu_last_error(void);         /* text of the last failure (TLab_Write_ASCII(efile, ...)) */
+int tlab_gpu_set_async(int on);
+int tlab_gpu_synchronize(void);
+int tlab_gpu_malloc(void** ptr, size_t bytes); /* TLab_Allocate_Real, src/base/tlab_memory.f90:164-216 */
+int tlab_gpu_free(void* ptr);
+int tlab_gpu_upload(void* dst_device, const void* src_host, size_t bytes);
+int tlab_gpu_download(void* dst_host, const void* src_device, size_t bytes);
+int tlab_gpu_set_tuning(const char* key, int value); /* "lines_x", "lines_yz": lines per CTA (0 = automatic) */
+
+/* ---- plans ---------------------------------------------------------------------------------- */
+/* FDM_CreatePlan(x, g), src/fdm/fdm.f90:143-252: builds Jacobians, scheme tables, Neumann reductions
+ * and LU factors from the node positions and uploads them.  dir = 1,2,3 (x,y,z) is informative. */
+int tlab_fdm_plan_create(int dir, int n, const double* nodes_host, int periodic, int uniform,
+                         int mode_der1, int mode_der2, tlab_plan_t* out);
+/* same tables on the host only (no device needed): the handle is valid for tlab_fdm_plan_get/destroy only */
+int tlab_fdm_plan_create_host(int dir, int n, const double* nodes_host, int periodic, int uniform,
+                              int mode_der1, int mode_der2, tlab_plan_t* out);
+int tlab_fdm_plan_destroy(tlab_plan_t plan);
+/* read back host tables of a plan (for hosts that want g%jac, g%der1%mwn, ... from this library):
+ * what = "nodes" | "jac1" | "jac2" | "jac3" | "mwn1" | "mwn2" | "lhs1" | "rhs1" | "lu1" | "lhs2" | "rhs2" | "lu2"
+ * | "rhs1_b" | "rhs1_t"; matrices are returned column-major (Fortran order); *count receives the length. */
+int tlab_fdm_plan_get(tlab_plan_t plan, const char* what, double* out_host, int capacity, int* count);
+
+/* ---- operators ------------------------------------------------------------------------------ */
+/* OPR_Partial_X/Y/Z(type, nx, ny, nz, bcs, g, u, result, tmp1), src/operators/opr_partial.f90:31-377 */
+int tlab_opr_partial(int dir, int type, int nx, int ny, int nz, const int bcs[4], tlab_plan_t g,
+                     const double* u, double* result, double* tmp1_or_null);
+
+/* OPR_Burgers_Initialize, src/physics/opr_burgers.f90:52-115: diffusivity-scaled LU of the second
+ * derivative for is = 0 (visc) and is = 1..nscal (visc/schmidt(is)) on the three plans */
+int tlab_opr_burgers_init(tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz, double visc, int nscal,
+                          const double* schmidt_host);
+/* OPR_Burgers_X/Y/Z(ivel, is, nx, ny, nz, bcs, s, u, result, tmp1, u_t), opr_burgers.f90:190-431.
+ * result = diffusivity(is) * d2s - u * ds along dir.  tmp1 and u_t only carry the reference's transposed
+ * copy of the velocity; no transposed copies exist here, they are accepted and ignored. */
+int tlab_opr_burgers(int dir, int ivel, int is, int nx, int ny, int nz, const int bcs[4], const double* s,
+                     const double* u, double* result, double* tmp1_ignored, const double* u_t_ignored);
+
+/* FDM_Der1_Solve / FDM_Der2_Solve on the reference's lines-first view u(nlines, n),
+ * src/fdm/fdm_derivative.f90:218-278, 413-459 */
+int tlab_fdm_der1_solve(tlab_plan_t g, int nlines, int ibc, const double* u, double* result);
+int tlab_fdm_der2_solve(tlab_plan_t g, int nlines, int is_or_minus1, const double* u, const double* du_ignored,
+                        double* result);
+
+/* BOUNDARY_BCS_NEUMANN_Y(ibc, nx, ny, nz, g, u, bcs_hb, bcs_ht, tmp1), src/tools/dns/boundary_bcs.f90:368-473 */
+int tlab_boundary_bcs_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_t gy, const double* u, double* bcs_hb,
+                                double* bcs_ht);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,133 @@
+"""GPU parity of the directional operators against the oracle (rel. L2 <= 1e-12 per operator call)."""
+import itertools
+
+import numpy as np
+import pytest
+
+from common import grid_periodic, grid_tanh, grid_stretched, smooth_field, rel_l2
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _plans(nx, ny, nz, ykind="stretched", xper=True, zper=True):
+    from oracle import fdm
+    from tlab_b200 import opr
+    x = grid_periodic(nx) if xper else grid_stretched(nx, 2.0)
+    z = grid_periodic(nz) if zper else grid_stretched(nz, 3.0)
+    y = {"stretched": grid_stretched(ny), "tanh": grid_tanh(ny), "uniform": np.linspace(0, 1, ny)}[ykind]
+    yuni = ykind == "uniform"
+    go = [fdm.Plan(x, xper, xper, name="x"), fdm.Plan(y, False, yuni, name="y"), fdm.Plan(z, zper, zper, name="z")]
+    gg = [opr.FdmPlan(x, xper, xper, name="x"), opr.FdmPlan(y, False, yuni, name="y"), opr.FdmPlan(z, zper, zper, name="z")]
+    return (x, y, z), go, gg
+
+
+CASES = [(64, 48, 32, "stretched", True, True),
+         (50, 33, 20, "tanh", True, True),          # ragged: chunk sizes 16/17, lines not a multiple of the tile
+         (32, 16, 17, "uniform", False, False),      # biased schemes in all directions, single-chunk y
+         (130, 40, 36, "stretched", True, False)]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_opr_partial(cuda, case):
+    import torch
+    from oracle import operators as O
+    from tlab_b200 import opr
+    nx, ny, nz, ykind, xper, zper = case
+    grids, go, gg = _plans(nx, ny, nz, ykind, xper, zper)
+    a = smooth_field((nz, ny, nx), grids)
+    u = torch.from_numpy(a).to(cuda)
+    fns = [opr.OPR_Partial_X, opr.OPR_Partial_Y, opr.OPR_Partial_Z]
+    bad = []
+    for idir in range(3):
+        per = go[idir].periodic
+        bcs_list = [[[0, 0], [0, 0]]] if per else [[[b1, 0], [b2, 0]] for b1, b2 in itertools.product((0, 1), (0, 1))]
+        for bcs in bcs_list:
+            for type_ in (O.OPR_P1, O.OPR_P2, O.OPR_P2_P1):
+                res = torch.full_like(u, float("nan"))
+                tmp = torch.full_like(u, float("nan"))
+                fns[idir](type_, nx, ny, nz, bcs, gg[idir], u, res, tmp if type_ == O.OPR_P2_P1 else None)
+                ref = O.opr_partial(idir, type_, bcs, go[idir], a)
+                if type_ == O.OPR_P2_P1:
+                    e2, e1 = rel_l2(res.cpu().numpy(), ref[0]), rel_l2(tmp.cpu().numpy(), ref[1])
+                    if not (e2 <= TOL and e1 <= TOL):
+                        bad.append((idir, bcs, type_, e2, e1))
+                else:
+                    e = rel_l2(res.cpu().numpy(), ref)
+                    if not e <= TOL:
+                        bad.append((idir, bcs, type_, e))
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_opr_burgers(cuda, case):
+    import torch
+    from oracle import operators as O
+    from tlab_b200 import opr
+    nx, ny, nz, ykind, xper, zper = case
+    grids, go, gg = _plans(nx, ny, nz, ykind, xper, zper)
+    visc, schmidt = 1.0 / 5000.0, [1.0, 0.7]
+    B = O.Burgers(go, visc, schmidt)
+    opr.OPR_Burgers_Initialize(gg, visc, schmidt)
+    s_np = smooth_field((nz, ny, nx), grids, seed=1)
+    v_np = smooth_field((nz, ny, nx), grids, seed=2)
+    s, v = torch.from_numpy(s_np).to(cuda), torch.from_numpy(v_np).to(cuda)
+    fns = [opr.OPR_Burgers_X, opr.OPR_Burgers_Y, opr.OPR_Burgers_Z]
+    bcs = [[0, 0], [0, 0]]
+    for idir in range(3):
+        for is_ in range(3):
+            res = torch.full_like(s, float("nan"))
+            fns[idir](opr.OPR_B_U_IN, is_, nx, ny, nz, bcs, s, v, res)
+            e = rel_l2(res.cpu().numpy(), B.apply(idir, is_, bcs, s_np, v_np))
+            assert e <= TOL, ("u_in", idir, is_, e)
+        res = torch.full_like(s, float("nan"))
+        fns[idir](opr.OPR_B_SELF, 0, nx, ny, nz, bcs, s, s, res)
+        e = rel_l2(res.cpu().numpy(), B.apply(idir, 0, bcs, s_np, s_np))
+        assert e <= TOL, ("self", idir, e)
+        # the reference's own consistency check (src/valid/burgers/vburgers.f90:76-153)
+        d2 = torch.empty_like(s)
+        d1 = torch.empty_like(s)
+        [opr.OPR_Partial_X, opr.OPR_Partial_Y, opr.OPR_Partial_Z][idir](opr.OPR_P2_P1, nx, ny, nz, bcs, gg[idir], s, d2, d1)
+        ident = (visc * d2 - s * d1).cpu().numpy()
+        assert rel_l2(res.cpu().numpy(), ident) <= 1e-11
+
+
+def test_boundary_bcs_neumann_y(cuda):
+    import torch
+    from oracle import operators as O
+    from tlab_b200 import opr
+    nx, ny, nz = 40, 37, 24
+    grids, go, gg = _plans(nx, ny, nz, "tanh")
+    a = smooth_field((nz, ny, nx), grids, seed=5)
+    u = torch.from_numpy(a).to(cuda)
+    for ibc in (1, 2, 3):
+        hb = torch.full((nz, nx), float("nan"), dtype=torch.float64, device=cuda)
+        ht = torch.full((nz, nx), float("nan"), dtype=torch.float64, device=cuda)
+        opr.BOUNDARY_BCS_NEUMANN_Y(ibc, nx, ny, nz, gg[1], u, hb, ht)
+        rb, rt = O.boundary_bcs_neumann_y(ibc, go[1], a)
+        if ibc in (1, 3):
+            assert rel_l2(hb.cpu().numpy(), rb) <= TOL
+        if ibc in (2, 3):
+            assert rel_l2(ht.cpu().numpy(), rt) <= TOL
+
+
+def test_fdm_solve_lines_first(cuda):
+    """FDM_Der1_Solve / FDM_Der2_Solve on the (nlines, n) view, as src/valid/fdm/vpartial.f90 drives them."""
+    import torch
+    from oracle import fdm
+    from tlab_b200 import opr
+    n, nlines = 256, 6
+    y = grid_tanh(n)
+    go = fdm.Plan(y, False, False)
+    gg = opr.FdmPlan(y, False, False, name="y")
+    rng = np.random.default_rng(7)
+    u_np = np.exp(-((y[:, None] - 0.5) / 0.1) ** 2) * rng.uniform(0.5, 1.5, (1, nlines))   # (n, nlines)
+    u = torch.from_numpy(np.ascontiguousarray(u_np)).to(cuda)
+    for ibc in range(4):
+        r = torch.empty_like(u)
+        opr.FDM_Der1_Solve(nlines, ibc, gg, u, r)
+        assert rel_l2(r.cpu().numpy(), fdm.der1_solve(ibc, go.der1, go.der1.lu, u_np)) <= TOL
+    r = torch.empty_like(u)
+    opr.FDM_Der2_Solve(nlines, gg, u, r)
+    d1 = fdm.der1_solve(0, go.der1, go.der1.lu, u_np)
+    assert rel_l2(r.cpu().numpy(), fdm.der2_solve(go.der2, go.der2.lu, u_np, d1)) <= TOL

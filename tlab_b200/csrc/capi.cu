@@ -1,0 +1,375 @@
+// C ABI: runtime, plans and the directional operators (see include/tlab_gpu.h).
+#include "../../include/tlab_gpu.h"
+#include "context.h"
+#include <cstring>
+#include <cstdio>
+#include <vector>
+
+namespace tlab {
+
+Context& ctx() {
+    static Context c;
+    return c;
+}
+
+int fail(int code, const std::string& msg) {
+    ctx().last_error = msg;
+    return code;
+}
+
+int cuda_check(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return 0;
+    return fail(TLAB_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+int finish() {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_check(e, "kernel launch");
+    if (!ctx().async) return cuda_check(cudaStreamSynchronize(ctx().stream), "stream synchronize");
+    return 0;
+}
+
+static int need_ready() {
+    if (!ctx().ready) {
+        int rc = tlab_gpu_init(-1);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static void fill_common(LineArgs& a, const DevPlan& p) {
+    a.n = p.n; a.T = p.T; a.cbase = p.cbase; a.crem = p.crem;
+    a.rhs_d1 = p.rhs_d1;
+    a.rhs2 = p.rhs2;
+}
+
+static void set_geometry(LineArgs& a, int dir, int nx, int ny, int nz, bool& contig) {
+    contig = false;
+    if (dir == 1) {
+        contig = true;
+        a.nlines = (long long)ny * nz; a.stride = 1; a.inner = 1; a.outer_stride = nx;
+    } else if (dir == 2) {
+        a.nlines = (long long)nx * nz; a.stride = nx; a.inner = nx; a.outer_stride = (long long)nx * ny;
+    } else {
+        a.nlines = (long long)nx * ny; a.stride = (long long)nx * ny; a.inner = a.nlines; a.outer_stride = 0;
+    }
+    a.L = pick_lines_per_cta(a.T, contig, contig ? ctx().tune_lines_x : ctx().tune_lines_yz);
+    while (a.L > 1 && a.L * a.T > 512) a.L >>= 1;
+    a.xstride = contig ? xtile_stride(a.n, a.L) : 0;
+}
+
+static int check_dims(int dir, int nx, int ny, int nz, const tlab_plan_s* g) {
+    const int n = (dir == 1) ? nx : (dir == 2 ? ny : nz);
+    if (!g) return fail(TLAB_ERR_OPTION, "null plan");
+    if (dir < 1 || dir > 3) return fail(TLAB_ERR_OPTION, "direction must be 1, 2 or 3");
+    if (g->p.n != n) return fail(TLAB_ERR_DIMGRID, "plan size does not match the field extent along this direction");
+    if (nx < 1 || ny < 1 || nz < 1) return fail(TLAB_ERR_DIMGRID, "non-positive extent");
+    if (n > 1 && g->p.T > 512) return fail(TLAB_ERR_DIMGRID, "line longer than 8192 points");
+    return 0;
+}
+
+int run_partial(int dir, int type, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* u, double* result,
+                double* tmp1) {
+    int rc = check_dims(dir, nx, ny, nz, g);
+    if (rc) return rc;
+    const size_t bytes = (size_t)nx * ny * nz * sizeof(double);
+    cudaStream_t st = ctx().stream;
+    if (type != TLAB_OPR_P1 && type != TLAB_OPR_P2 && type != TLAB_OPR_P2_P1)
+        return fail(TLAB_ERR_UNDEVELOP, "OPR_Partial: only OPR_P1, OPR_P2, OPR_P2_P1 are implemented");
+    if (type == TLAB_OPR_P2_P1 && !tmp1) return fail(TLAB_ERR_OPTION, "OPR_P2_P1 needs tmp1");
+    if (g->p.n == 1) {       // 2-D case: derivative set to zero (opr_partial.f90:174-177, 287-289)
+        cudaMemsetAsync(result, 0, bytes, st);
+        if (type == TLAB_OPR_P2_P1) cudaMemsetAsync(tmp1, 0, bytes, st);
+        return 0;
+    }
+    if (ibc < 0 || ibc > 3) return fail(TLAB_ERR_OPTION, "bcs codes must be 0 or 1");
+    const DevPlan& p = g->p;
+    LineArgs a;
+    fill_common(a, p);
+    bool contig;
+    set_geometry(a, dir, nx, ny, nz, contig);
+    a.u = u; a.out1 = result; a.out2 = tmp1;
+    a.rhs1 = p.rhs1[ibc];
+    a.lu1 = p.lu1[ibc];
+    a.lu2 = p.lu2[0];
+    const int mode = (type == TLAB_OPR_P1) ? MODE_P1 : (type == TLAB_OPR_P2 ? MODE_P2 : MODE_P2_P1);
+    return cuda_check(launch_lines(mode, a, p.periodic, p.need_1der, contig, st), "line kernel");
+}
+
+int run_burgers(int dir, int is, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* s, const double* vel,
+                double* result, int accumulate) {
+    int rc = check_dims(dir, nx, ny, nz, g);
+    if (rc) return rc;
+    cudaStream_t st = ctx().stream;
+    if (g->p.n == 1) {       // opr_burgers.f90:207-210
+        if (!accumulate) cudaMemsetAsync(result, 0, (size_t)nx * ny * nz * sizeof(double), st);
+        return 0;
+    }
+    if (g->burgers_first < 0) return fail(TLAB_ERR_OPTION, "tlab_opr_burgers_init has not been called for this plan");
+    if (is < 0 || is >= g->burgers_count) return fail(TLAB_ERR_OPTION, "scalar index out of range");
+    if (ibc < 0 || ibc > 3) return fail(TLAB_ERR_OPTION, "bcs codes must be 0 or 1");
+    const DevPlan& p = g->p;
+    LineArgs a;
+    fill_common(a, p);
+    bool contig;
+    set_geometry(a, dir, nx, ny, nz, contig);
+    a.u = s; a.vel = vel; a.out1 = result; a.accumulate = accumulate;
+    a.rhs1 = p.rhs1[ibc];
+    a.lu1 = p.lu1[ibc];
+    a.lu2 = p.lu2[g->burgers_first + is];
+    return cuda_check(launch_lines(MODE_BURGERS, a, p.periodic, p.need_1der, contig, st), "burgers kernel");
+}
+
+int run_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_s* g, const double* u, double* hb, double* ht) {
+    int rc = check_dims(2, nx, ny, nz, g);
+    if (rc) return rc;
+    cudaStream_t st = ctx().stream;
+    const size_t pb = (size_t)nx * nz * sizeof(double);
+    if (g->p.n == 1) {       // boundary_bcs.f90:390-391
+        cudaMemsetAsync(hb, 0, pb, st);
+        cudaMemsetAsync(ht, 0, pb, st);
+        return 0;
+    }
+    if (g->p.periodic) return fail(TLAB_ERR_OPTION, "Neumann boundary values need a non-periodic direction");
+    if (ibc < 1 || ibc > 3) return fail(TLAB_ERR_OPTION, "ibc must be 1, 2 or 3");
+    const DevPlan& p = g->p;
+    LineArgs a;
+    fill_common(a, p);
+    bool contig;
+    set_geometry(a, 2, nx, ny, nz, contig);
+    a.u = u;
+    a.rhs1 = p.rhs1[ibc];
+    a.lu1 = p.lu1[ibc];
+    a.lu2 = p.lu2[0];
+    a.bcs_hb = (ibc == BCS_ND || ibc == BCS_NN) ? hb : nullptr;
+    a.bcs_ht = (ibc == BCS_DN || ibc == BCS_NN) ? ht : nullptr;
+    std::memcpy(a.neu_bot, p.neu_bot[ibc], sizeof(a.neu_bot));
+    std::memcpy(a.neu_top, p.neu_top[ibc], sizeof(a.neu_top));
+    a.neu_lu_bot = p.neu_lu_bot[ibc];
+    a.neu_lu_top = p.neu_lu_top[ibc];
+    return cuda_check(launch_lines(MODE_NEUMANN, a, false, false, false, st), "neumann kernel");
+}
+
+}  // namespace tlab
+
+using namespace tlab;
+
+extern "C" {
+
+int tlab_gpu_init(int device) {
+    Context& c = ctx();
+    if (c.ready) return 0;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(TLAB_ERR_CUDA, "no CUDA device available: this library has no CPU fallback");
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) device = 0;
+    }
+    if (int rc = cuda_check(cudaSetDevice(device), "cudaSetDevice")) return rc;
+    c.device = device;
+    if (int rc = cuda_check(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking), "cudaStreamCreate")) return rc;
+    c.ready = true;
+    return 0;
+}
+
+int tlab_gpu_finalize(void) {
+    Context& c = ctx();
+    if (!c.ready) return 0;
+    cudaStreamSynchronize(c.stream);
+    cudaStreamDestroy(c.stream);
+    c.stream = nullptr;
+    c.ready = false;
+    return 0;
+}
+
+const char* tlab_gpu_last_error(void) { return ctx().last_error.c_str(); }
+
+int tlab_gpu_set_async(int on) { ctx().async = (on != 0); return 0; }
+
+int tlab_gpu_synchronize(void) {
+    if (int rc = need_ready()) return rc;
+    return cuda_check(cudaStreamSynchronize(ctx().stream), "synchronize");
+}
+
+int tlab_gpu_malloc(void** ptr, size_t bytes) {
+    if (int rc = need_ready()) return rc;
+    cudaError_t e = cudaMalloc(ptr, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(TLAB_ERR_ALLOC, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    return 0;
+}
+
+int tlab_gpu_free(void* ptr) { return cuda_check(cudaFree(ptr), "cudaFree"); }
+
+int tlab_gpu_upload(void* dst, const void* src, size_t bytes) {
+    if (int rc = need_ready()) return rc;
+    if (int rc = cuda_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx().stream), "upload")) return rc;
+    return cuda_check(cudaStreamSynchronize(ctx().stream), "upload");
+}
+
+int tlab_gpu_download(void* dst, const void* src, size_t bytes) {
+    if (int rc = need_ready()) return rc;
+    if (int rc = cuda_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx().stream), "download")) return rc;
+    return cuda_check(cudaStreamSynchronize(ctx().stream), "download");
+}
+
+int tlab_gpu_set_tuning(const char* key, int value) {
+    if (!key) return fail(TLAB_ERR_OPTION, "null key");
+    if (!std::strcmp(key, "lines_x")) ctx().tune_lines_x = value;
+    else if (!std::strcmp(key, "lines_yz")) ctx().tune_lines_yz = value;
+    else return fail(TLAB_ERR_OPTION, std::string("unknown tuning key ") + key);
+    return 0;
+}
+
+static int plan_create(int dir, int n, const double* nodes, int periodic, int uniform, int mode1, int mode2,
+                       tlab_plan_t* out, bool device) {
+    if (device) { if (int rc = need_ready()) return rc; }
+    if (!out || !nodes || n < 1) return fail(TLAB_ERR_OPTION, "tlab_fdm_plan_create: bad arguments");
+    if (n > 1 && n < 16) return fail(TLAB_ERR_DIMGRID, "a direction needs 1 or at least 16 grid points");
+    tlab_plan_s* g = new tlab_plan_s();
+    g->dir = dir;
+    int rc = create_plan(nodes, n, periodic != 0, uniform != 0, mode1, mode2, g->p.h);
+    if (rc) {
+        delete g;
+        return fail(rc, rc == 85 ? "grid must be uniform in a periodic direction"
+                                 : (rc == 104 ? "finite-difference scheme not implemented on the GPU path" : "plan creation failed"));
+    }
+    g->p.n = n;
+    if (device) {
+        rc = devplan_build(g->p);
+        if (rc) { devplan_free(g->p); delete g; return fail(rc, "device plan upload failed"); }
+    }
+    *out = g;
+    return 0;
+}
+
+int tlab_fdm_plan_create(int dir, int n, const double* nodes, int periodic, int uniform, int mode1, int mode2,
+                         tlab_plan_t* out) {
+    return plan_create(dir, n, nodes, periodic, uniform, mode1, mode2, out, true);
+}
+
+int tlab_fdm_plan_create_host(int dir, int n, const double* nodes, int periodic, int uniform, int mode1, int mode2,
+                              tlab_plan_t* out) {
+    return plan_create(dir, n, nodes, periodic, uniform, mode1, mode2, out, false);
+}
+
+int tlab_fdm_plan_destroy(tlab_plan_t g) {
+    if (!g) return 0;
+    for (int i = 0; i < 3; i++) if (ctx().burgers_plans[i] == g) ctx().burgers_plans[i] = nullptr;
+    devplan_free(g->p);
+    delete g;
+    return 0;
+}
+
+static int copy_mat(const Mat& m, int c0, int c1, double* out, int cap, int* count) {
+    const int nr = m.nrow(), nc = c1 - c0 + 1;
+    if (count) *count = nr * nc;
+    if (cap < nr * nc) return fail(TLAB_ERR_ALLOC, "output buffer too small");
+    for (int j = 0; j < nc; j++) for (int i = 0; i < nr; i++) out[(size_t)j * nr + i] = m(m.r0 + i, c0 + j);
+    return 0;
+}
+
+static int copy_vec(const std::vector<double>& v, double* out, int cap, int* count) {
+    if (count) *count = (int)v.size();
+    if (cap < (int)v.size()) return fail(TLAB_ERR_ALLOC, "output buffer too small");
+    std::copy(v.begin(), v.end(), out);
+    return 0;
+}
+
+int tlab_fdm_plan_get(tlab_plan_t g, const char* what, double* out, int cap, int* count) {
+    if (!g || !what || !out) return fail(TLAB_ERR_OPTION, "tlab_fdm_plan_get: bad arguments");
+    const HostPlan& h = g->p.h;
+    const std::string w(what);
+    if (w == "nodes") return copy_vec(h.nodes, out, cap, count);
+    if (w == "mwn1") return copy_vec(h.der1.mwn, out, cap, count);
+    if (w == "mwn2") return copy_vec(h.der2.mwn, out, cap, count);
+    if (w == "jac1") return copy_mat(h.jac, 1, 1, out, cap, count);
+    if (w == "jac2") return copy_mat(h.jac, 2, 2, out, cap, count);
+    if (w == "jac3") return copy_mat(h.jac, 3, 3, out, cap, count);
+    if (h.size <= 1) return fail(TLAB_ERR_OPTION, "plan of size 1 has no tables");
+    if (w == "lhs1") return copy_mat(h.der1.lhs, 1, h.der1.ndl, out, cap, count);
+    if (w == "rhs1") return copy_mat(h.der1.rhs, 1, h.der1.ndr, out, cap, count);
+    if (w == "lu1") return copy_mat(h.der1.lu, h.der1.lu.c0, h.der1.lu.c1, out, cap, count);
+    if (w == "rhs1_b") return copy_mat(h.der1.rhs_b, 0, 7, out, cap, count);
+    if (w == "rhs1_t") return copy_mat(h.der1.rhs_t, 1, 7, out, cap, count);
+    if (w == "lhs2") return copy_mat(h.der2.lhs, 1, h.der2.ndl, out, cap, count);
+    if (w == "rhs2") return copy_mat(h.der2.rhs, 1, h.der2.ndr + h.der2.ndl, out, cap, count);
+    if (w == "lu2") return copy_mat(h.der2.lu, h.der2.lu.c0, h.der2.lu.c1, out, cap, count);
+    return fail(TLAB_ERR_OPTION, "tlab_fdm_plan_get: unknown table " + w);
+}
+
+int tlab_opr_partial(int dir, int type, int nx, int ny, int nz, const int bcs[4], tlab_plan_t g, const double* u,
+                     double* result, double* tmp1) {
+    if (int rc = need_ready()) return rc;
+    if (!bcs || !u || !result) return fail(TLAB_ERR_OPTION, "OPR_Partial: null argument");
+    if (u == result || (tmp1 && (tmp1 == u || tmp1 == result)))
+        return fail(TLAB_ERR_OPTION, "OPR_Partial: u, result and tmp1 must not alias");
+    const int ibc = bcs[0] + bcs[1] * 2;       // opr_partial.f90:91
+    if (int rc = run_partial(dir, type, nx, ny, nz, ibc, g, u, result, tmp1)) return rc;
+    return finish();
+}
+
+int tlab_opr_burgers_init(tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz, double visc, int nscal, const double* schmidt) {
+    if (int rc = need_ready()) return rc;
+    if (nscal < 0 || (nscal > 0 && !schmidt)) return fail(TLAB_ERR_OPTION, "OPR_Burgers_Initialize: bad scalar list");
+    tlab_plan_s* gs[3] = {gx, gy, gz};
+    for (int ig = 0; ig < 3; ig++) {
+        tlab_plan_s* g = gs[ig];
+        ctx().burgers_plans[ig] = g;
+        if (!g) continue;
+        if (g->p.n <= 1) { g->burgers_first = 0; g->burgers_count = nscal + 1; continue; }
+        if (g->p.h.der2.ndl != 3) return fail(TLAB_ERR_OPTION, "Burgers: more than 3 LHS diagonals in the second derivative");
+        g->burgers_first = (int)g->p.lu2.size();
+        g->burgers_count = nscal + 1;
+        for (int is = 0; is <= nscal; is++) {
+            const double d = (is == 0) ? visc : visc / schmidt[is - 1];
+            devplan_add_diffusion(g->p, d);
+        }
+    }
+    return cuda_check(cudaGetLastError(), "burgers init");
+}
+
+int tlab_opr_burgers(int dir, int ivel, int is, int nx, int ny, int nz, const int bcs[4], const double* s, const double* u,
+                     double* result, double* tmp1, const double* u_t) {
+    (void)tmp1; (void)u_t;
+    if (int rc = need_ready()) return rc;
+    if (!bcs || !s || !result) return fail(TLAB_ERR_OPTION, "OPR_Burgers: null argument");
+    if (bcs[2] + bcs[3] > 0) return fail(TLAB_ERR_UNDEVELOP, "OPR_Burgers: only developed for biased BCs");  // opr_burgers.f90:460-463
+    if (dir < 1 || dir > 3) return fail(TLAB_ERR_OPTION, "direction must be 1, 2 or 3");
+    tlab_plan_s* g = ctx().burgers_plans[dir - 1];
+    if (!g) return fail(TLAB_ERR_OPTION, "tlab_opr_burgers_init has not been called");
+    const double* vel = (ivel == TLAB_OPR_B_SELF) ? s : u;
+    if (!vel) return fail(TLAB_ERR_OPTION, "OPR_Burgers: velocity missing");
+    if (result == s || result == vel) return fail(TLAB_ERR_OPTION, "OPR_Burgers: result must not alias the inputs");
+    const int ibc = bcs[0] + bcs[1] * 2;
+    if (int rc = run_burgers(dir, is, nx, ny, nz, ibc, g, s, vel, result, 0)) return rc;
+    return finish();
+}
+
+int tlab_fdm_der1_solve(tlab_plan_t g, int nlines, int ibc, const double* u, double* result) {
+    if (int rc = need_ready()) return rc;
+    if (!g || !u || !result || nlines < 1) return fail(TLAB_ERR_OPTION, "FDM_Der1_Solve: bad arguments");
+    // u(nlines, n): the derivative direction is the slow index -> same access pattern as a z-derivative
+    if (int rc = run_partial(3, TLAB_OPR_P1, nlines, 1, g->p.n, ibc, g, u, result, nullptr)) return rc;
+    return finish();
+}
+
+int tlab_fdm_der2_solve(tlab_plan_t g, int nlines, int is, const double* u, const double* du, double* result) {
+    (void)du;   // the first derivative needed on non-uniform grids is recomputed in registers
+    if (int rc = need_ready()) return rc;
+    if (!g || !u || !result || nlines < 1) return fail(TLAB_ERR_OPTION, "FDM_Der2_Solve: bad arguments");
+    if (is < 0) {
+        if (int rc = run_partial(3, TLAB_OPR_P2, nlines, 1, g->p.n, 0, g, u, result, nullptr)) return rc;
+        return finish();
+    }
+    return fail(TLAB_ERR_UNDEVELOP, "FDM_Der2_Solve with a diffusivity-scaled LU is only reachable through OPR_Burgers");
+}
+
+int tlab_boundary_bcs_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_t gy, const double* u, double* hb, double* ht) {
+    if (int rc = need_ready()) return rc;
+    if (!u || !hb || !ht) return fail(TLAB_ERR_OPTION, "BOUNDARY_BCS_NEUMANN_Y: null argument");
+    if (int rc = run_neumann_y(ibc, nx, ny, nz, gy, u, hb, ht)) return rc;
+    return finish();
+}
+
+}  // extern "C"

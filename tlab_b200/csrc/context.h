@@ -1,0 +1,39 @@
+// Library-wide state (one GPU per process, like one MPI rank of the reference).
+#pragma once
+#include "plan.h"
+#include "lines.h"
+#include <string>
+#include <cuda_runtime.h>
+
+struct tlab_plan_s {
+    tlab::DevPlan p;
+    int dir = 0;
+    int burgers_first = -1;   // index in p.lu2 of the is = 0 diffusion-scaled LU (-1: tlab_opr_burgers_init not called)
+    int burgers_count = 0;
+};
+
+namespace tlab {
+
+struct Context {
+    bool ready = false;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool async = false;
+    std::string last_error;
+    int tune_lines_x = 0, tune_lines_yz = 0;
+    tlab_plan_s* burgers_plans[3] = {nullptr, nullptr, nullptr};
+};
+
+Context& ctx();
+int fail(int code, const std::string& msg);
+int cuda_check(cudaError_t e, const char* what);
+int finish();          // synchronise unless async; maps errors
+
+// launch helpers shared by the operator entry points and the RHS driver (all device pointers)
+int run_partial(int dir, int type, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* u, double* result,
+                double* tmp1);
+int run_burgers(int dir, int is, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* s, const double* vel,
+                double* result, int accumulate);
+int run_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_s* g, const double* u, double* hb, double* ht);
+
+}  // namespace tlab

@@ -1,0 +1,513 @@
+// Batched compact-scheme line operators for sm_100a: banded right-hand side + factored tridiagonal
+// solve, fused (first derivative, second derivative, both, or the Burgers operator nu*s'' - u*s')
+// in one pass over the pencil: every data array is read once and written once.
+//
+// Replaces, per call, the reference chain  TLab_Transpose -> g%matmul -> TRIDSS/TRIDPSS -> TLab_Transpose
+// (src/operators/opr_partial.f90:31-377, src/physics/opr_burgers.f90:190-521,
+//  src/fdm/fdm_derivative.f90:218-278,413-459, src/fdm/fdm_matmul.f90, src/utils/linear3.f90:56-150,321-442).
+//
+// Parallel decomposition ("chunked substitution"):  a line of n points is owned by T threads,
+// each holding a chunk of <= CHUNK consecutive points in registers.  Thomas' forward and backward
+// substitutions are first-order linear recurrences  y_i = s_i + m_i y_{i-1};  each thread first runs its
+// chunk with zero inflow, publishes the chunk-end value to shared memory, rebuilds its true inflow from
+// the preceding chunks' ends and their precomputed multiplier products (look-back window W chosen on the
+// host so that the dropped factor is < 2^-80), and then repeats the recurrence with the true inflow --
+// the same operations, in the same order, as the sequential algorithm.
+//
+// Thread mapping: tid = l + L*t, l = line within the CTA tile (fastest, so that a warp touches L
+// consecutive lines x 32/L chunks), t = chunk.  For the y and z directions lines are contiguous in l and
+// global accesses are coalesced directly into registers.  For the x direction (lines contiguous in
+// memory) the tile is staged through padded shared memory.
+#include "lines.h"
+#include <cstdio>
+
+namespace tlab {
+
+namespace {
+
+struct Chunk {
+    int t, T;        // chunk index, chunks per line
+    int s0, cnt;     // first point, number of points
+    int j0;          // register slot of the first point (the last chunk is right-aligned: its end is slot CHUNK-1)
+};
+
+__device__ __forceinline__ Chunk make_chunk(int t, int T, int cbase, int crem) {
+    Chunk c;
+    c.t = t; c.T = T;
+    c.s0 = t * cbase + min(t, crem);
+    c.cnt = cbase + (t < crem ? 1 : 0);
+    c.j0 = (t == T - 1) ? CHUNK - c.cnt : 0;
+    return c;
+}
+
+__device__ __forceinline__ double ldro(const double* p) { return __ldg(p); }
+
+// ------------------------------------------------------------------------------------------------
+// factored tridiagonal solve on register chunks; sm_f / sm_b: [T*L] exchange buffers,
+// sm_p: [T*L], sm_q: [ceil(T/8)*L + L] (periodic only)
+template <bool PER>
+__device__ __forceinline__ void solve_tri(double (&f)[CHUNK], const Chunk& c, const SolveTab& S, int l, int L,
+                                          double* sm_f, double* sm_b, double* sm_p, double* sm_q) {
+    const int base = c.s0 - c.j0;     // coefficient index of register slot j is base + j
+    const int j1 = c.j0 + c.cnt;
+    // ---- forward substitution
+    {
+        double e = 0.0;
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) {
+            if (j >= c.j0 && j < j1) {
+                const double a = ldro(S.alpha + base + j);
+                if (PER) e = f[j] * ldro(S.beta + base + j) + a * e;
+                else e = f[j] + a * e;
+            }
+        }
+        sm_f[c.t * L + l] = e;
+        __syncthreads();
+        double cin = 0.0;
+        for (int k = max(0, c.t - S.Wf); k < c.t; k++) cin = sm_f[k * L + l] + ldro(S.Af + k) * cin;
+        double y = cin;
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) {
+            if (j >= c.j0 && j < j1) {
+                const double a = ldro(S.alpha + base + j);
+                if (PER) y = f[j] * ldro(S.beta + base + j) + a * y;
+                else y = f[j] + a * y;
+                f[j] = y;
+            }
+        }
+    }
+    double xN = 0.0;
+    if (PER) {
+        // ---- rank-one closure of the circulant system: x_N = (y_N - sum d_i y_i) * b_N
+        double part = 0.0;
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++)
+            if (j >= c.j0 && j < j1) part = part + ldro(S.pd + base + j) * f[j];
+        const int T8 = (c.T + 7) >> 3;
+        sm_p[c.t * L + l] = part;
+        if (c.t == c.T - 1) sm_q[T8 * L + l] = f[CHUNK - 1];
+        __syncthreads();
+        if (c.t < T8) {
+            double q = 0.0;
+            for (int k = c.t * 8; k < min(c.T, c.t * 8 + 8); k++) q = q + sm_p[k * L + l];
+            sm_q[c.t * L + l] = q;
+        }
+        __syncthreads();
+        double wrk = 0.0;
+        for (int k = 0; k < T8; k++) wrk = wrk + sm_q[k * L + l];
+        xN = (sm_q[T8 * L + l] - wrk) * S.bN;
+        if (c.t == c.T - 1) f[CHUNK - 1] = xN;
+    }
+    // ---- backward substitution
+    {
+        double e = 0.0;
+#pragma unroll
+        for (int j = CHUNK - 1; j >= 0; j--) {
+            if (j >= c.j0 && j < j1) {
+                const double g = ldro(S.gamma + base + j);
+                if (PER) e = (f[j] + g * e) + ldro(S.pe + base + j) * xN;
+                else e = (f[j] + g * e) * ldro(S.delta + base + j);
+            }
+        }
+        sm_b[c.t * L + l] = e;
+        __syncthreads();
+        double cin = 0.0;
+        for (int k = min(c.T - 1, c.t + S.Wb); k > c.t; k--) cin = sm_b[k * L + l] + ldro(S.Ab + k) * cin;
+        double x = cin;
+#pragma unroll
+        for (int j = CHUNK - 1; j >= 0; j--) {
+            if (j >= c.j0 && j < j1) {
+                const double g = ldro(S.gamma + base + j);
+                if (PER) x = (f[j] + g * x) + ldro(S.pe + base + j) * xN;
+                else x = (f[j] + g * x) * ldro(S.delta + base + j);
+                f[j] = x;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// banded right-hand sides from the chunk + 3-point halo  (u[k] holds point s0 - 3 + (k - j0))
+// The right-hand sides are sums with heavy cancellation (B u = O(h^2 u'')), so they are evaluated with
+// explicitly rounded multiplies and adds in the reference's association order (no FMA contraction):
+// a differently-rounded B u would be amplified by 1/(h k)^2 in the result.
+#define DMUL(a, b) __dmul_rn((a), (b))
+#define DADD(a, b) __dadd_rn((a), (b))
+#define DSUB(a, b) __dsub_rn((a), (b))
+
+template <bool SECOND>
+__device__ __forceinline__ void rhs_interior(const double (&u)[CHUNK + 6], double (&f)[CHUNK], const RhsTab& R) {
+#pragma unroll
+    for (int j = 0; j < CHUNK; j++) {
+        if (SECOND) {
+            // r4*u(n) + u(n+1) + u(n-1) + r6*(u(n+2) + u(n-2)) + r7*(u(n+3) + u(n-3)), fdm_matmul.f90:608-612
+            double s = DADD(DADD(DMUL(R.rc, u[j + 3]), u[j + 4]), u[j + 2]);
+            s = DADD(s, DMUL(R.r2, DADD(u[j + 5], u[j + 1])));
+            if (R.r3 != 0.0) s = DADD(s, DMUL(R.r3, DADD(u[j + 6], u[j])));
+            f[j] = s;
+        } else {
+            // u(n+1) - u(n-1) + r5*(u(n+2) - u(n-2)), fdm_matmul.f90:396-398
+            double s = DSUB(u[j + 4], u[j + 2]);
+            if (R.r2 != 0.0) s = DADD(s, DMUL(R.r2, DSUB(u[j + 5], u[j + 1])));
+            f[j] = s;
+        }
+    }
+}
+
+// special rows at the two ends; wb[k] = u_k (k from the bottom), wt[k] = u_{n-1-k}.  Zero coefficients
+// are skipped so that the sum runs over the same terms, in the same order, as the reference's rows.
+__device__ __forceinline__ void rhs_bottom(const double (&wb)[BROW_W], double (&f)[CHUNK], const RhsTab& R) {
+#pragma unroll
+    for (int i = 0; i < MAX_BROWS; i++) {
+        if (i < R.nb) {
+            double s = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int k = 0; k < BROW_W; k++) {
+                const double cf = R.bot[i][k];
+                if (cf != 0.0) {
+                    const double term = DMUL(cf, wb[k]);
+                    s = first ? term : DADD(s, term);
+                    first = false;
+                }
+            }
+            f[i] = s;
+        }
+    }
+}
+__device__ __forceinline__ void rhs_top(const double (&wt)[BROW_W], double (&f)[CHUNK], const RhsTab& R) {
+#pragma unroll
+    for (int q = 0; q < MAX_BROWS; q++) {
+        if (q < R.nb) {
+            double s = 0.0;
+            bool first = true;
+#pragma unroll
+            for (int k = BROW_W - 1; k >= 0; k--) {      // ascending column order, as the reference
+                const double cf = R.top[q][k];
+                if (cf != 0.0) {
+                    const double term = DMUL(cf, wt[k]);
+                    s = first ? term : DADD(s, term);
+                    first = false;
+                }
+            }
+            f[CHUNK - 1 - q] = s;
+        }
+    }
+}
+
+// Jacobian correction of the second derivative on non-uniform grids:  f2 += A2*jac2 * du  (tridiagonal,
+// extended stencil in the first and last row)
+__device__ __forceinline__ void add_jacobian_term(double (&f2)[CHUNK], const double (&d1)[CHUNK], const Chunk& c,
+                                                  const double* __restrict__ rd1, int n, int l, int L, double* sm_h) {
+    const int j1 = c.j0 + c.cnt;
+    double first = 0.0, last = 0.0;
+#pragma unroll
+    for (int j = 0; j < CHUNK; j++) {
+        if (j == c.j0) first = d1[j];
+        if (j == j1 - 1) last = d1[j];
+    }
+    sm_h[(2 * c.t) * L + l] = first;
+    sm_h[(2 * c.t + 1) * L + l] = last;
+    __syncthreads();
+    const double left = (c.t > 0) ? sm_h[(2 * (c.t - 1) + 1) * L + l] : 0.0;
+    const double right = (c.t < c.T - 1) ? sm_h[(2 * (c.t + 1)) * L + l] : 0.0;
+    const int base = c.s0 - c.j0;
+#pragma unroll
+    for (int j = 0; j < CHUNK; j++) {
+        if (j >= c.j0 && j < j1) {
+            const int i = base + j;
+            double um = (j == c.j0) ? left : d1[j > 0 ? j - 1 : 0];
+            double up = (j == j1 - 1) ? right : d1[j < CHUNK - 1 ? j + 1 : CHUNK - 1];
+            if (i == 0) um = d1[j < CHUNK - 2 ? j + 2 : CHUNK - 1];           // extended stencil, first row
+            if (i == n - 1) up = d1[j > 1 ? j - 2 : 0];                       // extended stencil, last row
+            const double r1 = ldro(rd1 + 3 * i), r2 = ldro(rd1 + 3 * i + 1), r3 = ldro(rd1 + 3 * i + 2);
+            if (i == n - 1) f2[j] = DADD(DADD(DADD(f2[j], DMUL(up, r3)), DMUL(um, r1)), DMUL(d1[j], r2));
+            else f2[j] = DADD(DADD(DADD(f2[j], DMUL(um, r1)), DMUL(d1[j], r2)), DMUL(up, r3));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared-memory exchange area (doubles): [sm_f T*L][sm_b T*L][sm_p T*L][sm_q (T8+1)*L][sm_h 2*T*L]
+__host__ __device__ inline size_t exch_doubles(int T, int L) {
+    return (size_t)T * L * 5 + (size_t)(((T + 7) >> 3) + 1) * L;
+}
+
+template <int MODE, bool PER, bool NEED1>
+__device__ __forceinline__ void line_core(double (&u)[CHUNK + 6], const double (&wb)[BROW_W], const double (&wt)[BROW_W],
+                                          const Chunk& c, const LineArgs& a, int l, int L, double* sm,
+                                          double (&d1)[CHUNK], double (&d2)[CHUNK]) {
+    double* sm_f = sm;
+    double* sm_b = sm_f + c.T * L;
+    double* sm_p = sm_b + c.T * L;
+    double* sm_q = sm_p + c.T * L;
+    double* sm_h = sm_q + (((c.T + 7) >> 3) + 1) * L;
+    constexpr bool WANT1 = (MODE == MODE_P1) || (MODE == MODE_P2_P1) || (MODE == MODE_BURGERS) ||
+                           (MODE == MODE_NEUMANN) || NEED1;
+    constexpr bool WANT2 = (MODE == MODE_P2) || (MODE == MODE_P2_P1) || (MODE == MODE_BURGERS);
+    if (WANT1) {
+        rhs_interior<false>(u, d1, a.rhs1);
+        if (!PER) {
+            if (c.t == 0) rhs_bottom(wb, d1, a.rhs1);
+            if (c.t == c.T - 1) rhs_top(wt, d1, a.rhs1);
+        }
+    }
+    if (WANT2) {
+        rhs_interior<true>(u, d2, a.rhs2);
+        if (!PER) {
+            if (c.t == 0) rhs_bottom(wb, d2, a.rhs2);
+            if (c.t == c.T - 1) rhs_top(wt, d2, a.rhs2);
+        }
+    }
+    if (WANT1) solve_tri<PER>(d1, c, a.lu1, l, L, sm_f, sm_b, sm_p, sm_q);
+    if (WANT2) {
+        if (NEED1) add_jacobian_term(d2, d1, c, a.rhs_d1, a.n, l, L, sm_h);
+        solve_tri<PER>(d2, c, a.lu2, l, L, sm_f, sm_b, sm_p, sm_q);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// y / z directions: lines strided in memory, contiguous across lines
+template <int MODE, bool PER, bool NEED1>
+__global__ void __launch_bounds__(512) line_kernel_strided(LineArgs a) {
+    extern __shared__ double sm[];
+    const int L = a.L;
+    const int l = threadIdx.x % L;
+    const int t = threadIdx.x / L;
+    const Chunk c = make_chunk(t, a.T, a.cbase, a.crem);
+    long long line = (long long)blockIdx.x * L + l;
+    const bool active = line < a.nlines;
+    if (!active) line = a.nlines - 1;
+    const long long lbase = (line / a.inner) * a.outer_stride + (line % a.inner);
+    const double* __restrict__ up = a.u + lbase;
+    const long long st = a.stride;
+    const int n = a.n;
+
+    double u[CHUNK + 6];
+#pragma unroll
+    for (int k = 0; k < CHUNK + 6; k++) {
+        int p = c.s0 - 3 + (k - c.j0);
+        const bool in_win = (k >= c.j0) && (k < c.j0 + c.cnt + 6);
+        if (PER) p = (p < 0) ? p + n : (p >= n ? p - n : p);
+        const bool ok = in_win && p >= 0 && p < n;
+        u[k] = ok ? __ldcs(up + (long long)p * st) : 0.0;
+    }
+    double wb[BROW_W], wt[BROW_W];
+    if (!PER) {
+#pragma unroll
+        for (int k = 0; k < BROW_W; k++) {
+            wb[k] = (c.t == 0) ? u[3 + k] : 0.0;
+            wt[k] = (c.t == c.T - 1) ? u[3 + CHUNK - 1 - k] : 0.0;
+        }
+    }
+    double d1[CHUNK], d2[CHUNK];
+    line_core<MODE, PER, NEED1>(u, wb, wt, c, a, l, L, sm, d1, d2);
+
+    const int j1 = c.j0 + c.cnt;
+    if (MODE == MODE_NEUMANN) {
+        // boundary values such that the normal derivative vanishes (BOUNDARY_BCS_NEUMANN_Y)
+        if (active && c.t == 0 && a.bcs_hb != nullptr) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < BROW_W; k++) s = s + a.neu_bot[k] * wb[k];
+            a.bcs_hb[line] = s + a.neu_lu_bot * d1[1];
+        }
+        if (active && c.t == c.T - 1 && a.bcs_ht != nullptr) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < BROW_W; k++) s = s + a.neu_top[k] * wt[k];
+            a.bcs_ht[line] = s + a.neu_lu_top * d1[CHUNK - 2];
+        }
+        return;
+    }
+    double* __restrict__ o1 = a.out1 + lbase;
+    double* __restrict__ o2 = (MODE == MODE_P2_P1) ? a.out2 + lbase : nullptr;
+    const double* __restrict__ vp = (MODE == MODE_BURGERS) ? a.vel + lbase : nullptr;
+#pragma unroll
+    for (int j = 0; j < CHUNK; j++) {
+        if (active && j >= c.j0 && j < j1) {
+            const long long off = (long long)(c.s0 + j - c.j0) * st;
+            if (MODE == MODE_P1) o1[off] = d1[j];
+            if (MODE == MODE_P2) o1[off] = d2[j];
+            if (MODE == MODE_P2_P1) { o1[off] = d2[j]; o2[off] = d1[j]; }
+            if (MODE == MODE_BURGERS) {
+                const double v = __ldcs(vp + off);
+                double r = d2[j] - v * d1[j];
+                if (a.accumulate) r = o1[off] + r;
+                o1[off] = r;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// x direction: lines contiguous in memory; a tile of L lines is staged through padded shared memory
+__device__ __forceinline__ int xpos(int i) { return i + (i >> 4); }
+
+template <int MODE, bool PER, bool NEED1>
+__global__ void __launch_bounds__(512) line_kernel_contig(LineArgs a) {
+    extern __shared__ double sm[];
+    const int L = a.L;
+    const int l = threadIdx.x % L;
+    const int t = threadIdx.x / L;
+    const int n = a.n;
+    const int S = a.xstride;                       // shared-memory stride between lines
+    const Chunk c = make_chunk(t, a.T, a.cbase, a.crem);
+    const long long line0 = (long long)blockIdx.x * L;
+    const int nl = (int)min((long long)L, a.nlines - line0);
+    double* tile = sm + exch_doubles(a.T, L);
+    double* vtile = tile + (size_t)L * S;
+
+    // cooperative coalesced load of the tile(s)
+    const bool two = (MODE == MODE_BURGERS) && (a.vel != a.u);
+    for (int ll = 0; ll < nl; ll++) {
+        const double* __restrict__ src = a.u + (line0 + ll) * (long long)n;
+        const double* __restrict__ vsrc = two ? a.vel + (line0 + ll) * (long long)n : nullptr;
+        if ((n & 1) == 0) {
+            for (int i = 2 * threadIdx.x; i < n; i += 2 * blockDim.x) {
+                const double2 v = __ldcs(reinterpret_cast<const double2*>(src + i));
+                tile[ll * S + xpos(i)] = v.x;
+                tile[ll * S + xpos(i + 1)] = v.y;
+                if (two) {
+                    const double2 w = __ldcs(reinterpret_cast<const double2*>(vsrc + i));
+                    vtile[ll * S + xpos(i)] = w.x;
+                    vtile[ll * S + xpos(i + 1)] = w.y;
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                tile[ll * S + xpos(i)] = src[i];
+                if (two) vtile[ll * S + xpos(i)] = vsrc[i];
+            }
+        }
+    }
+    __syncthreads();
+
+    const int lr = (l < nl) ? l : 0;               // inactive lines redo line 0 (keeps barriers uniform)
+    const double* row = tile + lr * S;
+    double u[CHUNK + 6];
+#pragma unroll
+    for (int k = 0; k < CHUNK + 6; k++) {
+        int p = c.s0 - 3 + (k - c.j0);
+        const bool in_win = (k >= c.j0) && (k < c.j0 + c.cnt + 6);
+        if (PER) p = (p < 0) ? p + n : (p >= n ? p - n : p);
+        const bool ok = in_win && p >= 0 && p < n;
+        u[k] = ok ? row[xpos(ok ? p : 0)] : 0.0;
+    }
+    double wb[BROW_W], wt[BROW_W];
+    if (!PER) {
+#pragma unroll
+        for (int k = 0; k < BROW_W; k++) {
+            wb[k] = (c.t == 0) ? u[3 + k] : 0.0;
+            wt[k] = (c.t == c.T - 1) ? u[3 + CHUNK - 1 - k] : 0.0;
+        }
+    }
+    double d1[CHUNK], d2[CHUNK];
+    line_core<MODE, PER, NEED1>(u, wb, wt, c, a, l, L, sm, d1, d2);
+    // all halo reads of the tile happened before the first barrier inside line_core; results may overwrite it
+
+    const int j1 = c.j0 + c.cnt;
+    const int npass = (MODE == MODE_P2_P1) ? 2 : 1;
+    for (int pass = 0; pass < npass; pass++) {
+        if (pass == 1) __syncthreads();
+        double* wrow = tile + lr * S;
+        const double* vrow = (two ? vtile : tile) + lr * S;
+        if (l < nl) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) {
+                if (j >= c.j0 && j < j1) {
+                    const int pp = xpos(c.s0 + j - c.j0);
+                    double r;
+                    if (MODE == MODE_P1) r = d1[j];
+                    else if (MODE == MODE_P2) r = d2[j];
+                    else if (MODE == MODE_P2_P1) r = (pass == 0) ? d2[j] : d1[j];
+                    else r = d2[j] - vrow[pp] * d1[j];
+                    wrow[pp] = r;
+                }
+            }
+        }
+        __syncthreads();
+        double* __restrict__ obase = (pass == 0) ? a.out1 : a.out2;
+        for (int ll = 0; ll < nl; ll++) {
+            double* __restrict__ dst = obase + (line0 + ll) * (long long)n;
+            if ((n & 1) == 0) {
+                for (int i = 2 * threadIdx.x; i < n; i += 2 * blockDim.x) {
+                    double2 v;
+                    v.x = tile[ll * S + xpos(i)];
+                    v.y = tile[ll * S + xpos(i + 1)];
+                    if (a.accumulate) {
+                        const double2 o = *reinterpret_cast<const double2*>(dst + i);
+                        v.x = o.x + v.x; v.y = o.y + v.y;
+                    }
+                    *reinterpret_cast<double2*>(dst + i) = v;
+                }
+            } else {
+                for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                    double v = tile[ll * S + xpos(i)];
+                    if (a.accumulate) v = dst[i] + v;
+                    dst[i] = v;
+                }
+            }
+        }
+    }
+}
+
+template <int MODE, bool PER, bool NEED1>
+cudaError_t launch_one(const LineArgs& a, bool contig, cudaStream_t stream) {
+    const int threads = a.L * a.T;
+    const long long blocks = (a.nlines + a.L - 1) / a.L;
+    size_t smem = exch_doubles(a.T, a.L) * sizeof(double);
+    if (contig) {
+        const bool two = (MODE == MODE_BURGERS) && (a.vel != a.u);
+        smem += (size_t)a.L * a.xstride * sizeof(double) * (two ? 2 : 1);
+        auto k = line_kernel_contig<MODE, PER, NEED1>;
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        k<<<(unsigned)blocks, threads, smem, stream>>>(a);
+    } else {
+        auto k = line_kernel_strided<MODE, PER, NEED1>;
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+        }
+        k<<<(unsigned)blocks, threads, smem, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch_mode(const LineArgs& a, bool per, bool need1, bool contig, cudaStream_t s) {
+    if (per) return launch_one<MODE, true, false>(a, contig, s);
+    if (need1) return launch_one<MODE, false, true>(a, contig, s);
+    return launch_one<MODE, false, false>(a, contig, s);
+}
+
+}  // namespace
+
+int pick_lines_per_cta(int T, bool contig, int override_L) {
+    if (override_L > 0) return override_L;
+    // tile = L lines x n points; keep the CTA at <= 512 threads and at least 4 lines (32 B segments)
+    int L = contig ? 4 : 8;
+    while (L > 1 && L * T > 512) L >>= 1;
+    return L;
+}
+
+int xtile_stride(int n, int L) {
+    int S = n + (n >> 4) + 1;
+    const int want = (L >= 16) ? 1 : 16 / L;        // S mod 16 == 16/L makes chunk reads conflict-free
+    while ((S & 15) != (want & 15)) S++;
+    return S;
+}
+
+cudaError_t launch_lines(int mode, const LineArgs& a, bool periodic, bool need1, bool contig, cudaStream_t s) {
+    switch (mode) {
+        case MODE_P1: return launch_mode<MODE_P1>(a, periodic, false, contig, s);
+        case MODE_P2: return launch_mode<MODE_P2>(a, periodic, need1, contig, s);
+        case MODE_P2_P1: return launch_mode<MODE_P2_P1>(a, periodic, need1, contig, s);
+        case MODE_BURGERS: return launch_mode<MODE_BURGERS>(a, periodic, need1, contig, s);
+        case MODE_NEUMANN: return launch_mode<MODE_NEUMANN>(a, periodic, false, false, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tlab

@@ -1,0 +1,210 @@
+// Build the device tables of a plan from the host plan (see plan.h).
+#include "plan.h"
+#include <cmath>
+#include <cstring>
+#include <algorithm>
+
+namespace tlab {
+
+namespace {
+
+const double* upload(DevPlan& p, const std::vector<double>& v) {
+    double* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(double)) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice);
+    p.allocs.push_back(d);
+    return d;
+}
+
+int chunk_cnt(const DevPlan& p, int t) { return p.cbase + (t < p.crem ? 1 : 0); }
+
+// smallest look-back window W such that any product of W consecutive chunk multipliers is < 2^-80
+int window(const std::vector<double>& A, bool forward) {
+    const int T = (int)A.size();
+    const double tiny = std::ldexp(1.0, -80);
+    for (int W = 1; W < T; W++) {
+        bool ok = true;
+        for (int t = 0; t < T && ok; t++) {
+            // chunks feeding chunk t: forward t-W..t-1, backward t+1..t+W; only complete windows matter
+            int lo = forward ? t - W : t + 1, hi = forward ? t - 1 : t + W;
+            if (lo < 0 || hi > T - 1) continue;     // window reaches the end of the line: nothing is dropped
+            double prod = 1.0;
+            for (int k = lo; k <= hi; k++) prod *= std::fabs(A[k]);
+            if (!(prod < tiny)) ok = false;
+        }
+        if (ok) return W;
+    }
+    return std::max(T - 1, 0);
+}
+
+void finish_solve(DevPlan& p, SolveTab& s, std::vector<double>& alpha, std::vector<double>& beta,
+                  std::vector<double>& gamma, std::vector<double>& delta, std::vector<double>& pd,
+                  std::vector<double>& pe, bool periodic) {
+    const int T = p.T;
+    std::vector<double> Af(T, 1.0), Ab(T, 1.0);
+    for (int t = 0; t < T; t++) {
+        int s0 = chunk_start(p, t), c = chunk_cnt(p, t);
+        for (int j = 0; j < c; j++) {
+            Af[t] *= alpha[s0 + j];
+            Ab[t] *= periodic ? gamma[s0 + j] : gamma[s0 + j] * delta[s0 + j];
+        }
+    }
+    s.Wf = window(Af, true);
+    s.Wb = window(Ab, false);
+    s.alpha = upload(p, alpha);
+    s.gamma = upload(p, gamma);
+    s.Af = upload(p, Af);
+    s.Ab = upload(p, Ab);
+    if (periodic) {
+        s.beta = upload(p, beta);
+        s.pd = upload(p, pd);
+        s.pe = upload(p, pe);
+    } else {
+        s.delta = upload(p, delta);
+    }
+}
+
+// lu columns c0+1..c0+3 (c0+1..c0+5 periodic); rows nmin..nmax active; scale = diffusivity (1 = none)
+void make_solve(DevPlan& p, SolveTab& s, const Mat& lu, int c0, int nmin, int nmax, bool periodic, double diff,
+                bool scaled) {
+    const int n = p.n;
+    std::vector<double> alpha(n, 0.0), beta(n, 1.0), gamma(n, 0.0), delta(n, 1.0), pd(n, 0.0), pe(n, 0.0);
+    if (periodic) {
+        for (int r = 1; r <= n; r++) {
+            const int i = r - 1;
+            double a = lu(r, 1), b = lu(r, 2), c = lu(r, 3), d = lu(r, 4), e = lu(r, 5);
+            if (scaled) { b = b * diff; d = d / diff; }
+            if (r >= 2 && r <= n - 1) alpha[i] = a;
+            if (r <= n - 1) { beta[i] = b; pd[i] = d; pe[i] = e; }
+            if (r <= n - 2) gamma[i] = c;
+            if (r == n) s.bN = b;
+        }
+    } else {
+        for (int r = 1; r <= n; r++) {
+            const int i = r - 1;
+            if (r < nmin || r > nmax) continue;
+            double a = lu(r, c0 + 1), b = lu(r, c0 + 2), c = lu(r, c0 + 3);
+            if (scaled) { b = b * diff; c = c / diff; }
+            if (r > nmin) alpha[i] = a;
+            if (r < nmax) gamma[i] = c;
+            delta[i] = b;
+        }
+    }
+    finish_solve(p, s, alpha, beta, gamma, delta, pd, pe, periodic);
+}
+
+// special rows of the banded right-hand side, densified
+void make_rhs(const HostDer& g, bool second, int ibc, RhsTab& R) {
+    std::memset(&R, 0, sizeof(R));
+    const int n = g.size, ndr = g.ndr, idr = ndr / 2 + 1;
+    const int nb = second ? idr - 1 : idr;
+    const int ref = nb + 1;
+    R.rc = second ? g.rhs(ref, idr) : 0.0;
+    R.r2 = (ndr >= 5) ? g.rhs(ref, idr + 2) : 0.0;
+    R.r3 = (ndr >= 7) ? g.rhs(ref, idr + 3) : 0.0;
+    if (g.periodic) { R.nb = 0; return; }
+    R.nb = nb;
+    const bool neu_min = !second && (ibc == BCS_ND || ibc == BCS_NN);
+    const bool neu_max = !second && (ibc == BCS_DN || ibc == BCS_NN);
+    for (int i = 1; i <= nb; i++) {
+        if (neu_min) {
+            if (i == 1) continue;
+            for (int j = 0; j <= ndr; j++) { int col = i + j - idr; if (col >= 2 && col <= BROW_W) R.bot[i - 1][col - 1] += g.rhs_b(i, j); }
+        } else {
+            for (int j = 1; j <= ndr; j++) { int col = i + j - idr; if (col >= 1 && col <= BROW_W) R.bot[i - 1][col - 1] += g.rhs(i, j); }
+            if (i == 1) R.bot[0][idr] += g.rhs(1, 1);
+        }
+    }
+    for (int q = 0; q < nb; q++) {
+        const int i = n - q;
+        if (neu_max) {
+            if (q == 0) continue;
+            const int tr = idr - q;
+            for (int j = 1; j <= ndr; j++) { int col = i + j - idr; int k = n - col; if (k >= 1 && k < BROW_W) R.top[q][k] += g.rhs_t(tr, j); }
+        } else {
+            for (int j = 1; j <= ndr; j++) { int col = i + j - idr; int k = n - col; if (k >= 0 && k < BROW_W) R.top[q][k] += g.rhs(i, j); }
+            if (q == 0) R.top[0][idr] += g.rhs(n, ndr);
+        }
+    }
+}
+
+}  // namespace
+
+int devplan_build(DevPlan& p) {
+    const HostPlan& h = p.h;
+    p.n = h.size;
+    p.periodic = h.periodic;
+    if (p.n <= 1) { p.T = 1; p.cbase = 1; p.crem = 0; return 0; }
+    p.need_1der = h.der2.need_1der;
+    p.T = (p.n + CHUNK - 1) / CHUNK;
+    p.cbase = p.n / p.T;
+    p.crem = p.n % p.T;
+    const int n = p.n;
+    // first derivative
+    if (h.periodic) {
+        make_rhs(h.der1, false, BCS_PERIODIC, p.rhs1[0]);
+        make_solve(p, p.lu1[0], h.der1.lu, 0, 1, n, true, 1.0, false);
+        for (int b = 1; b < 4; b++) { p.rhs1[b] = p.rhs1[0]; p.lu1[b] = p.lu1[0]; }
+    } else {
+        for (int ibc = 0; ibc < 4; ibc++) {
+            make_rhs(h.der1, false, ibc, p.rhs1[ibc]);
+            int nmin = 1, nmax = n;
+            if (ibc == BCS_ND || ibc == BCS_NN) nmin++;
+            if (ibc == BCS_DN || ibc == BCS_NN) nmax--;
+            make_solve(p, p.lu1[ibc], h.der1.lu, ibc * 5, nmin, nmax, false, 1.0, false);
+        }
+    }
+    // second derivative
+    make_rhs(h.der2, true, BCS_DD, p.rhs2);
+    p.lu2.clear();
+    p.lu2.emplace_back();
+    make_solve(p, p.lu2[0], h.der2.lu, 0, 1, n, h.periodic, 1.0, false);
+    if (p.need_1der) {
+        std::vector<double> r(3 * (size_t)n);
+        for (int i = 1; i <= n; i++) for (int j = 1; j <= 3; j++) r[3 * (size_t)(i - 1) + (j - 1)] = h.der2.rhs(i, h.der2.ndr + j);
+        p.rhs_d1 = upload(p, r);
+    }
+    {
+        std::vector<double> j1(n);
+        for (int i = 1; i <= n; i++) j1[i - 1] = h.jac(i, 1);
+        p.d_jac = upload(p, j1);
+        p.d_mwn1 = upload(p, h.der1.mwn);
+    }
+    // Neumann boundary-value closures
+    std::memset(p.neu_bot, 0, sizeof(p.neu_bot));
+    std::memset(p.neu_top, 0, sizeof(p.neu_top));
+    std::memset(p.neu_lu_bot, 0, sizeof(p.neu_lu_bot));
+    std::memset(p.neu_lu_top, 0, sizeof(p.neu_lu_top));
+    if (!h.periodic) {
+        const HostDer& g = h.der1;
+        const int ndr = g.ndr, idr = ndr / 2 + 1;
+        for (int ibc = 1; ibc < 4; ibc++) {
+            const int ip = ibc * 5;
+            if (ibc == BCS_ND || ibc == BCS_NN) {
+                for (int j = idr + 1; j <= ndr; j++) p.neu_bot[ibc][j - idr] += g.rhs_b(1, j);   // col 1+j-idr, 0-based k = j-idr
+                p.neu_bot[ibc][idr] += g.rhs_b(1, 1);                                            // extended stencil, col idr+1
+                p.neu_lu_bot[ibc] = g.lu(1, ip + 3);
+            }
+            if (ibc == BCS_DN || ibc == BCS_NN) {
+                for (int j = 1; j <= idr - 1; j++) p.neu_top[ibc][idr - j] += g.rhs_t(idr, j);  // col n+j-idr, k = idr-j
+                p.neu_top[ibc][idr] += g.rhs_t(idr, ndr);                                        // extended stencil, col n-idr
+                p.neu_lu_top[ibc] = g.lu(n, ip + 1);
+            }
+        }
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : 80;
+}
+
+int devplan_add_diffusion(DevPlan& p, double diff) {
+    if (p.n <= 1) return 0;
+    p.lu2.emplace_back();
+    make_solve(p, p.lu2.back(), p.h.der2.lu, 0, 1, p.n, p.h.periodic, diff, true);
+    return (int)p.lu2.size() - 1;
+}
+
+void devplan_free(DevPlan& p) {
+    for (void* a : p.allocs) cudaFree(a);
+    p.allocs.clear();
+}
+
+}  // namespace tlab

@@ -1,0 +1,67 @@
+// Device-side plan: the tables the line kernels read (uploaded once per plan).
+#pragma once
+#include "fdm_host.h"
+#include <cuda_runtime.h>
+#include <vector>
+#include <map>
+
+namespace tlab {
+
+constexpr int CHUNK = 16;        // points of one line owned by one thread (register-resident)
+constexpr int MAX_BROWS = 4;     // special rows at each end of a banded right-hand side
+constexpr int BROW_W = 8;        // columns a special row may touch (counted from the wall)
+
+// One LU-factored tridiagonal system, rewritten as two first-order linear recurrences
+//   forward : y_i = f_i * beta_i + alpha_i * y_{i-1}
+//   backward: x_i = (y_i + gamma_i * x_{i+1} [+ pe_i * x_N]) * delta_i
+// plus, for circulant systems, the rank-one closure x_N = (y_N - sum_i pd_i y_i) * bN.
+// Rows excluded by a homogeneous Neumann condition have alpha = gamma = 0 and a zero rhs row.
+struct SolveTab {
+    const double* alpha = nullptr;
+    const double* beta = nullptr;    // periodic only
+    const double* gamma = nullptr;
+    const double* delta = nullptr;   // non-periodic only
+    const double* pd = nullptr;      // periodic only
+    const double* pe = nullptr;      // periodic only
+    const double* Af = nullptr;      // [T] product of alpha over each chunk
+    const double* Ab = nullptr;      // [T] product of gamma*delta over each chunk
+    double bN = 0.0;
+    int Wf = 0, Wb = 0;              // look-back windows (in chunks), see DESIGN.md "chunked substitution"
+};
+
+// banded right-hand side B u: constant interior stencil + dense special rows at the ends
+struct RhsTab {
+    double rc = 0.0;                 // centre coefficient (symmetric stencils; 0 for antisymmetric)
+    double r2 = 0.0, r3 = 0.0;       // 2nd and 3rd off-diagonals (1st off-diagonal is 1 by normalisation)
+    int nb = 0;                      // # of special rows at each end (0: periodic)
+    double bot[MAX_BROWS][BROW_W];   // f_i     = sum_k bot[i][k] * u_k            (i, k 0-based from the bottom)
+    double top[MAX_BROWS][BROW_W];   // f_{n-1-q} = sum_k top[q][k] * u_{n-1-k}     (q, k 0-based from the top)
+};
+
+struct DevPlan {
+    HostPlan h;
+    int n = 0;
+    int T = 1;                       // chunks per line
+    int cbase = 0, crem = 0;         // chunk t starts at t*cbase + min(t, crem), has cbase + (t < crem) points
+    bool periodic = false;
+    bool need_1der = false;
+    RhsTab rhs1[4];                  // first derivative, per ibc (only [0] for periodic)
+    RhsTab rhs2;                     // second derivative
+    SolveTab lu1[4];                 // first derivative LU per ibc
+    std::vector<SolveTab> lu2;       // second derivative LU: [0] plain, [1 + is] scaled by diffusivity is (Burgers)
+    const double* rhs_d1 = nullptr;  // [n][3] Jacobian correction of the second derivative (need_1der)
+    const double* d_mwn1 = nullptr;  // [n] modified wavenumbers of the first derivative (periodic)
+    const double* d_jac = nullptr;   // [n] dx/ds
+    // Neumann boundary-value closure (BOUNDARY_BCS_NEUMANN_Y): value = sum_k bcsrow[k] u_k + lu_coef * du_1
+    double neu_bot[4][BROW_W], neu_top[4][BROW_W];
+    double neu_lu_bot[4], neu_lu_top[4];
+    std::vector<void*> allocs;       // device allocations owned by the plan
+};
+
+int devplan_build(DevPlan& p);                       // upload tables of p.h
+int devplan_add_diffusion(DevPlan& p, double diff);  // append a diffusivity-scaled second-derivative LU; returns index or <0
+void devplan_free(DevPlan& p);
+
+inline int chunk_start(const DevPlan& p, int t) { return t * p.cbase + (t < p.crem ? t : p.crem); }
+
+}  // namespace tlab
