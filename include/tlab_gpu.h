@@ -80,6 +80,12 @@ int tlab_fdm_plan_destroy(tlab_plan_t plan);
  * | "rhs1_b" | "rhs1_t"; matrices are returned column-major (Fortran order); *count receives the length. */
 int tlab_fdm_plan_get(tlab_plan_t plan, const char* what, double* out_host, int capacity, int* count);
 
+/* FDM_Int1_CreateSystem(x, g, lambda, ibc, fdmi), src/fdm/fdm_integral.f90:91-214, on the host for one
+ * eigenvalue (ibc = 1 BCS_MIN, 2 BCS_MAX).  Outputs, column-major: lhs(n,5) before LU, rhs(n,3),
+ * rhs_b(1:5,0:7), rhs_t(0:4,1:8). */
+int tlab_fdm_int1_system_host(tlab_plan_t plan, int ibc, double lambda, double* lhs, double* rhs, double* rhs_b,
+                              double* rhs_t);
+
 /* ---- operators ------------------------------------------------------------------------------ */
 /* OPR_Partial_X/Y/Z(type, nx, ny, nz, bcs, g, u, result, tmp1), src/operators/opr_partial.f90:31-377 */
 int tlab_opr_partial(int dir, int type, int nx, int ny, int nz, const int bcs[4], tlab_plan_t g,
@@ -104,6 +110,15 @@ int tlab_fdm_der2_solve(tlab_plan_t g, int nlines, int is_or_minus1, const doubl
 /* BOUNDARY_BCS_NEUMANN_Y(ibc, nx, ny, nz, g, u, bcs_hb, bcs_ht, tmp1), src/tools/dns/boundary_bcs.f90:368-473 */
 int tlab_boundary_bcs_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_t gy, const double* u, double* bcs_hb,
                                 double* bcs_ht);
+
+/* OPR_Elliptic_Initialize, src/operators/opr_elliptic.f90:86-250 (FourierXZ_Factorize): eigenvalues from the
+ * x/z modified wavenumbers, integral-operator tables in y, cuFFT plans, fundamental solutions per mode */
+int tlab_opr_elliptic_init(tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz);
+/* OPR_Poisson(nx, ny, nz, ibc, p, tmp1, tmp2, bcs_hb, bcs_ht, dpdy), opr_elliptic.f90:263-364.
+ * p: forcing in, solution out; tmp1, tmp2: work arrays of (nx+2)*ny*nz doubles (the reference's
+ * isize_txc_field); dpdy may be NULL.  Only ibc = BCS_NN. */
+int tlab_opr_poisson(int nx, int ny, int nz, int ibc, double* p, double* tmp1, double* tmp2,
+                     const double* bcs_hb, const double* bcs_ht, double* dpdy_or_null);
 
 #ifdef __cplusplus
 }

@@ -298,6 +298,25 @@ int tlab_fdm_plan_get(tlab_plan_t g, const char* what, double* out, int cap, int
     return fail(TLAB_ERR_OPTION, "tlab_fdm_plan_get: unknown table " + w);
 }
 
+// FDM_Int1_CreateSystem for one eigenvalue, assembled on the host exactly as the device threads do it
+// (L0 + lambda*L1, then the reduction at the opposite end); used to validate the split tables.
+int tlab_fdm_int1_system_host(tlab_plan_t g, int ibc, double lambda, double* lhs, double* rhs, double* rhs_b, double* rhs_t) {
+    if (!g || !lhs || !rhs || !rhs_b || !rhs_t) return fail(TLAB_ERR_OPTION, "tlab_fdm_int1_system_host: null argument");
+    if (ibc != BCS_MIN && ibc != BCS_MAX) return fail(TLAB_ERR_OPTION, "ibc must be BCS_MIN (1) or BCS_MAX (2)");
+    HostInt1 H;
+    if (int rc = int1_create_base(g->p.h.der1, ibc, H)) return fail(rc, "integral operator not available for this scheme");
+    const int n = H.n;
+    Mat L(1, n, 1, 5);
+    for (int r = 1; r <= n; r++) for (int k = 1; k <= 5; k++) L(r, k) = H.L0(r, k) + lambda * H.L1(r, k);
+    if (ibc == BCS_MIN) fdm_bcs_reduce(BCS_MAX, L, H.rhs, nullptr, &H.rhs_t0);
+    else fdm_bcs_reduce(BCS_MIN, L, H.rhs, &H.rhs_b0, nullptr);
+    for (int k = 1; k <= 5; k++) for (int r = 1; r <= n; r++) lhs[(size_t)(k - 1) * n + r - 1] = L(r, k);
+    for (int k = 1; k <= 3; k++) for (int r = 1; r <= n; r++) rhs[(size_t)(k - 1) * n + r - 1] = H.rhs(r, k);
+    for (int c = 0; c <= 7; c++) for (int r = 1; r <= 5; r++) rhs_b[(size_t)c * 5 + r - 1] = H.rhs_b0(r, c);
+    for (int c = 1; c <= 8; c++) for (int r = 0; r <= 4; r++) rhs_t[(size_t)(c - 1) * 5 + r] = H.rhs_t0(r, c);
+    return 0;
+}
+
 int tlab_opr_partial(int dir, int type, int nx, int ny, int nz, const int bcs[4], tlab_plan_t g, const double* u,
                      double* result, double* tmp1) {
     if (int rc = need_ready()) return rc;

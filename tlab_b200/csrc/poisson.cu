@@ -1,0 +1,607 @@
+// OPR_Poisson: Fourier in x and z (cuFFT), factorised compact integral operators in y.
+//
+// Replaces OPR_Elliptic_Initialize / OPR_Poisson_FourierXZ_Factorize (src/operators/opr_elliptic.f90:86-364),
+// OPR_Fourier_X/Z_Forward/Backward (src/operators/opr_fourier.f90:219-433), OPR_ODE2_Factorize_NN and
+// _NN_Sing/_DN_Sing (src/operators/opr_odes.f90:37-96,165-183,265-386), FDM_Int1_Initialize/Solve
+// (src/fdm/fdm_integral.f90:58-314) and PENTADFS/PENTADSS (src/utils/linear5.f90:30-131).
+//
+// Layout: the half spectrum stays in cuFFT's natural order c(kx, y, kz), kx fastest.  One thread owns one
+// (kx,kz) mode and marches along y, so consecutive threads read consecutive kx: coalesced, and the three
+// complex transposes of the reference (opr_elliptic.f90:301,335,336) disappear.  The pentadiagonal system
+// of each mode, (B + lambda A) with lambda = +-sqrt(kx'^2 + kz'^2), is assembled from two shared banded
+// tables (L0 + lambda L1, built on the host) and factorised on the fly during the forward sweep instead
+// of being stored (the reference keeps 2 x ny x 5 doubles per mode, opr_elliptic.f90:140,205-209).
+// The lambda-only "fundamental" solutions (v1, e-, u1, s+, e+; opr_odes.f90:308-348) are computed once
+// at initialisation and kept, since they do not depend on the forcing.
+#include "../../include/tlab_gpu.h"
+#include "context.h"
+#include "poisson.h"
+#include <cufft.h>
+#include <cmath>
+#include <vector>
+
+namespace tlab {
+
+namespace {
+
+struct LineRef {
+    double* p;            // element of row r (1-based) is p[(r-1)*js]; nullptr reads as 0
+    long long js;
+    __device__ __forceinline__ double get(int r) const { return p ? p[(long long)(r - 1) * js] : 0.0; }
+    __device__ __forceinline__ void set(int r, double v) const { p[(long long)(r - 1) * js] = v; }
+};
+
+// -------------------------------------------------------------------------------------------------
+// Solve one first-order integral problem  u' + lam u = f  for NL right-hand sides of one mode.
+//   P      shared banded tables of this side (BCS_MIN: condition at row 1, BCS_MAX: at row n)
+//   f      forcing lines; rows 1 and n are never read, the far-end value is passed in fend
+//   bc     value imposed at the near end;   res: result lines (rows 1..n written)
+//   ysc, csc, dsc, esc: per-mode scratch lines (intermediate vector and the three upper factors)
+//   du     (optional) derivative at the far end, FDM_Int1_Solve's du_boundary
+template <int NL>
+__device__ void int1_solve(const Int1Dev& P, double lam, const LineRef (&f)[NL], double fscale,
+                           const double (&fend)[NL], const double (&bc)[NL], const LineRef (&res)[NL],
+                           const LineRef (&ysc)[NL], LineRef csc, LineRef dsc, LineRef esc, double* du) {
+    const int n = P.n;
+    const bool is_min = (P.bc == BCS_MIN);
+    auto Lrow = [&](int r, double (&row)[6]) {
+#pragma unroll
+        for (int k = 1; k <= 5; k++) row[k] = P.L0[(r - 1) * 5 + k - 1] + lam * P.L1[(r - 1) * 5 + k - 1];
+    };
+    auto rhs = [&](int r, int k) { return P.rhs[(r - 1) * 3 + k - 1]; };
+    auto F = [&](int l, int r) { return f[l].get(r) * fscale; };
+
+    // ---- reduction of the far-end row into its neighbours (lambda-dependent)
+    double Le[6], La[6], Lb[6];           // far-end row, its neighbour, next neighbour (after reduction)
+    double rb[4][4], rt[3][5];            // rhs_b(1:3, 0:3), rhs_t(0:2, 1:4)
+#pragma unroll
+    for (int r = 1; r <= 3; r++)
+#pragma unroll
+        for (int c = 0; c <= 3; c++) rb[r][c] = P.rb[r][c];
+#pragma unroll
+    for (int r = 0; r <= 2; r++)
+#pragma unroll
+        for (int c = 1; c <= 4; c++) rt[r][c] = P.rt[r][c];
+    if (is_min) {
+        Lrow(n, Le); Lrow(n - 1, La); Lrow(n - 2, Lb);
+        const double dummy = 1.0 / Le[3];
+#pragma unroll
+        for (int k = 1; k <= 5; k++) Le[k] = -Le[k] * dummy;
+        Le[3] = 1.0;
+        La[1] = La[1] + La[4] * Le[5]; La[2] = La[2] + La[4] * Le[1]; La[3] = La[3] + La[4] * Le[2];
+        Lb[2] = Lb[2] + Lb[5] * Le[5]; Lb[3] = Lb[3] + Lb[5] * Le[1]; Lb[4] = Lb[4] + Lb[5] * Le[2];
+#pragma unroll
+        for (int r = 0; r <= 2; r++)
+#pragma unroll
+            for (int c = 1; c <= 3; c++) rt[r][c] = rhs(n - 2 + r, c);
+#pragma unroll
+        for (int c = 1; c <= 3; c++) rt[2][c] = rt[2][c] * dummy;
+        rt[1][1] = rt[1][1] - La[4] * rt[2][3]; rt[1][2] = rt[1][2] - La[4] * rt[2][1]; rt[1][3] = rt[1][3] - La[4] * rt[2][2];
+        rt[0][2] = rt[0][2] - Lb[5] * rt[2][3]; rt[0][3] = rt[0][3] - Lb[5] * rt[2][1]; rt[0][4] = rt[0][4] - Lb[5] * rt[2][2];
+    } else {
+        Lrow(1, Le); Lrow(2, La); Lrow(3, Lb);
+        const double dummy = 1.0 / Le[3];
+#pragma unroll
+        for (int k = 1; k <= 5; k++) Le[k] = -Le[k] * dummy;
+        Le[3] = 1.0;
+        La[3] = La[3] + La[2] * Le[4]; La[4] = La[4] + La[2] * Le[5]; La[5] = La[5] + La[2] * Le[1];
+        Lb[2] = Lb[2] + Lb[1] * Le[4]; Lb[3] = Lb[3] + Lb[1] * Le[5]; Lb[4] = Lb[4] + Lb[1] * Le[1];
+#pragma unroll
+        for (int r = 1; r <= 3; r++)
+#pragma unroll
+            for (int c = 1; c <= 3; c++) rb[r][c] = rhs(r, c);
+#pragma unroll
+        for (int c = 1; c <= 3; c++) rb[1][c] = rb[1][c] * dummy;
+        rb[2][1] = rb[2][1] - La[2] * rb[1][2]; rb[2][2] = rb[2][2] - La[2] * rb[1][3]; rb[2][3] = rb[2][3] - La[2] * rb[1][1];
+        rb[3][0] = rb[3][0] - Lb[1] * rb[1][2]; rb[3][1] = rb[3][1] - Lb[1] * rb[1][3]; rb[3][2] = rb[3][2] - Lb[1] * rb[1][1];
+    }
+
+    double F1[NL], FN[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+        F1[l] = is_min ? bc[l] : fend[l];
+        FN[l] = is_min ? fend[l] : bc[l];
+    }
+
+    // ---- forward sweep: right-hand side, on-the-fly LU (PENTADFS) and forward substitution (PENTADSS)
+    const int nmax = n - 2;
+    double c1 = 0, c2 = 0, d1 = 0, d2 = 0, e1 = 0, e2 = 0;      // factors of rows m-1 and m-2 (unflipped)
+    double y1[NL], y2[NL], um[NL], u0[NL], up[NL];              // u(r-1), u(r), u(r+1)
+    double bcs_far[NL];
+#pragma unroll
+    for (int l = 0; l < NL; l++) { y1[l] = y2[l] = 0.0; um[l] = 0.0; u0[l] = F(l, 2); up[l] = F(l, 3); bcs_far[l] = 0.0; }
+    if (!is_min) {
+#pragma unroll
+        for (int l = 0; l < NL; l++) bcs_far[l] = F1[l] * rb[1][2] + u0[l] * rb[1][3] + up[l] * rb[1][1];
+    }
+    for (int m = 1; m <= nmax; m++) {
+        const int r = m + 1;
+        double row[6];
+        if (is_min && r == n - 1) {
+#pragma unroll
+            for (int k = 1; k <= 5; k++) row[k] = La[k];
+        } else if (is_min && r == n - 2) {
+#pragma unroll
+            for (int k = 1; k <= 5; k++) row[k] = Lb[k];
+        } else if (!is_min && r == 2) {
+#pragma unroll
+            for (int k = 1; k <= 5; k++) row[k] = La[k];
+        } else if (!is_min && r == 3) {
+#pragma unroll
+            for (int k = 1; k <= 5; k++) row[k] = Lb[k];
+        } else {
+            Lrow(r, row);
+        }
+        double a = row[1], b = row[2], c = row[3], d = row[4], e = row[5];
+        if (m == 2) {
+            b = b / c1;
+            c = c - b * d1;
+            d = d - b * e1;
+        } else if (m >= 3) {
+            a = a / c2;
+            b = (b - a * d2) / c1;
+            c = c - b * d1 - a * e2;
+            if (m < nmax) d = d - b * e1;
+        }
+        const double nb = -b, na = -a;
+        double unext[NL];
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+            unext[l] = (r + 2 <= n - 1) ? F(l, r + 2) : 0.0;
+            double rv;
+            if (r == 2) rv = F1[l] * rb[2][1] + u0[l] * rb[2][2] + up[l] * rb[2][3];
+            else if (r == 3) rv = F1[l] * rb[3][0] + um[l] * rb[3][1] + u0[l] * rb[3][2] + up[l] * rb[3][3];
+            else if (r == n - 2) rv = um[l] * rt[0][1] + u0[l] * rt[0][2] + up[l] * rt[0][3] + FN[l] * rt[0][4];
+            else if (r == n - 1) rv = um[l] * rt[1][1] + u0[l] * rt[1][2] + FN[l] * rt[1][3];
+            else rv = um[l] * rhs(r, 1) + u0[l] * rhs(r, 2) + up[l];
+            if (is_min && r == n - 1) bcs_far[l] = um[l] * rt[2][3] + u0[l] * rt[2][1] + FN[l] * rt[2][2];
+            double y;
+            if (m == 1) y = rv;
+            else if (m == 2) y = rv + y1[l] * nb;
+            else y = rv + y1[l] * nb + y2[l] * na;
+            ysc[l].set(r, y);
+            y2[l] = y1[l]; y1[l] = y;
+            um[l] = u0[l]; u0[l] = up[l]; up[l] = unext[l];
+        }
+        csc.set(r, 1.0 / c);
+        dsc.set(r, -d);
+        esc.set(r, -e);
+        c2 = c1; c1 = c; d2 = d1; d1 = d; e2 = e1; e1 = e;
+    }
+
+    // ---- backward sweep
+    double x1[NL], x2[NL];            // x(m+1), x(m+2)
+#pragma unroll
+    for (int l = 0; l < NL; l++) x1[l] = x2[l] = 0.0;
+    double r2v[NL], r3v[NL], r4v[NL]; // results at rows 2, 3, 4 (near-end closure / derivative)
+    for (int m = nmax; m >= 1; m--) {
+        const int r = m + 1;
+        const double ci = csc.get(r), nd = dsc.get(r), ne = esc.get(r);
+#pragma unroll
+        for (int l = 0; l < NL; l++) {
+            const double y = ysc[l].get(r);
+            double x;
+            if (m == nmax) x = y * ci;
+            else if (m == nmax - 1) x = (y + x1[l] * nd) * ci;
+            else x = (y + x1[l] * nd + x2[l] * ne) * ci;
+            res[l].set(r, x);
+            if (m == nmax - 2) {
+                // rows n-1, n-2, n-3 are known: far-end closure (BCS_MIN) or far-end derivative (BCS_MAX)
+                const double xn1 = x2[l], xn2 = x1[l], xn3 = x;
+                if (is_min) {
+                    double v = bcs_far[l];
+                    v = v + Le[2] * xn1;
+                    v = v + Le[1] * xn2;
+                    v = v + Le[5] * xn3;
+                    res[l].set(n, v);
+                } else {
+                    res[l].set(n, bc[l]);
+                    if (du) {
+                        double row[6];
+                        Lrow(n, row);
+                        double v = row[3] * bc[l];
+                        v = v + row[2] * xn1;
+                        v = v + row[1] * xn2;
+                        v = v + row[5] * xn3;
+                        v = v + rhs(n, 1) * F(l, n - 1);
+                        du[l] = v;
+                    }
+                }
+            }
+            if (r == 4) r4v[l] = x;
+            if (r == 3) r3v[l] = x;
+            if (r == 2) r2v[l] = x;
+            x2[l] = x1[l]; x1[l] = x;
+        }
+    }
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+        if (is_min) {
+            res[l].set(1, bc[l]);
+            if (du) {
+                double row[6];
+                Lrow(1, row);
+                double v = row[3] * bc[l];
+                v = v + row[4] * r2v[l];
+                v = v + row[5] * r3v[l];
+                v = v + row[1] * r4v[l];
+                v = v + rhs(1, 3) * F(l, 2);
+                du[l] = v;
+            }
+        } else {
+            double v = bcs_far[l];
+            v = v + Le[4] * r2v[l];
+            v = v + Le[5] * r3v[l];
+            v = v + Le[1] * r4v[l];
+            res[l].set(1, v);
+        }
+    }
+}
+
+struct ModeGeom {
+    int nxh, ny, nz;          // half-spectrum extent in x, lines in y, modes in z (local)
+    long long nmodes;         // nxh * nz
+};
+
+__device__ __forceinline__ bool mode_is_singular(const PoissonDev& D, int i, int k) {
+    return (i == D.i_sing0 || i == D.i_sing1) && (k == D.k_sing0 || k == D.k_sing1);
+}
+
+// scratch planes: [row][mode]
+__device__ __forceinline__ LineRef plane(double* base, long long nmodes, long long m) {
+    LineRef r; r.p = base + m; r.js = nmodes; return r;
+}
+
+// -------------------------------------------------------------------------------------------------
+// initialisation: fundamental solutions and the 3x3 boundary system of every regular mode
+__global__ void poisson_fundamental_kernel(PoissonDev D) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= D.nmodes) return;
+    const int i = (int)(m % D.nxh), k = (int)(m / D.nxh);
+    if (mode_is_singular(D, i, k)) return;
+    const double lam = sqrt(D.lambda[m]);
+    const long long NM = D.nmodes;
+    const long long plane_sz = NM * D.ny;
+    const int n = D.ny;
+    // stage 1: v1 (forcing delta at row n, v1(1) = 0) and e- (no forcing, e-(1) = 1)
+    {
+        LineRef f[2] = {{nullptr, 0}, {nullptr, 0}};
+        double fend[2] = {1.0, 0.0}, bc[2] = {0.0, 1.0};
+        LineRef res[2] = {plane(D.fund + 0 * plane_sz, NM, m), plane(D.fund + 1 * plane_sz, NM, m)};
+        LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, NM, m), plane(D.scr + 1 * plane_sz, NM, m)};
+        int1_solve<2>(D.smin, lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, NM, m),
+                      plane(D.scr + 4 * plane_sz, NM, m), plane(D.scr + 5 * plane_sz, NM, m), nullptr);
+    }
+    // stage 2: u1, s+, e+ from (v1, e-, 0) with values (0, 0, 1) at row n
+    double der[3];
+    {
+        LineRef v1 = plane(D.fund + 0 * plane_sz, NM, m), em = plane(D.fund + 1 * plane_sz, NM, m);
+        LineRef f[3] = {v1, em, {nullptr, 0}};
+        double fend[3] = {v1.get(1), em.get(1), 0.0}, bc[3] = {0.0, 0.0, 1.0};
+        LineRef res[3] = {plane(D.fund + 2 * plane_sz, NM, m), plane(D.fund + 3 * plane_sz, NM, m),
+                          plane(D.fund + 4 * plane_sz, NM, m)};
+        LineRef ysc[3] = {plane(D.scr + 0 * plane_sz, NM, m), plane(D.scr + 1 * plane_sz, NM, m),
+                          plane(D.scr + 2 * plane_sz, NM, m)};
+        int1_solve<3>(D.smax, -lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, NM, m),
+                      plane(D.scr + 4 * plane_sz, NM, m), plane(D.scr + 5 * plane_sz, NM, m), der);
+    }
+    // boundary system (opr_odes.f90:329-348), stored LU-decomposed
+    const double v1n = plane(D.fund + 0 * plane_sz, NM, m).get(n), emn = plane(D.fund + 1 * plane_sz, NM, m).get(n);
+    const double u11 = plane(D.fund + 2 * plane_sz, NM, m).get(1), sp1 = plane(D.fund + 3 * plane_sz, NM, m).get(1);
+    const double ep1 = plane(D.fund + 4 * plane_sz, NM, m).get(1);
+    double a11 = 1.0 + lam * sp1, a21 = emn, a31 = der[1];
+    double a12 = lam * ep1, a22 = lam, a32 = der[2];
+    double a13 = lam * u11, a23 = v1n, a33 = der[0];
+    a12 = a12 / a11;
+    a22 = a22 - a21 * a12;
+    a32 = a32 - a31 * a12;
+    a13 = a13 / a11;
+    a23 = (a23 - a21 * a13) / a22;
+    a33 = a33 - a31 * a13 - a32 * a23;
+    double* A = D.amat;
+    A[0 * NM + m] = a11; A[1 * NM + m] = a21; A[2 * NM + m] = a31;
+    A[3 * NM + m] = a12; A[4 * NM + m] = a22; A[5 * NM + m] = a32;
+    A[6 * NM + m] = a13; A[7 * NM + m] = a23; A[8 * NM + m] = a33;
+}
+
+// -------------------------------------------------------------------------------------------------
+// per call: regular modes, Neumann/Neumann (OPR_ODE2_Factorize_NN)
+__global__ void __launch_bounds__(128) poisson_modes_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv) {
+    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= D.nmodes) return;
+    const int i = (int)(m % D.nxh), k = (int)(m / D.nxh);
+    if (mode_is_singular(D, i, k)) return;
+    const double lam = sqrt(D.lambda[m]);
+    const long long NM = D.nmodes;
+    const long long plane_sz = NM * D.ny;
+    const int n = D.ny;
+    // complex lines of this mode inside c(kx, y, kz): re/im interleaved
+    const long long off = 2 * ((long long)i + (long long)D.nxh * D.ny * k);
+    const long long js = 2LL * D.nxh;
+    LineRef fre = {cf + off, js}, fim = {cf + off + 1, js};
+    LineRef vre = {cv + off, js}, vim = {cv + off + 1, js};
+    const double norm = D.norm;
+    const double bcb[2] = {fre.get(1) * norm, fim.get(1) * norm};      // bcs(1:2,1) = f(1:2)
+    const double bct[2] = {fre.get(n) * norm, fim.get(n) * norm};      // bcs(1:2,2) = f(2ny-1:2ny)
+    LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, NM, m), plane(D.scr + 1 * plane_sz, NM, m)};
+    LineRef csc = plane(D.scr + 2 * plane_sz, NM, m), dsc = plane(D.scr + 3 * plane_sz, NM, m),
+            esc = plane(D.scr + 4 * plane_sz, NM, m);
+    const double zero2[2] = {0.0, 0.0};
+    // v^(0): v' + lam v = f, f(n) = 0, v(1) = 0
+    {
+        LineRef f[2] = {fre, fim}, res[2] = {vre, vim};
+        int1_solve<2>(D.smin, lam, f, norm, zero2, zero2, res, ysc, csc, dsc, esc, nullptr);
+    }
+    // u^(0): u' - lam u = v, u(n) = 0  (written over the forcing, which is no longer needed)
+    double du0[2];
+    {
+        LineRef f[2] = {vre, vim}, res[2] = {fre, fim};
+        const double fend[2] = {vre.get(1), vim.get(1)};
+        int1_solve<2>(D.smax, -lam, f, 1.0, fend, zero2, res, ysc, csc, dsc, esc, du0);
+    }
+    // constraint and boundary conditions (opr_odes.f90:350-367)
+    const double* A = D.amat;
+    const double a11 = A[0 * NM + m], a21 = A[1 * NM + m], a31 = A[2 * NM + m];
+    const double a12 = A[3 * NM + m], a22 = A[4 * NM + m], a32 = A[5 * NM + m];
+    const double a13 = A[6 * NM + m], a23 = A[7 * NM + m], a33 = A[8 * NM + m];
+    LineRef v1 = plane(D.fund + 0 * plane_sz, NM, m), em = plane(D.fund + 1 * plane_sz, NM, m);
+    LineRef u1 = plane(D.fund + 2 * plane_sz, NM, m), sp = plane(D.fund + 3 * plane_sz, NM, m),
+            ep = plane(D.fund + 4 * plane_sz, NM, m);
+    LineRef ul[2] = {fre, fim}, vl[2] = {vre, vim};
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+        double v_1 = (bcb[l] - lam * ul[l].get(1)) / a11;
+        double u_n = (bct[l] - vl[l].get(n) - a21 * v_1) / a22;
+        const double fn = (bct[l] - du0[l] - a31 * v_1 - a32 * u_n) / a33;
+        u_n = u_n - a23 * fn;
+        v_1 = v_1 - a12 * u_n - a13 * fn;
+        // rows n, n-1 .. 2, 1
+        {
+            const double un_new = u_n;       // u(:, nx) has been replaced by the boundary value
+            const double vv = vl[l].get(n) + fn * v1.get(n) + v_1 * em.get(n) + lam * un_new;
+            ul[l].set(n, un_new);
+            vl[l].set(n, vv);
+        }
+        for (int r = n - 1; r >= 2; r--) {
+            const double uu = ul[l].get(r) + fn * u1.get(r) + v_1 * sp.get(r) + u_n * ep.get(r);
+            const double vv = vl[l].get(r) + fn * v1.get(r) + v_1 * em.get(r) + lam * uu;
+            ul[l].set(r, uu);
+            vl[l].set(r, vv);
+        }
+        {
+            const double uu = ul[l].get(1) + fn * u1.get(1) + v_1 * sp.get(1) + u_n * ep.get(1);
+            ul[l].set(1, uu);
+            vl[l].set(1, v_1 + lam * uu);
+        }
+    }
+}
+
+// per call: the (up to four) singular modes, OPR_ODE2_Factorize_NN_Sing -> _DN_Sing
+__global__ void poisson_singular_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv) {
+    const int t = threadIdx.x;
+    const int i = (t & 1) ? D.i_sing1 : D.i_sing0;
+    const int k = (t & 2) ? D.k_sing1 : D.k_sing0;
+    if (i < 0 || i >= D.nxh || k < 0 || k >= D.nz) return;
+    if ((t & 1) && D.i_sing1 == D.i_sing0) return;
+    if ((t & 2) && D.k_sing1 == D.k_sing0) return;
+    const long long m = (long long)i + (long long)D.nxh * k;
+    const double lam = sqrt(D.lambda[m]);
+    const long long NM = D.nmodes;
+    const long long plane_sz = NM * D.ny;
+    const int n = D.ny;
+    const long long off = 2 * ((long long)i + (long long)D.nxh * D.ny * k);
+    const long long js = 2LL * D.nxh;
+    LineRef fre = {cf + off, js}, fim = {cf + off + 1, js};
+    LineRef vre = {cv + off, js}, vim = {cv + off + 1, js};
+    const double norm = D.norm;
+    const double bct[2] = {fre.get(n) * norm, fim.get(n) * norm};
+    LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, NM, m), plane(D.scr + 1 * plane_sz, NM, m)};
+    LineRef csc = plane(D.scr + 2 * plane_sz, NM, m), dsc = plane(D.scr + 3 * plane_sz, NM, m),
+            esc = plane(D.scr + 4 * plane_sz, NM, m);
+    // fundamental lines of this mode live in the (otherwise unused) fund planes of the mode
+    LineRef v1 = plane(D.fund + 0 * plane_sz, NM, m), u1 = plane(D.fund + 2 * plane_sz, NM, m);
+    const double zero2[2] = {0.0, 0.0};
+    // v^(0): v' = f with f(1) = 0, v(n) = bcs(:,2)
+    {
+        LineRef f[2] = {fre, fim}, res[2] = {vre, vim};
+        int1_solve<2>(D.smax, -lam, f, norm, zero2, bct, res, ysc, csc, dsc, esc, nullptr);
+    }
+    // v^(1): forcing delta at row 1, v1(n) = 0
+    {
+        LineRef f[1] = {{nullptr, 0}}, res[1] = {v1}, ys[1] = {ysc[0]};
+        const double fend[1] = {1.0}, bc[1] = {0.0};
+        int1_solve<1>(D.smax, -lam, f, 1.0, fend, bc, res, ys, csc, dsc, esc, nullptr);
+    }
+    // u^(0): u' = v, u(1) = 0
+    double du0[2], du1[1];
+    {
+        LineRef f[2] = {vre, vim}, res[2] = {fre, fim};
+        const double fend[2] = {vre.get(n), vim.get(n)};
+        int1_solve<2>(D.smin, lam, f, 1.0, fend, zero2, res, ysc, csc, dsc, esc, du0);
+    }
+    {
+        LineRef f[1] = {v1}, res[1] = {u1}, ys[1] = {ysc[0]};
+        const double fend[1] = {v1.get(n)}, bc[1] = {0.0};
+        int1_solve<1>(D.smin, lam, f, 1.0, fend, bc, res, ys, csc, dsc, esc, du1);
+    }
+    const double ff = 1.0 / (du1[0] - v1.get(1));
+    LineRef ul[2] = {fre, fim}, vl[2] = {vre, vim};
+#pragma unroll
+    for (int l = 0; l < 2; l++) {
+        const double cdu = (vl[l].get(1) - du0[l]) * ff;
+        for (int r = 1; r <= n; r++) {
+            ul[l].set(r, ul[l].get(r) + cdu * u1.get(r));
+            vl[l].set(r, vl[l].get(r) + cdu * v1.get(r));
+        }
+    }
+}
+
+// boundary-condition planes into rows 1 and ny of the forcing (opr_elliptic.f90:285-286)
+__global__ void poisson_set_bcs_kernel(double* __restrict__ p, const double* __restrict__ hb, const double* __restrict__ ht,
+                                       int nx, int ny, int nz) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nx * nz) return;
+    const int i = (int)(idx % nx);
+    const long long k = idx / nx;
+    p[i + (long long)nx * ny * k] = hb[idx];
+    p[i + (long long)nx * ((ny - 1) + (long long)ny * k)] = ht[idx];
+}
+
+const double* up(std::vector<void*>& allocs, const double* h, size_t count) {
+    double* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(double)) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, h, count * sizeof(double), cudaMemcpyHostToDevice);
+    allocs.push_back(d);
+    return d;
+}
+
+int make_side(const HostDer& der1, int bc, Int1Dev& S, std::vector<void*>& allocs) {
+    HostInt1 H;
+    int rc = int1_create_base(der1, bc, H);
+    if (rc) return rc;
+    const int n = H.n;
+    std::vector<double> L0((size_t)n * 5), L1((size_t)n * 5), R((size_t)n * 3);
+    for (int r = 1; r <= n; r++) {
+        for (int k = 1; k <= 5; k++) { L0[(size_t)(r - 1) * 5 + k - 1] = H.L0(r, k); L1[(size_t)(r - 1) * 5 + k - 1] = H.L1(r, k); }
+        for (int k = 1; k <= 3; k++) R[(size_t)(r - 1) * 3 + k - 1] = H.rhs(r, k);
+    }
+    S.n = n; S.bc = bc;
+    S.L0 = up(allocs, L0.data(), L0.size());
+    S.L1 = up(allocs, L1.data(), L1.size());
+    S.rhs = up(allocs, R.data(), R.size());
+    for (int r = 1; r <= 3; r++) for (int c = 0; c <= 3; c++) S.rb[r][c] = H.rhs_b0(r, c);
+    for (int r = 0; r <= 2; r++) for (int c = 1; c <= 4; c++) S.rt[r][c] = H.rhs_t0(r, c);
+    return (S.L0 && S.L1 && S.rhs) ? 0 : TLAB_ERR_ALLOC;
+}
+
+}  // namespace
+
+static int cufft_check(cufftResult r, const char* what) {
+    if (r == CUFFT_SUCCESS) return 0;
+    return fail(TLAB_ERR_CUDA, std::string(what) + ": cuFFT error " + std::to_string((int)r));
+}
+
+void Poisson::release() {
+    if (plan_fx) cufftDestroy(plan_fx);
+    if (plan_bx) cufftDestroy(plan_bx);
+    if (plan_z) cufftDestroy(plan_z);
+    plan_fx = plan_bx = plan_z = 0;
+    for (void* a : allocs) cudaFree(a);
+    allocs.clear();
+    ready = false;
+}
+
+int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz) {
+    release();
+    if (!gx || !gy || !gz) return fail(TLAB_ERR_OPTION, "OPR_Elliptic_Initialize: null plan");
+    if (!gx->p.periodic || (gz->p.n > 1 && !gz->p.periodic))
+        return fail(TLAB_ERR_OPTION, "OPR_Poisson (Fourier) needs periodic x and z");
+    if (gy->p.periodic || gy->p.n < 16) return fail(TLAB_ERR_OPTION, "OPR_Poisson needs a non-periodic y with >= 16 points");
+    nx = gx->p.n; ny = gy->p.n; nz = gz->p.n;
+    if (nx % 2) return fail(TLAB_ERR_DIMGRID, "OPR_Poisson needs an even number of points in x");
+    nxh = nx / 2 + 1;
+    D.nxh = nxh; D.ny = ny; D.nz = nz; D.nmodes = (long long)nxh * nz;
+    D.norm = 1.0 / double((long long)nx * nz);                               // opr_elliptic.f90:130
+    D.i_sing0 = 0; D.i_sing1 = nx / 2;                                       // opr_elliptic.f90:148-149 (0-based)
+    D.k_sing0 = 0; D.k_sing1 = nz / 2;
+    // lambda(k,i) = mwn_x(i)^2 + mwn_z(k)^2 from the first-derivative modified wavenumbers (:199-203)
+    std::vector<double> lam((size_t)D.nmodes);
+    const std::vector<double>& mx = gx->p.h.der1.mwn;
+    const std::vector<double>& mz = gz->p.h.der1.mwn;
+    for (int k = 0; k < nz; k++)
+        for (int i = 0; i < nxh; i++) {
+            double l = mx[i] * mx[i];
+            if (nz > 1) l = l + mz[k] * mz[k];
+            lam[(size_t)i + (size_t)nxh * k] = l;
+        }
+    D.lambda = up(allocs, lam.data(), lam.size());
+    if (int rc = make_side(gy->p.h.der1, BCS_MIN, D.smin, allocs)) return fail(rc, "integral operator (BCS_MIN) setup failed");
+    if (int rc = make_side(gy->p.h.der1, BCS_MAX, D.smax, allocs)) return fail(rc, "integral operator (BCS_MAX) setup failed");
+    const size_t plane_sz = (size_t)D.nmodes * ny;
+    double *fund = nullptr, *scr = nullptr, *amat = nullptr;
+    if (cudaMalloc(&fund, 5 * plane_sz * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&scr, 6 * plane_sz * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&amat, 9 * (size_t)D.nmodes * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        return fail(TLAB_ERR_ALLOC, "OPR_Elliptic_Initialize: out of device memory");
+    }
+    allocs.push_back(fund); allocs.push_back(scr); allocs.push_back(amat);
+    D.fund = fund; D.scr = scr; D.amat = amat;
+    cudaMemset(fund, 0, 5 * plane_sz * sizeof(double));
+    // cuFFT plans (Appendix B of SURVEY.md: same geometry as the FFTW plans, opr_fourier.f90:101-171)
+    cudaStream_t st = ctx().stream;
+    int n1[1] = {nx};
+    if (int rc = cufft_check(cufftPlanMany(&plan_fx, 1, n1, n1, 1, nx, n1, 1, nxh, CUFFT_D2Z, ny * nz), "cufftPlanMany D2Z")) return rc;
+    if (int rc = cufft_check(cufftPlanMany(&plan_bx, 1, n1, n1, 1, nxh, n1, 1, nx, CUFFT_Z2D, ny * nz), "cufftPlanMany Z2D")) return rc;
+    cufftSetStream(plan_fx, st);
+    cufftSetStream(plan_bx, st);
+    if (nz > 1) {
+        int n3[1] = {nz};
+        const int howmany = nxh * ny;
+        if (int rc = cufft_check(cufftPlanMany(&plan_z, 1, n3, n3, howmany, 1, n3, howmany, 1, CUFFT_Z2Z, howmany), "cufftPlanMany Z2Z")) return rc;
+        cufftSetStream(plan_z, st);
+    }
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
+    poisson_fundamental_kernel<<<blocks, threads, 0, st>>>(D);
+    if (int rc = cuda_check(cudaStreamSynchronize(st), "poisson fundamental solutions")) return rc;
+    ready = true;
+    return 0;
+}
+
+// p: forcing in, solution out (nx,ny,nz); c1, c2: complex work arrays of (nx/2+1)*ny*nz; dpdy optional
+int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const double* ht, double* dpdy) {
+    if (!ready) return fail(TLAB_ERR_OPTION, "OPR_Poisson called before OPR_Elliptic_Initialize");
+    cudaStream_t st = ctx().stream;
+    {
+        const long long np = (long long)nx * nz;
+        poisson_set_bcs_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(p, hb, ht, nx, ny, nz);
+    }
+    if (int rc = cufft_check(cufftExecD2Z(plan_fx, p, (cufftDoubleComplex*)c1), "cufftExecD2Z")) return rc;
+    if (nz > 1)
+        if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)c1, (cufftDoubleComplex*)c1, CUFFT_FORWARD), "cufftExecZ2Z fwd")) return rc;
+    const int threads = 128;
+    const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
+    poisson_modes_kernel<<<blocks, threads, 0, st>>>(D, c1, c2);
+    poisson_singular_kernel<<<1, 4, 0, st>>>(D, c1, c2);
+    if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
+    if (nz > 1)
+        if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)c1, (cufftDoubleComplex*)c1, CUFFT_INVERSE), "cufftExecZ2Z inv")) return rc;
+    if (int rc = cufft_check(cufftExecZ2D(plan_bx, (cufftDoubleComplex*)c1, p), "cufftExecZ2D")) return rc;
+    if (dpdy) {
+        if (nz > 1)
+            if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)c2, (cufftDoubleComplex*)c2, CUFFT_INVERSE), "cufftExecZ2Z inv")) return rc;
+        if (int rc = cufft_check(cufftExecZ2D(plan_bx, (cufftDoubleComplex*)c2, dpdy), "cufftExecZ2D")) return rc;
+    }
+    return 0;
+}
+
+Poisson& poisson() {
+    static Poisson P;
+    return P;
+}
+
+}  // namespace tlab
+
+using namespace tlab;
+
+extern "C" {
+
+int tlab_opr_elliptic_init(tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz) {
+    if (int rc = tlab_gpu_init(-1)) return rc;
+    return poisson().init(gx, gy, gz);
+}
+
+int tlab_opr_poisson(int nx, int ny, int nz, int ibc, double* p, double* tmp1, double* tmp2, const double* bcs_hb,
+                     const double* bcs_ht, double* dpdy) {
+    if (int rc = tlab_gpu_init(-1)) return rc;
+    Poisson& P = poisson();
+    if (!P.ready) return fail(TLAB_ERR_OPTION, "OPR_Poisson called before OPR_Elliptic_Initialize");
+    if (nx != P.nx || ny != P.ny || nz != P.nz) return fail(TLAB_ERR_DIMGRID, "OPR_Poisson: extents differ from the initialised ones");
+    if (ibc != TLAB_BCS_NN) return fail(TLAB_ERR_UNDEVELOP, "OPR_Poisson: only BCS_NN is implemented on the GPU path");
+    if (!p || !tmp1 || !tmp2 || !bcs_hb || !bcs_ht) return fail(TLAB_ERR_OPTION, "OPR_Poisson: null argument");
+    if (int rc = P.solve(p, tmp1, tmp2, bcs_hb, bcs_ht, dpdy)) return rc;
+    return finish();
+}
+
+}  // extern "C"

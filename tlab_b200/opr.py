@@ -149,3 +149,18 @@ def FDM_Der2_Solve(nlines, g, u, result, du=None):
 def BOUNDARY_BCS_NEUMANN_Y(ibc, nx, ny, nz, g, u, bcs_hb, bcs_ht):
     """boundary_bcs.f90:368-473"""
     _call(_lib.load().tlab_boundary_bcs_neumann_y, ibc, nx, ny, nz, g.handle, _ptr(u), _ptr(bcs_hb), _ptr(bcs_ht))
+
+
+def OPR_Elliptic_Initialize(g):
+    """opr_elliptic.f90:86-250 (FourierXZ_Factorize); g = (gx, gy, gz)"""
+    _sync()
+    _lib.check(_lib.load().tlab_opr_elliptic_init(g[0].handle, g[1].handle, g[2].handle))
+
+
+def OPR_Poisson(nx, ny, nz, ibc, p, tmp1, tmp2, bcs_hb, bcs_ht, dpdy=None):
+    """opr_elliptic.f90:263-364; tmp1, tmp2 need (nx+2)*ny*nz elements"""
+    need = (nx + 2) * ny * nz
+    if tmp1.numel() < need or tmp2.numel() < need:
+        raise ValueError("tmp1/tmp2 must hold (nx+2)*ny*nz doubles")
+    _call(_lib.load().tlab_opr_poisson, nx, ny, nz, ibc, _ptr(p), _ptr(tmp1), _ptr(tmp2), _ptr(bcs_hb), _ptr(bcs_ht),
+          _ptr(dpdy))
