@@ -53,6 +53,25 @@ extern "C" {
 #define TLAB_RKM_EXP4 4
 
 typedef struct tlab_plan_s* tlab_plan_t; /* one direction: type(fdm_dt), src/fdm/fdm.f90:14-29 */
+typedef struct tlab_dns_s* tlab_dns_t;   /* module state of tools/dns: q, s, hq, hs, txc, parameters */
+
+#define TLAB_MAX_SCAL 8
+/* parameters of the incompressible/Boussinesq path that the reference keeps in module variables
+ * (TLab_Memory, NavierStokes, Gravity, BOUNDARY_BCS, DNS_LOCAL, TIME) */
+typedef struct {
+    int nx, ny, nz;                   /* imax, jmax, kmax */
+    int nscal;                        /* inb_scal */
+    int rkm_mode;                     /* TLAB_RKM_EXP3 | TLAB_RKM_EXP4 */
+    int buoyancy_type;                /* 0 none, 1 EQNS_BOD_HOMOGENEOUS, 2 EQNS_BOD_LINEAR (first scalar) */
+    int scal_limit;                   /* [Control] ScalLimit */
+    int bcs_flow_jmin[3], bcs_flow_jmax[3];                         /* TLAB_DNS_BCS_DIRICHLET | _NEUMANN */
+    int bcs_scal_jmin[TLAB_MAX_SCAL], bcs_scal_jmax[TLAB_MAX_SCAL];
+    double visc;                      /* 1/Reynolds */
+    double schmidt[TLAB_MAX_SCAL];
+    double buoyancy_params[2];        /* linear: {c1, c0}; homogeneous: {b, -} */
+    double buoyancy_vector[3];        /* [Gravity] Vector / Froude */
+    double scal_min[TLAB_MAX_SCAL], scal_max[TLAB_MAX_SCAL];
+} tlab_dns_params;
 
 /* ---- runtime ------------------------------------------------------------------------------- */
 int tlab_gpu_init(int device);                 /* TLab_Start, src/base/tlab_workflow.f90:36-101 (device part) */
@@ -119,6 +138,30 @@ int tlab_opr_elliptic_init(tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz);
  * isize_txc_field); dpdy may be NULL.  Only ibc = BCS_NN. */
 int tlab_opr_poisson(int nx, int ny, int nz, int ibc, double* p, double* tmp1, double* tmp2,
                      const double* bcs_hb, const double* bcs_ht, double* dpdy_or_null);
+
+/* ---- time advance --------------------------------------------------------------------------- */
+/* Device-resident state: allocates q(3), s(nscal), hq, hs and work arrays (TLab_Initialize_Memory,
+ * src/base/tlab_memory.f90:164-216; dns_main.f90:103-104), calls OPR_Burgers_Initialize and
+ * OPR_Elliptic_Initialize.  bbackground_host: reference buoyancy profile (ny) or NULL for zero. */
+int tlab_dns_create(const tlab_dns_params* prm, tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz,
+                    const double* bbackground_host, tlab_dns_t* out);
+int tlab_dns_destroy(tlab_dns_t dns);
+/* device pointer of "q1".."q3", "s1"..,"hq1".., "hs1".., "p" (pressure of the last RHS), "dpdy" */
+int tlab_dns_field(tlab_dns_t dns, const char* name, double** dev_ptr);
+int tlab_dns_upload_host(tlab_dns_t dns, const char* name, const double* src_host);
+int tlab_dns_download_host(tlab_dns_t dns, const char* name, double* dst_host);
+int tlab_dns_launch_count(tlab_dns_t dns, long long* count); /* kernels of this library launched so far */
+/* TIME_INITIALIZE coefficients, src/tools/dns/time.f90:86-112 */
+int tlab_time_rk_coefficients(int rkm_mode, double* kdt, double* ktime, double* kco, int* nsub);
+/* RHS_GLOBAL_INCOMPRESSIBLE_1, src/tools/dns/rhs_global_incompressible_1.f90:15-405: accumulates into hq, hs */
+int tlab_rhs_global_incompressible_1(tlab_dns_t dns, double dte);
+/* one Runge-Kutta stage: TLab_Sources_Flow + RHS + q += dte*hq (TIME_SUBSTEP_INCOMPRESSIBLE_EXPLICIT,
+ * time.f90:559-670), DNS_BOUNDS_LIMIT, and hq *= kco when scale_h != 0 (time.f90:261-298) */
+int tlab_time_substep(tlab_dns_t dns, double dte, double kco, int scale_h);
+/* TIME_RUNGEKUTTA, time.f90:185-333: hq = hs = 0, then all stages with dte = dtime*kdt(s) */
+int tlab_time_rungekutta(tlab_dns_t dns, double dtime);
+/* same, starting from and returning to HOST arrays q(N,3), s(N,nscal) (pinned memory recommended) */
+int tlab_time_rungekutta_host(tlab_dns_t dns, double dtime, double* q_host, double* s_host);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,100 @@
+"""GPU parity of the RHS and the Runge-Kutta advance: rel. L2 <= 1e-12 on hq/hs after one RHS call,
+<= 1e-10 on the fields after 10 RK steps (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+
+from common import grid_periodic, grid_tanh, grid_stretched, smooth_field, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _pair(nx, ny, nz, ykind="tanh", rkm=4, free_slip_top=True, buoy=True):
+    from oracle import fdm, dns as OD
+    from tlab_b200 import opr, dns as GD
+    x = grid_periodic(nx)
+    z = grid_periodic(nz) if nz > 1 else np.zeros(1)
+    y = {"stretched": grid_stretched(ny), "tanh": grid_tanh(ny), "uniform": np.linspace(0, 1, ny)}[ykind]
+    yuni = ykind == "uniform"
+    go = [fdm.Plan(x, True, True, name="x"), fdm.Plan(y, False, yuni, name="y"), fdm.Plan(z, True, True, name="z")]
+    gg = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, yuni, name="y"), opr.FdmPlan(z, True, True, name="z")]
+    D, N = OD.DNS_BCS_DIRICHLET, OD.DNS_BCS_NEUMANN
+    kw = dict(visc=1.0 / 5000.0, schmidt=[1.0], rkm_mode=rkm,
+              bcs_flow_jmin=(D, D, D), bcs_flow_jmax=(N, D, N) if free_slip_top else (D, D, D),
+              bcs_scal_jmin=(D,), bcs_scal_jmax=(N,) if free_slip_top else (D,))
+    if buoy:
+        kw.update(buoyancy_type="linear", buoyancy_params=(1.0, 0.0), buoyancy_vector=(0.0, 1.0, 0.0),
+                  bbackground=0.1 * y)
+    o = OD.Dns(go, **kw)
+    g = GD.Dns(gg, **kw)
+    grids = (x, y, z)
+    shape = (nz, ny, nx)
+    wall = np.sin(np.pi * y / y[-1] / 2.0)[None, :, None] if free_slip_top else np.sin(np.pi * y / y[-1])[None, :, None]
+    fields = [0.5 * smooth_field(shape, grids, seed=31 + i) * wall for i in range(3)]
+    if nz == 1:
+        fields[2][:] = 0.0
+    sc = 0.5 + 0.2 * smooth_field(shape, grids, seed=40) * wall / 3.0
+    for i in range(3):
+        o.q[i][...] = fields[i]
+        g.set("q%d" % (i + 1), fields[i])
+    o.s[0][...] = sc
+    g.set("s1", sc)
+    return o, g
+
+
+@pytest.mark.parametrize("case", [(32, 33, 16, "tanh", True), (48, 40, 20, "stretched", False), (64, 32, 1, "uniform", True)])
+def test_rhs_single_call(cuda, case):
+    nx, ny, nz, ykind, fs = case
+    o, g = _pair(nx, ny, nz, ykind, free_slip_top=fs)
+    dte = 1e-3
+    o.dte = dte
+    o.sources_flow()
+    o.rhs_global_incompressible_1()
+    g.substep(dte, 0.0, False)       # sources + rhs + q update; compare hq (unchanged by the update) and q
+    for i in range(3):
+        e = rel_l2(g.get("hq%d" % (i + 1)), o.hq[i])
+        assert e <= 1e-12, ("hq", i, e)
+    assert rel_l2(g.get("hs1"), o.hs[0]) <= 1e-12
+    assert rel_l2(g.get("p"), o.last_pressure) <= 1e-11
+
+
+@pytest.mark.parametrize("rkm", [3, 4])
+def test_ten_rk_steps(cuda, rkm):
+    o, g = _pair(32, 33, 16, "tanh", rkm=rkm)
+    dt = 2e-3
+    for it in range(10):
+        o.runge_kutta(dt)
+        g.runge_kutta(dt)
+    for i in range(3):
+        e = rel_l2(g.get("q%d" % (i + 1)), o.q[i])
+        assert e <= 1e-10, ("q", i, e)
+    assert rel_l2(g.get("s1"), o.s[0]) <= 1e-10
+
+
+def test_rk_step_from_host_buffers(cuda):
+    import torch
+    o, g = _pair(32, 33, 16, "tanh")
+    N = 32 * 33 * 16
+    qh = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+    sh = torch.empty(N, dtype=torch.float64).pin_memory()
+    for i in range(3):
+        qh[i * N:(i + 1) * N] = torch.from_numpy(o.q[i].ravel())
+    sh[:] = torch.from_numpy(o.s[0].ravel())
+    o.runge_kutta(1e-3)
+    g.runge_kutta_host(1e-3, qh.data_ptr(), sh.data_ptr())
+    for i in range(3):
+        assert rel_l2(qh[i * N:(i + 1) * N].numpy(), o.q[i].ravel()) <= 1e-11
+    assert rel_l2(sh.numpy(), o.s[0].ravel()) <= 1e-11
+    assert g.launch_count() > 0
+
+
+def test_scalar_clipping(cuda):
+    """DNS_BOUNDS_LIMIT: default [0,1] clipping of the scalar is part of the substep."""
+    o, g = _pair(32, 33, 16, "tanh")
+    big = o.s[0] * 3.0 - 0.7
+    o.s[0][...] = big
+    g.set("s1", big)
+    o.runge_kutta(1e-3)
+    g.runge_kutta(1e-3)
+    s = g.get("s1")
+    assert s.min() >= 0.0 and s.max() <= 1.0
+    assert rel_l2(s, o.s[0]) <= 1e-11

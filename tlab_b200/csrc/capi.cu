@@ -69,7 +69,7 @@ static int check_dims(int dir, int nx, int ny, int nz, const tlab_plan_s* g) {
 }
 
 int run_partial(int dir, int type, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* u, double* result,
-                double* tmp1) {
+                double* tmp1, const double* u2, double scale, int accumulate) {
     int rc = check_dims(dir, nx, ny, nz, g);
     if (rc) return rc;
     const size_t bytes = (size_t)nx * ny * nz * sizeof(double);
@@ -78,7 +78,7 @@ int run_partial(int dir, int type, int nx, int ny, int nz, int ibc, tlab_plan_s*
         return fail(TLAB_ERR_UNDEVELOP, "OPR_Partial: only OPR_P1, OPR_P2, OPR_P2_P1 are implemented");
     if (type == TLAB_OPR_P2_P1 && !tmp1) return fail(TLAB_ERR_OPTION, "OPR_P2_P1 needs tmp1");
     if (g->p.n == 1) {       // 2-D case: derivative set to zero (opr_partial.f90:174-177, 287-289)
-        cudaMemsetAsync(result, 0, bytes, st);
+        if (accumulate == 0) cudaMemsetAsync(result, 0, bytes, st);
         if (type == TLAB_OPR_P2_P1) cudaMemsetAsync(tmp1, 0, bytes, st);
         return 0;
     }
@@ -89,6 +89,7 @@ int run_partial(int dir, int type, int nx, int ny, int nz, int ibc, tlab_plan_s*
     bool contig;
     set_geometry(a, dir, nx, ny, nz, contig);
     a.u = u; a.out1 = result; a.out2 = tmp1;
+    a.u2 = u2; a.scale = scale; a.accumulate = accumulate;
     a.rhs1 = p.rhs1[ibc];
     a.lu1 = p.lu1[ibc];
     a.lu2 = p.lu2[0];

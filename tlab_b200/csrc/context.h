@@ -31,7 +31,7 @@ int finish();          // synchronise unless async; maps errors
 
 // launch helpers shared by the operator entry points and the RHS driver (all device pointers)
 int run_partial(int dir, int type, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* u, double* result,
-                double* tmp1);
+                double* tmp1, const double* u2 = nullptr, double scale = 0.0, int accumulate = 0);
 int run_burgers(int dir, int is, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* s, const double* vel,
                 double* result, int accumulate);
 int run_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_s* g, const double* u, double* hb, double* ht);

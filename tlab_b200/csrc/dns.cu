@@ -1,0 +1,376 @@
+// Right-hand side of the incompressible/Boussinesq equations and the low-storage Runge-Kutta substep,
+// device resident.
+//
+// Replaces TIME_RUNGEKUTTA / TIME_SUBSTEP_INCOMPRESSIBLE_EXPLICIT (src/tools/dns/time.f90:185-333,559-670),
+// RHS_GLOBAL_INCOMPRESSIBLE_1 (src/tools/dns/rhs_global_incompressible_1.f90:15-405, combined mode,
+// remove_divergence), TLab_Sources_Flow + Gravity_Buoyancy (src/physics/tlab_sources.f90:36-131,
+// src/physics/gravity.f90:232-342; homogeneous and linear), DNS_BOUNDS_LIMIT (src/tools/dns/dns_local.f90:67-90).
+//
+// Fusion relative to the reference's call sequence (values identical up to round-off, association of
+// every sum kept):  each Burgers operator accumulates straight into hq/hs (no tmp + add sweep);
+// the pressure forcing hq + q/dte is formed while loading the pencil of the divergence kernels and the
+// three divergence terms accumulate into one array; the pressure gradient is subtracted from hq by the
+// derivative kernels; q += dte*hq, the scalar clipping and hq *= kco are one sweep.
+#include "../../include/tlab_gpu.h"
+#include "context.h"
+#include "poisson.h"
+#include <vector>
+#include <string>
+#include <cstring>
+
+namespace tlab {
+
+namespace {
+
+constexpr int EW_THREADS = 256;
+
+inline unsigned ew_blocks(long long n) {
+    long long b = (n + EW_THREADS - 1) / EW_THREADS;
+    const long long cap = 148LL * 16;     // a few waves of resident CTAs; grid-stride beyond that
+    return (unsigned)(b < cap ? b : cap);
+}
+
+// hq(iq) += vector(iq) * b,   b = c1*s1 - (ref(j) - c0)   (linear)  or  b = const (homogeneous)
+__global__ void buoyancy_kernel(double* __restrict__ hq1, double* __restrict__ hq2, double* __restrict__ hq3,
+                                const double* __restrict__ s1, const double* __restrict__ ref, double c1, double c0,
+                                double bhom, int linear, double g1, double g2, double g3, int nx, int ny, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        double b;
+        if (linear) {
+            const int j = (int)((i / nx) % ny);
+            const double dummy = ref[j] - c0;
+            b = c1 * s1[i] - dummy;
+        } else {
+            b = bhom;
+        }
+        if (g1 != 0.0) hq1[i] = hq1[i] + g1 * b;
+        if (g2 != 0.0) hq2[i] = hq2[i] + g2 * b;
+        if (g3 != 0.0) hq3[i] = hq3[i] + g3 * b;
+    }
+}
+
+__global__ void sub_kernel(double* __restrict__ a, const double* __restrict__ b, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        a[i] = a[i] - b[i];
+}
+
+// q += dte*h ; optional clipping ; h *= kco
+__global__ void rk_update_kernel(double* __restrict__ q, double* __restrict__ h, double dte, double kco, int scale_h,
+                                 int clip, double vmin, double vmax, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double hv = h[i];
+        double v = q[i] + dte * hv;
+        if (clip) v = fmin(fmax(v, vmin), vmax);
+        q[i] = v;
+        if (scale_h) h[i] = kco * hv;
+    }
+}
+
+// planes j = 0 and j = ny-1 of a field <-> (nx, nz) arrays
+__global__ void get_planes_kernel(const double* __restrict__ f, double* __restrict__ hb, double* __restrict__ ht,
+                                  int nx, int ny, int nz) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nx * nz) return;
+    const int i = (int)(idx % nx);
+    const long long k = idx / nx;
+    hb[idx] = f[i + (long long)nx * ny * k];
+    ht[idx] = f[i + (long long)nx * ((ny - 1) + (long long)ny * k)];
+}
+
+__global__ void set_planes_kernel(double* __restrict__ f, const double* __restrict__ hb, const double* __restrict__ ht,
+                                  int use_b, int use_t, int nx, int ny, int nz) {
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)nx * nz) return;
+    const int i = (int)(idx % nx);
+    const long long k = idx / nx;
+    f[i + (long long)nx * ny * k] = use_b ? hb[idx] : 0.0;
+    f[i + (long long)nx * ((ny - 1) + (long long)ny * k)] = use_t ? ht[idx] : 0.0;
+}
+
+void rk_tables(int mode, std::vector<double>& kdt, std::vector<double>& ktime, std::vector<double>& kco) {
+    if (mode == TLAB_RKM_EXP3) {        // Williamson 1980 (time.f90:87-92)
+        kdt = {1.0 / 3.0, 15.0 / 16.0, 8.0 / 15.0};
+        ktime = {0.0, 1.0 / 3.0, 3.0 / 4.0};
+        kco = {-5.0 / 9.0, -153.0 / 128.0};
+    } else {                            // Carpenter & Kennedy 1994, 5 stages (time.f90:94-112)
+        kdt = {1432997174477.0 / 9575080441755.0, 5161836677717.0 / 13612068292357.0, 1720146321549.0 / 2090206949498.0,
+               3134564353537.0 / 4481467310338.0, 2277821191437.0 / 14882151754819.0};
+        ktime = {0.0, kdt[0], 2526269341429.0 / 6820363962896.0, 2006345519317.0 / 3224310063776.0,
+                 2802321613138.0 / 2924317926251.0};
+        kco = {-567301805773.0 / 1357537059087.0, -2404267990393.0 / 2016746695238.0,
+               -3550918686646.0 / 2091501179385.0, -1275806237668.0 / 842570457699.0};
+    }
+}
+
+}  // namespace
+
+struct Dns {
+    tlab_dns_params prm;
+    tlab_plan_s* g[3] = {nullptr, nullptr, nullptr};
+    int nx = 0, ny = 0, nz = 0, ns = 0;
+    long long N = 0, Nt = 0;             // points per field; points of a work array, (nx+2)*ny*nz
+    std::vector<double*> q, s, hq, hs;   // device fields
+    double *tmp1 = nullptr, *tmp3 = nullptr, *c1 = nullptr, *c2 = nullptr;
+    double *hb = nullptr, *ht = nullptr;
+    double* bbackground = nullptr;
+    std::vector<double> kdt, ktime, kco;
+    std::vector<void*> allocs;
+    double* host_stage = nullptr;        // pinned staging buffer for the *_host entry points
+    size_t host_stage_bytes = 0;
+    long long launches = 0;
+
+    int alloc(double** p, long long count) {
+        if (cudaMalloc(p, (size_t)count * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(TLAB_ERR_ALLOC, "tlab_dns_create: out of device memory");
+        }
+        allocs.push_back(*p);
+        return cuda_check(cudaMemsetAsync(*p, 0, (size_t)count * sizeof(double), ctx().stream), "memset");
+    }
+
+    int sources_flow() {
+        if (prm.buoyancy_type == 0) return 0;
+        const double g1 = prm.buoyancy_vector[0], g2 = prm.buoyancy_vector[1], g3 = prm.buoyancy_vector[2];
+        if (g1 == 0.0 && g2 == 0.0 && g3 == 0.0) return 0;
+        const int linear = (prm.buoyancy_type == 2);
+        if (linear && ns < 1) return fail(TLAB_ERR_OPTION, "linear buoyancy needs a scalar");
+        buoyancy_kernel<<<ew_blocks(N), EW_THREADS, 0, ctx().stream>>>(
+            hq[0], hq[1], hq[2], linear ? s[0] : nullptr, bbackground, prm.buoyancy_params[0], prm.buoyancy_params[1],
+            prm.buoyancy_params[0], linear, g1, g2, g3, nx, ny, N);
+        launches++;
+        return 0;
+    }
+
+    int rhs(double dte) {
+        cudaStream_t st = ctx().stream;
+        const int b0 = 0;   // bcs = 0: biased, non-zero (rhs_global_incompressible_1.f90:67)
+        int rc = 0;
+        auto B = [&](int dir, int is, const double* sf, const double* vel, double* out) {
+            if (rc) return;
+            rc = run_burgers(dir, is, nx, ny, nz, b0, g[dir - 1], sf, vel, out, +1);
+            launches++;
+        };
+        double *u = q[0], *v = q[1], *w = q[2];
+        // hq1 += Bx(u,u) + By(u,v) + Bz(u,w)          (:98-111)
+        B(1, 0, u, u, hq[0]); B(2, 0, u, v, hq[0]); B(3, 0, u, w, hq[0]);
+        // hq2 += By(v,v) + Bx(v,u) + Bz(v,w)          (:99,115-123)
+        B(2, 0, v, v, hq[1]); B(1, 0, v, u, hq[1]); B(3, 0, v, w, hq[1]);
+        // hq3 += Bz(w,w) + Bx(w,u) + By(w,v)          (:100,127-135)
+        B(3, 0, w, w, hq[2]); B(1, 0, w, u, hq[2]); B(2, 0, w, v, hq[2]);
+        for (int is = 0; is < ns; is++) {              // (:149-162)
+            B(1, is + 1, s[is], u, hs[is]); B(2, is + 1, s[is], v, hs[is]); B(3, is + 1, s[is], w, hs[is]);
+        }
+        if (rc) return rc;
+        // pressure forcing: div(hq + q/dte), accumulated in the order y, x, z (:177-260)
+        const double dummy = 1.0 / dte;
+        if ((rc = run_partial(2, TLAB_OPR_P1, nx, ny, nz, b0, g[1], hq[1], tmp1, nullptr, v, dummy, 0))) return rc;
+        if ((rc = run_partial(1, TLAB_OPR_P1, nx, ny, nz, b0, g[0], hq[0], tmp1, nullptr, u, dummy, +1))) return rc;
+        if ((rc = run_partial(3, TLAB_OPR_P1, nx, ny, nz, b0, g[2], hq[2], tmp1, nullptr, w, dummy, +1))) return rc;
+        launches += 3;
+        // Neumann data for the pressure: hq2 at the walls (:272-281)
+        const long long np = (long long)nx * nz;
+        get_planes_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(hq[1], hb, ht, nx, ny, nz);
+        launches++;
+        if ((rc = poisson().solve(tmp1, c1, c2, hb, ht, tmp3))) return rc;     // (:284)
+        launches += 3;   // boundary planes, regular modes, singular modes (cuFFT's own kernels not counted)
+        // hq -= grad p (:319-352)
+        if ((rc = run_partial(1, TLAB_OPR_P1, nx, ny, nz, b0, g[0], tmp1, hq[0], nullptr, nullptr, 0.0, -1))) return rc;
+        if ((rc = run_partial(3, TLAB_OPR_P1, nx, ny, nz, b0, g[2], tmp1, hq[2], nullptr, nullptr, 0.0, -1))) return rc;
+        sub_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(hq[1], tmp3, N);
+        launches += 3;
+        // boundary conditions (:356-398)
+        for (int f = 0; f < 3 + ns; f++) {
+            double* h = (f < 3) ? hq[f] : hs[f - 3];
+            const int tmin = (f < 3) ? prm.bcs_flow_jmin[f] : prm.bcs_scal_jmin[f - 3];
+            const int tmax = (f < 3) ? prm.bcs_flow_jmax[f] : prm.bcs_scal_jmax[f - 3];
+            int ibc = 0;
+            if (tmin == TLAB_DNS_BCS_NEUMANN) ibc += 1;
+            if (tmax == TLAB_DNS_BCS_NEUMANN) ibc += 2;
+            if (ibc > 0) {
+                if ((rc = run_neumann_y(ibc, nx, ny, nz, g[1], h, hb, ht))) return rc;
+                launches++;
+            }
+            set_planes_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(h, hb, ht, ibc & 1, (ibc >> 1) & 1, nx, ny, nz);
+            launches++;
+        }
+        return cuda_check(cudaGetLastError(), "rhs");
+    }
+
+    // TIME_SUBSTEP_INCOMPRESSIBLE_EXPLICIT + DNS_BOUNDS_LIMIT + hq *= kco
+    int substep(double dte, double kcoef, int scale_h) {
+        int rc = sources_flow();
+        if (rc) return rc;
+        if ((rc = rhs(dte))) return rc;
+        cudaStream_t st = ctx().stream;
+        for (int f = 0; f < 3; f++)
+            rk_update_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(q[f], hq[f], dte, kcoef, scale_h, 0, 0.0, 0.0, N);
+        for (int is = 0; is < ns; is++)
+            rk_update_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(s[is], hs[is], dte, kcoef, scale_h, prm.scal_limit,
+                                                                  prm.scal_min[is], prm.scal_max[is], N);
+        launches += 3 + ns;
+        return cuda_check(cudaGetLastError(), "rk update");
+    }
+
+    int runge_kutta(double dtime) {
+        cudaStream_t st = ctx().stream;
+        for (double* h : hq) cudaMemsetAsync(h, 0, (size_t)N * sizeof(double), st);
+        for (double* h : hs) cudaMemsetAsync(h, 0, (size_t)N * sizeof(double), st);
+        const int nsub = (int)kdt.size();
+        for (int sub = 0; sub < nsub; sub++) {
+            const double dte = dtime * kdt[sub];
+            const bool last = (sub == nsub - 1);
+            int rc = substep(dte, last ? 0.0 : kco[sub], last ? 0 : 1);
+            if (rc) return rc;
+        }
+        return 0;
+    }
+
+    void release() {
+        for (void* a : allocs) cudaFree(a);
+        allocs.clear();
+        if (host_stage) cudaFreeHost(host_stage);
+        host_stage = nullptr;
+    }
+};
+
+}  // namespace tlab
+
+struct tlab_dns_s {
+    tlab::Dns d;
+};
+
+using namespace tlab;
+
+static double* field_ptr(Dns& d, const char* name) {
+    const std::string w(name ? name : "");
+    auto idx = [&](size_t pre) { return w.size() > pre ? atoi(w.c_str() + pre) - 1 : -1; };
+    if (w.rfind("hq", 0) == 0) { int i = idx(2); return (i >= 0 && i < 3) ? d.hq[i] : nullptr; }
+    if (w.rfind("hs", 0) == 0) { int i = idx(2); return (i >= 0 && i < d.ns) ? d.hs[i] : nullptr; }
+    if (w.rfind("q", 0) == 0) { int i = idx(1); return (i >= 0 && i < 3) ? d.q[i] : nullptr; }
+    if (w.rfind("s", 0) == 0) { int i = idx(1); return (i >= 0 && i < d.ns) ? d.s[i] : nullptr; }
+    if (w == "p") return d.tmp1;
+    if (w == "dpdy") return d.tmp3;
+    return nullptr;
+}
+
+extern "C" {
+
+int tlab_dns_create(const tlab_dns_params* prm, tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz,
+                    const double* bbackground_host, tlab_dns_t* out) {
+    if (int rc = tlab_gpu_init(-1)) return rc;
+    if (!prm || !gx || !gy || !gz || !out) return fail(TLAB_ERR_OPTION, "tlab_dns_create: null argument");
+    if (prm->nscal < 0 || prm->nscal > TLAB_MAX_SCAL) return fail(TLAB_ERR_OPTION, "tlab_dns_create: too many scalars");
+    if (prm->rkm_mode != TLAB_RKM_EXP3 && prm->rkm_mode != TLAB_RKM_EXP4)
+        return fail(TLAB_ERR_UNDEVELOP, "only the explicit RK3 / RK4(5) schemes are implemented");
+    if (gx->p.n != prm->nx || gy->p.n != prm->ny || gz->p.n != prm->nz)
+        return fail(TLAB_ERR_DIMGRID, "tlab_dns_create: plan sizes differ from nx, ny, nz");
+    tlab_dns_s* h = new tlab_dns_s();
+    Dns& d = h->d;
+    d.prm = *prm;
+    d.g[0] = gx; d.g[1] = gy; d.g[2] = gz;
+    d.nx = prm->nx; d.ny = prm->ny; d.nz = prm->nz; d.ns = prm->nscal;
+    d.N = (long long)d.nx * d.ny * d.nz;
+    d.Nt = (long long)(d.nx + 2) * d.ny * d.nz;
+    rk_tables(prm->rkm_mode, d.kdt, d.ktime, d.kco);
+    int rc = tlab_opr_burgers_init(gx, gy, gz, prm->visc, prm->nscal, prm->schmidt);
+    if (!rc) rc = tlab_opr_elliptic_init(gx, gy, gz);
+    d.q.resize(3); d.hq.resize(3); d.s.resize(d.ns); d.hs.resize(d.ns);
+    for (int i = 0; i < 3 && !rc; i++) { rc = d.alloc(&d.q[i], d.N); if (!rc) rc = d.alloc(&d.hq[i], d.N); }
+    for (int i = 0; i < d.ns && !rc; i++) { rc = d.alloc(&d.s[i], d.N); if (!rc) rc = d.alloc(&d.hs[i], d.N); }
+    if (!rc) rc = d.alloc(&d.tmp1, d.Nt);
+    if (!rc) rc = d.alloc(&d.tmp3, d.Nt);
+    if (!rc) rc = d.alloc(&d.c1, d.Nt);
+    if (!rc) rc = d.alloc(&d.c2, d.Nt);
+    if (!rc) rc = d.alloc(&d.hb, (long long)d.nx * d.nz);
+    if (!rc) rc = d.alloc(&d.ht, (long long)d.nx * d.nz);
+    if (!rc) rc = d.alloc(&d.bbackground, d.ny);
+    if (!rc && bbackground_host)
+        rc = cuda_check(cudaMemcpyAsync(d.bbackground, bbackground_host, d.ny * sizeof(double), cudaMemcpyHostToDevice, ctx().stream), "bbackground");
+    if (!rc) rc = cuda_check(cudaStreamSynchronize(ctx().stream), "tlab_dns_create");
+    if (rc) { d.release(); delete h; return rc; }
+    *out = h;
+    return 0;
+}
+
+int tlab_dns_destroy(tlab_dns_t h) {
+    if (!h) return 0;
+    cudaStreamSynchronize(ctx().stream);
+    h->d.release();
+    delete h;
+    return 0;
+}
+
+int tlab_dns_field(tlab_dns_t h, const char* name, double** dev_ptr) {
+    if (!h || !dev_ptr) return fail(TLAB_ERR_OPTION, "tlab_dns_field: null argument");
+    double* p = field_ptr(h->d, name);
+    if (!p) return fail(TLAB_ERR_OPTION, std::string("tlab_dns_field: unknown field ") + (name ? name : "(null)"));
+    *dev_ptr = p;
+    return 0;
+}
+
+int tlab_dns_upload_host(tlab_dns_t h, const char* name, const double* src_host) {
+    if (!h || !src_host) return fail(TLAB_ERR_OPTION, "tlab_dns_upload_host: null argument");
+    double* p = field_ptr(h->d, name);
+    if (!p) return fail(TLAB_ERR_OPTION, "tlab_dns_upload_host: unknown field");
+    return tlab_gpu_upload(p, src_host, (size_t)h->d.N * sizeof(double));
+}
+
+int tlab_dns_download_host(tlab_dns_t h, const char* name, double* dst_host) {
+    if (!h || !dst_host) return fail(TLAB_ERR_OPTION, "tlab_dns_download_host: null argument");
+    double* p = field_ptr(h->d, name);
+    if (!p) return fail(TLAB_ERR_OPTION, "tlab_dns_download_host: unknown field");
+    return tlab_gpu_download(dst_host, p, (size_t)h->d.N * sizeof(double));
+}
+
+int tlab_time_substep(tlab_dns_t h, double dte, double kco, int scale_h) {
+    if (!h) return fail(TLAB_ERR_OPTION, "tlab_time_substep: null state");
+    if (int rc = h->d.substep(dte, kco, scale_h)) return rc;
+    return finish();
+}
+
+int tlab_rhs_global_incompressible_1(tlab_dns_t h, double dte) {
+    if (!h) return fail(TLAB_ERR_OPTION, "null state");
+    if (int rc = h->d.rhs(dte)) return rc;
+    return finish();
+}
+
+int tlab_time_rungekutta(tlab_dns_t h, double dtime) {
+    if (!h) return fail(TLAB_ERR_OPTION, "tlab_time_rungekutta: null state");
+    if (int rc = h->d.runge_kutta(dtime)) return rc;
+    return finish();
+}
+
+int tlab_time_rungekutta_host(tlab_dns_t h, double dtime, double* q_host, double* s_host) {
+    if (!h || !q_host) return fail(TLAB_ERR_OPTION, "tlab_time_rungekutta_host: null argument");
+    Dns& d = h->d;
+    cudaStream_t st = ctx().stream;
+    const size_t fb = (size_t)d.N * sizeof(double);
+    for (int i = 0; i < 3; i++)
+        if (int rc = cuda_check(cudaMemcpyAsync(d.q[i], q_host + (size_t)i * d.N, fb, cudaMemcpyHostToDevice, st), "upload q")) return rc;
+    for (int i = 0; i < d.ns; i++)
+        if (int rc = cuda_check(cudaMemcpyAsync(d.s[i], s_host + (size_t)i * d.N, fb, cudaMemcpyHostToDevice, st), "upload s")) return rc;
+    if (int rc = d.runge_kutta(dtime)) return rc;
+    for (int i = 0; i < 3; i++)
+        if (int rc = cuda_check(cudaMemcpyAsync(q_host + (size_t)i * d.N, d.q[i], fb, cudaMemcpyDeviceToHost, st), "download q")) return rc;
+    for (int i = 0; i < d.ns; i++)
+        if (int rc = cuda_check(cudaMemcpyAsync(s_host + (size_t)i * d.N, d.s[i], fb, cudaMemcpyDeviceToHost, st), "download s")) return rc;
+    return cuda_check(cudaStreamSynchronize(st), "tlab_time_rungekutta_host");
+}
+
+int tlab_time_rk_coefficients(int rkm_mode, double* kdt, double* ktime, double* kco, int* nsub) {
+    if (rkm_mode != TLAB_RKM_EXP3 && rkm_mode != TLAB_RKM_EXP4) return fail(TLAB_ERR_UNDEVELOP, "unknown RK scheme");
+    std::vector<double> a, b, c;
+    rk_tables(rkm_mode, a, b, c);
+    if (nsub) *nsub = (int)a.size();
+    for (size_t i = 0; i < a.size(); i++) { if (kdt) kdt[i] = a[i]; if (ktime) ktime[i] = b[i]; }
+    for (size_t i = 0; i < c.size(); i++) if (kco) kco[i] = c[i];
+    return 0;
+}
+
+int tlab_dns_launch_count(tlab_dns_t h, long long* count) {
+    if (!h || !count) return fail(TLAB_ERR_OPTION, "tlab_dns_launch_count: null argument");
+    *count = h->d.launches;
+    return 0;
+}
+
+}  // extern "C"

@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(512) line_kernel_strided(LineArgs a) {
         if (PER) p = (p < 0) ? p + n : (p >= n ? p - n : p);
         const bool ok = in_win && p >= 0 && p < n;
         u[k] = ok ? __ldcs(up + (long long)p * st) : 0.0;
+        if (a.u2 != nullptr && ok) u[k] = u[k] + __ldcs(a.u2 + lbase + (long long)p * st) * a.scale;
     }
     double wb[BROW_W], wt[BROW_W];
     if (!PER) {
@@ -327,13 +328,14 @@ __global__ void __launch_bounds__(512) line_kernel_strided(LineArgs a) {
     for (int j = 0; j < CHUNK; j++) {
         if (active && j >= c.j0 && j < j1) {
             const long long off = (long long)(c.s0 + j - c.j0) * st;
-            if (MODE == MODE_P1) o1[off] = d1[j];
+            if (MODE == MODE_P1) o1[off] = (a.accumulate == 0) ? d1[j] : (a.accumulate > 0 ? o1[off] + d1[j] : o1[off] - d1[j]);
             if (MODE == MODE_P2) o1[off] = d2[j];
             if (MODE == MODE_P2_P1) { o1[off] = d2[j]; o2[off] = d1[j]; }
             if (MODE == MODE_BURGERS) {
                 const double v = __ldcs(vp + off);
                 double r = d2[j] - v * d1[j];
-                if (a.accumulate) r = o1[off] + r;
+                if (a.accumulate > 0) r = o1[off] + r;
+                else if (a.accumulate < 0) r = o1[off] - r;
                 o1[off] = r;
             }
         }
@@ -365,7 +367,11 @@ __global__ void __launch_bounds__(512) line_kernel_contig(LineArgs a) {
         const double* __restrict__ vsrc = two ? a.vel + (line0 + ll) * (long long)n : nullptr;
         if ((n & 1) == 0) {
             for (int i = 2 * threadIdx.x; i < n; i += 2 * blockDim.x) {
-                const double2 v = __ldcs(reinterpret_cast<const double2*>(src + i));
+                double2 v = __ldcs(reinterpret_cast<const double2*>(src + i));
+                if (a.u2 != nullptr) {
+                    const double2 w2 = __ldcs(reinterpret_cast<const double2*>(a.u2 + (line0 + ll) * (long long)n + i));
+                    v.x = v.x + w2.x * a.scale; v.y = v.y + w2.y * a.scale;
+                }
                 tile[ll * S + xpos(i)] = v.x;
                 tile[ll * S + xpos(i + 1)] = v.y;
                 if (two) {
@@ -376,7 +382,9 @@ __global__ void __launch_bounds__(512) line_kernel_contig(LineArgs a) {
             }
         } else {
             for (int i = threadIdx.x; i < n; i += blockDim.x) {
-                tile[ll * S + xpos(i)] = src[i];
+                double v = src[i];
+                if (a.u2 != nullptr) v = v + a.u2[(line0 + ll) * (long long)n + i] * a.scale;
+                tile[ll * S + xpos(i)] = v;
                 if (two) vtile[ll * S + xpos(i)] = vsrc[i];
             }
         }
@@ -435,16 +443,18 @@ __global__ void __launch_bounds__(512) line_kernel_contig(LineArgs a) {
                     double2 v;
                     v.x = tile[ll * S + xpos(i)];
                     v.y = tile[ll * S + xpos(i + 1)];
-                    if (a.accumulate) {
+                    if (a.accumulate != 0) {
                         const double2 o = *reinterpret_cast<const double2*>(dst + i);
-                        v.x = o.x + v.x; v.y = o.y + v.y;
+                        if (a.accumulate > 0) { v.x = o.x + v.x; v.y = o.y + v.y; }
+                        else { v.x = o.x - v.x; v.y = o.y - v.y; }
                     }
                     *reinterpret_cast<double2*>(dst + i) = v;
                 }
             } else {
                 for (int i = threadIdx.x; i < n; i += blockDim.x) {
                     double v = tile[ll * S + xpos(i)];
-                    if (a.accumulate) v = dst[i] + v;
+                    if (a.accumulate > 0) v = dst[i] + v;
+                    else if (a.accumulate < 0) v = dst[i] - v;
                     dst[i] = v;
                 }
             }

@@ -10,12 +10,14 @@ struct LineArgs {
     int n = 0, T = 1, cbase = 0, crem = 0;
     int L = 1;                        // lines per CTA
     int xstride = 0;                  // shared-memory line stride (contiguous-line kernel)
-    int accumulate = 0;               // out1 += result instead of out1 = result
+    int accumulate = 0;               // +1: out1 += result, -1: out1 -= result, 0: out1 = result
+    double scale = 0.0;               // input is u + scale * u2 when u2 != nullptr
     long long nlines = 0;
     long long stride = 1;             // distance between consecutive points of a line
     long long inner = 1;              // line index -> offset: (line / inner) * outer_stride + line % inner
     long long outer_stride = 0;
     const double* u = nullptr;        // field to differentiate (s in the Burgers operator)
+    const double* u2 = nullptr;       // optional second input, see scale
     const double* vel = nullptr;      // advecting velocity (Burgers)
     double* out1 = nullptr;           // P1: du, P2: d2u, P2_P1: d2u, BURGERS: nu d2s - vel ds
     double* out2 = nullptr;           // P2_P1: du

@@ -37,6 +37,7 @@ def parse_header(path=HEADER):
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     src = re.sub(r"//[^\n]*", "", src)
     protos = {}
+    src = re.sub(r"typedef\s+struct\s*\{.*?\}\s*\w+\s*;", "", src, flags=re.S)
     for m in re.finditer(r"\b(int|const char\s*\*)\s+(tlab_\w+)\s*\(([^;{]*?)\)\s*;", src, flags=re.S):
         ret, name, args = m.group(1), m.group(2), " ".join(m.group(3).split())
         argtypes = [] if args in ("void", "") else [_ctype(a) for a in args.split(",")]
