@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""Benchmark of the tlab hot path: RK-substep throughput (Gpts/s) on synthetic fields.
+
+A "step" is one low-storage Runge-Kutta substep (sources + RHS_GLOBAL_INCOMPRESSIBLE_1 + update) of the
+incompressible/Boussinesq equations with one scalar on the BASELINE.json configuration
+"convective boundary layer 1024x512x1024, RK + FFT Poisson" (C3 of SURVEY.md section 8(d)).
+
+  python bench.py --gpus 1 --steps K --warmup W            GPU arm (this library)
+  python bench.py --impl reference ...                     reference arm: the CPU restatement of the
+                                                           reference's algorithm (oracle/, "port"), all host cores
+
+One JSON line is printed by rank 0.  See DESIGN.md "Measurement" for the definitions.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (nx, ny, nz)
+    "c3": (1024, 512, 1024),      # BASELINE.json configs[2], single GPU
+    "c3-half": (1024, 512, 512),
+    "c2": (512, 512, 512),
+    "small": (256, 128, 256),
+    "tiny": (64, 48, 32),
+}
+ALG_BYTES_PER_PT_SUBSTEP = 995.0          # 124.4 sweeps of 8 B
+PHYS = dict(visc=1.0 / 5000.0, schmidt=[1.0], dtime=1.0e-3)
+
+
+def grid_periodic(n, length=2.0 * np.pi):
+    return np.arange(n) * length / n
+
+
+def grid_tanh(n, length=1.0, st=0.9375, f=2.0, delta=0.0078125):
+    s = np.arange(n) * length / (n - 1)
+    y = s + (f - 1.0) * delta * np.logaddexp((s - st) / delta, 0.0)
+    return y - y[0]
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            parts = [p.strip() for p in r.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax = float(parts[2])
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_port_worker(args):
+    """One process = one host core running the oracle RK step on the sample grid."""
+    nx, ny, nz, nsteps, seed = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import fdm, dns as OD
+    x, z, y = grid_periodic(nx), grid_periodic(nz), grid_tanh(ny)
+    g = [fdm.Plan(x, True, True, name="x"), fdm.Plan(y, False, False, name="y"), fdm.Plan(z, True, True, name="z")]
+    D, Nn = OD.DNS_BCS_DIRICHLET, OD.DNS_BCS_NEUMANN
+    o = OD.Dns(g, visc=PHYS["visc"], schmidt=PHYS["schmidt"], buoyancy_type="linear", buoyancy_params=(1.0, 0.0),
+               buoyancy_vector=(0.0, 1.0, 0.0), bcs_flow_jmin=(D, D, D), bcs_flow_jmax=(Nn, D, Nn),
+               bcs_scal_jmin=(D,), bcs_scal_jmax=(Nn,))
+    rng = np.random.default_rng(seed)
+    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    wall = np.sin(0.5 * np.pi * Y)
+    for i in range(3):
+        o.q[i][...] = 0.3 * np.sin(rng.integers(1, 5) * X + rng.integers(1, 5) * Z + rng.uniform(0, 6.28)) * wall
+    o.s[0][...] = 0.5 + 0.2 * np.sin(X + 2 * Z) * wall
+    o.runge_kutta(PHYS["dtime"])                    # warm-up step (plans, caches)
+    t0 = time.perf_counter()
+    for _ in range(nsteps):
+        o.runge_kutta(PHYS["dtime"])
+    dt = time.perf_counter() - t0
+    return dt / (nsteps * o.rkm_endstep)            # seconds per substep on this core
+
+
+def cpu_port_rate(sample=(128, 64, 128), rk_steps=1, cores=None):
+    """Aggregate Gpts/s per substep of `cores` independent oracle instances (no communication cost charged)."""
+    import multiprocessing as mp
+    cores = cores or max(1, (os.cpu_count() or 1))
+    cores = min(cores, 64)
+    nx, ny, nz = sample
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        secs = pool.map(cpu_port_worker, [(nx, ny, nz, rk_steps, 100 + i) for i in range(cores)])
+    pts = nx * ny * nz
+    rate = sum(pts / s for s in secs) / 1e9
+    return rate, cores, "%d independent %dx%dx%d oracle instances, %d RK step(s) each" % (cores, nx, ny, nz, rk_steps)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    nx, ny, nz = WORKLOADS[args.workload]
+    sample = (128, 64, 128)
+    per_step = []
+    cores = None
+    desc = ""
+    total = args.warmup + args.steps
+    # each "step" of this arm is one bounded sample (one RK step of every instance = 5 substeps per core)
+    for i in range(min(total, 3)):
+        t0 = time.perf_counter()
+        rate, cores, desc = cpu_port_rate(sample, 1, None)
+        per_step.append((rate, time.perf_counter() - t0))
+    rates = [r for r, _ in per_step[min(args.warmup, len(per_step) - 1):]]
+    value = float(np.median(rates))
+    out = {"impl": "reference", "metric": "rk_substep_throughput", "value": value, "unit": "Gpts/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nx * ny * nz / (value * 1e9),
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "incompressible Boussinesq CBL %dx%dx%d, RK4-5 substep, 1 scalar" % (nx, ny, nz),
+                      "note": "CPU restatement of the reference algorithm (no Fortran compiler in the image); "
+                              "rate measured on a bounded sample and quoted per point"},
+           "cpu_baseline": {"value": value, "unit": "Gpts/s", "cores": cores, "kind": "port", "sample": desc},
+           "e2e": {"value": value, "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------
+def synth_field(torch, dev, shape, x, y, z, seed, amp):
+    """sum of 8 smooth modes A sin(kx x + kz z + phi) g(y), built on the device."""
+    nz, ny, nx = shape
+    rng = np.random.default_rng(seed)
+    xt = torch.from_numpy(x).to(dev)
+    zt = torch.from_numpy(z).to(dev)
+    yt = torch.from_numpy(y / (y[-1] if y[-1] != 0 else 1.0)).to(dev)
+    out = torch.zeros(shape, dtype=torch.float64, device=dev)
+    gs = [torch.ones_like(yt), torch.cos(np.pi * yt), yt]
+    wall = torch.sin(0.5 * np.pi * yt)
+    for m in range(8):
+        kx, kz = int(rng.integers(-8, 9)), int(rng.integers(-8, 9))
+        a, ph = float(rng.uniform(0.1, 1.0)), float(rng.uniform(0, 2 * np.pi))
+        # sin(kx x + kz z + ph) = sin(kx x + ph) cos(kz z) + cos(kx x + ph) sin(kz z)
+        sx, cx = torch.sin(kx * xt + ph), torch.cos(kx * xt + ph)
+        sz, cz = torch.sin(kz * zt), torch.cos(kz * zt)
+        gy = (a * amp) * gs[m % 3] * wall
+        out += gy[None, :, None] * (cz[:, None, None] * sx[None, None, :] + sz[:, None, None] * cx[None, None, :])
+    return out
+
+
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from tlab_b200 import lib as tl, opr, dns as GD
+    import ctypes
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the GPU arm has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = tl.load()
+    tl.check(L.tlab_gpu_init(local_rank))
+
+    nx, ny, nz = WORKLOADS[args.workload]
+    if args.nx:
+        nx, ny, nz = args.nx, args.ny, args.nz
+    if world > 1:
+        raise SystemExit("bench.py: multi-GPU z-slab path not enabled in this build")
+    x, z, y = grid_periodic(nx), grid_periodic(nz), grid_tanh(ny)
+    g = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, False, name="y"), opr.FdmPlan(z, True, True, name="z")]
+    D, Nn = GD.DNS_BCS_DIRICHLET, GD.DNS_BCS_NEUMANN
+    sim = GD.Dns(g, visc=PHYS["visc"], schmidt=PHYS["schmidt"], rkm_mode=GD.RKM_EXP4, buoyancy_type="linear",
+                 buoyancy_params=(1.0, 0.0), buoyancy_vector=(0.0, 1.0, 0.0),
+                 bcs_flow_jmin=(D, D, D), bcs_flow_jmax=(Nn, D, Nn), bcs_scal_jmin=(D,), bcs_scal_jmax=(Nn,))
+    N = nx * ny * nz
+    shape = (nz, ny, nx)
+    names = ["q1", "q2", "q3", "s1"]
+    for i, nm in enumerate(names):
+        f = synth_field(torch, dev, shape, x, y, z, 20261017 + i, 0.05)
+        if nm == "s1":
+            f = 0.5 + f
+        torch.cuda.synchronize()
+        tl.check(L.tlab_gpu_copy(ctypes.c_void_p(sim.device_ptr(nm)), ctypes.c_void_p(f.data_ptr()), N * 8))
+        del f
+    torch.cuda.empty_cache()
+
+    sp = ctypes.c_void_p()
+    tl.check(L.tlab_gpu_stream(ctypes.byref(sp)))
+    stream = torch.cuda.ExternalStream(sp.value, device=dev)
+    dtime = PHYS["dtime"]
+    nstage = 5
+
+    def substeps(k0, k):
+        for i in range(k0, k0 + k):
+            sim.runge_kutta_stage(dtime, i % nstage)
+
+    tl.check(L.tlab_gpu_set_async(1))
+    substeps(0, args.warmup)
+    tl.check(L.tlab_gpu_synchronize())
+    launches0 = sim.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    tl.check(L.tlab_gpu_profile(1))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    substeps(args.warmup, args.steps)
+    e1.record(stream)
+    tl.check(L.tlab_gpu_synchronize())
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    launches = sim.launch_count() - launches0
+    ms_cls = (ctypes.c_double * 11)()
+    cnt_cls = (ctypes.c_int * 11)()
+    tl.check(L.tlab_gpu_profile_report(ms_cls, cnt_cls, 11))
+    tl.check(L.tlab_gpu_profile(0))
+    cls_names = ["burgers_x", "burgers_y", "burgers_z", "partial_x", "partial_y", "partial_z", "neumann_bcs", "fft",
+                 "poisson_y", "elementwise", "transpose"]
+    breakdown = {n_: {"ms_per_step": ms_cls[i] / args.steps, "launches_per_step": cnt_cls[i] / args.steps}
+                 for i, n_ in enumerate(cls_names) if cnt_cls[i] > 0}
+    ms_per_step = ms_total / args.steps
+    value = N / (ms_per_step * 1e-3) / 1e9
+
+    # roofline of the dominant kernel class (by device time inside the timed region)
+    peak, peak_kind = load_peaks()
+    line_classes = {"burgers_x": 22.0, "burgers_y": 22.0, "burgers_z": 22.0,      # (16 + 3*24)/4 B/pt per launch
+                    "partial_x": 16.0, "partial_y": 16.0, "partial_z": 16.0}
+    dom = max((k for k in breakdown if k in line_classes), key=lambda k: breakdown[k]["ms_per_step"])
+    avg_ms = ms_cls[cls_names.index(dom)] / cnt_cls[cls_names.index(dom)]
+    achieved = line_classes[dom] * N / (avg_ms * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None,
+                "algorithmic_bytes_per_launch": line_classes[dom] * N, "avg_launch_ms": avg_ms,
+                "substep": {"algorithmic_bytes": ALG_BYTES_PER_PT_SUBSTEP * N,
+                            "achieved": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9,
+                            "frac": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9 / peak}}
+
+    # end to end: one full RK step (5 substeps) from and to pinned host buffers through the C ABI
+    tl.check(L.tlab_gpu_set_async(0))
+    e2e = None
+    try:
+        qh = torch.empty(3 * N, dtype=torch.float64).pin_memory()
+        sh = torch.empty(N, dtype=torch.float64).pin_memory()
+        for i in range(3):
+            tl.check(L.tlab_gpu_download(ctypes.c_void_p(qh.data_ptr() + i * N * 8), ctypes.c_void_p(sim.device_ptr("q%d" % (i + 1))), N * 8))
+        tl.check(L.tlab_gpu_download(ctypes.c_void_p(sh.data_ptr()), ctypes.c_void_p(sim.device_ptr("s1")), N * 8))
+        sim.runge_kutta_host(dtime, qh.data_ptr(), sh.data_ptr())      # warm-up
+        reps = 2
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record(stream)
+        for _ in range(reps):
+            sim.runge_kutta_host(dtime, qh.data_ptr(), sh.data_ptr())
+        a1.record(stream)
+        torch.cuda.synchronize()
+        ms_e2e = a0.elapsed_time(a1) / (reps * nstage)
+        e2e = {"value": N / (ms_e2e * 1e-3) / 1e9, "unit": "Gpts/s", "h2d_bytes_per_step": 4 * N * 8 / nstage,
+               "d2h_bytes_per_step": 4 * N * 8 / nstage, "ms_per_step": ms_e2e,
+               "call": "tlab_time_rungekutta_host: 4 fields up, 5 substeps, 4 fields down"}
+        del qh, sh
+    except Exception as ex:           # e.g. not enough pinned host memory
+        e2e = {"value": None, "unit": "Gpts/s", "error": str(ex)}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        rate, cores, desc = cpu_port_rate((128, 64, 128), 1, None)
+        cpu = {"value": rate, "unit": "Gpts/s", "cores": cores, "kind": "port", "sample": desc}
+
+    out = {"metric": "rk_substep_throughput", "value": value, "unit": "Gpts/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
+           "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": "incompressible Boussinesq CBL %dx%dx%d, RK4-5 substep, 1 scalar, CompactJacobian6 + "
+                                  "CompactJacobian6Hyper, tanh-stretched y" % (nx, ny, nz),
+                      "l2": "working set per substep >> 126 MB L2 (each field %.2f GB)" % (N * 8 / 1e9),
+                      "decomposition": "z-slabs x%d" % world},
+           "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+           "breakdown_ms": breakdown}
+    if rank == 0:
+        print(json.dumps(out))
+    sim.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="gpu", choices=["gpu", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--nx", type=int, default=0)
+    ap.add_argument("--ny", type=int, default=0)
+    ap.add_argument("--nz", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

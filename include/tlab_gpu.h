@@ -83,7 +83,17 @@ int tlab_gpu_malloc(void** ptr, size_t bytes); /* TLab_Allocate_Real, src/base/t
 int tlab_gpu_free(void* ptr);
 int tlab_gpu_upload(void* dst_device, const void* src_host, size_t bytes);
 int tlab_gpu_download(void* dst_host, const void* src_device, size_t bytes);
+int tlab_gpu_copy(void* dst_device, const void* src_device, size_t bytes);
 int tlab_gpu_set_tuning(const char* key, int value); /* "lines_x", "lines_yz": lines per CTA (0 = automatic) */
+
+/* the CUDA stream (cudaStream_t) every call is ordered on, for event timing by the host */
+int tlab_gpu_stream(void** stream);
+/* per-class device timing of this library's launches (USE_PROFILE of the reference, time.f90:195-198,311-329):
+ * classes 0-2 Burgers x/y/z, 3-5 Partial x/y/z, 6 Neumann BCs, 7 FFTs, 8 Poisson y solves, 9 element-wise,
+ * 10 transposes.  The report synchronises, fills 11 entries and clears the records. */
+#define TLAB_PROF_CLASSES 11
+int tlab_gpu_profile(int on);
+int tlab_gpu_profile_report(double* ms_per_class, int* count_per_class, int nclass);
 
 /* ---- plans ---------------------------------------------------------------------------------- */
 /* FDM_CreatePlan(x, g), src/fdm/fdm.f90:143-252: builds Jacobians, scheme tables, Neumann reductions
@@ -158,6 +168,9 @@ int tlab_rhs_global_incompressible_1(tlab_dns_t dns, double dte);
 /* one Runge-Kutta stage: TLab_Sources_Flow + RHS + q += dte*hq (TIME_SUBSTEP_INCOMPRESSIBLE_EXPLICIT,
  * time.f90:559-670), DNS_BOUNDS_LIMIT, and hq *= kco when scale_h != 0 (time.f90:261-298) */
 int tlab_time_substep(tlab_dns_t dns, double dte, double kco, int scale_h);
+/* stage `stage` (0-based) of TIME_RUNGEKUTTA's loop: zeroes hq, hs when stage == 0 (time.f90:212-216), then
+ * tlab_time_substep with dte = dtime*kdt(stage) and kco(stage) */
+int tlab_time_rungekutta_stage(tlab_dns_t dns, double dtime, int stage);
 /* TIME_RUNGEKUTTA, time.f90:185-333: hq = hs = 0, then all stages with dte = dtime*kdt(s) */
 int tlab_time_rungekutta(tlab_dns_t dns, double dtime);
 /* same, starting from and returning to HOST arrays q(N,3), s(N,nscal) (pinned memory recommended) */

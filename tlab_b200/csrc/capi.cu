@@ -29,6 +29,26 @@ int finish() {
     return 0;
 }
 
+ProfScope::ProfScope(int cls) {
+    Context& c = ctx();
+    if (!c.profiling) return;
+    Context::ProfRec r;
+    r.cls = cls;
+    for (cudaEvent_t* e : {&r.a, &r.b}) {
+        if (!c.event_pool.empty()) { *e = c.event_pool.back(); c.event_pool.pop_back(); }
+        else cudaEventCreate(e);
+    }
+    cudaEventRecord(r.a, c.stream);
+    c.prof.push_back(r);
+    idx = (int)c.prof.size() - 1;
+}
+
+ProfScope::~ProfScope() {
+    if (idx < 0) return;
+    Context& c = ctx();
+    cudaEventRecord(c.prof[idx].b, c.stream);
+}
+
 static int need_ready() {
     if (!ctx().ready) {
         int rc = tlab_gpu_init(-1);
@@ -94,6 +114,7 @@ int run_partial(int dir, int type, int nx, int ny, int nz, int ibc, tlab_plan_s*
     a.lu1 = p.lu1[ibc];
     a.lu2 = p.lu2[0];
     const int mode = (type == TLAB_OPR_P1) ? MODE_P1 : (type == TLAB_OPR_P2 ? MODE_P2 : MODE_P2_P1);
+    ProfScope ps(PC_PARTIAL_X + dir - 1);
     return cuda_check(launch_lines(mode, a, p.periodic, p.need_1der, contig, st), "line kernel");
 }
 
@@ -118,6 +139,7 @@ int run_burgers(int dir, int is, int nx, int ny, int nz, int ibc, tlab_plan_s* g
     a.rhs1 = p.rhs1[ibc];
     a.lu1 = p.lu1[ibc];
     a.lu2 = p.lu2[g->burgers_first + is];
+    ProfScope ps(PC_BURGERS_X + dir - 1);
     return cuda_check(launch_lines(MODE_BURGERS, a, p.periodic, p.need_1der, contig, st), "burgers kernel");
 }
 
@@ -148,6 +170,7 @@ int run_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_s* g, const double*
     std::memcpy(a.neu_top, p.neu_top[ibc], sizeof(a.neu_top));
     a.neu_lu_bot = p.neu_lu_bot[ibc];
     a.neu_lu_top = p.neu_lu_top[ibc];
+    ProfScope ps(PC_NEUMANN);
     return cuda_check(launch_lines(MODE_NEUMANN, a, false, false, false, st), "neumann kernel");
 }
 
@@ -208,10 +231,47 @@ int tlab_gpu_upload(void* dst, const void* src, size_t bytes) {
     return cuda_check(cudaStreamSynchronize(ctx().stream), "upload");
 }
 
+int tlab_gpu_copy(void* dst, const void* src, size_t bytes) {
+    if (int rc = need_ready()) return rc;
+    if (int rc = cuda_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, ctx().stream), "copy")) return rc;
+    return finish();
+}
+
 int tlab_gpu_download(void* dst, const void* src, size_t bytes) {
     if (int rc = need_ready()) return rc;
     if (int rc = cuda_check(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx().stream), "download")) return rc;
     return cuda_check(cudaStreamSynchronize(ctx().stream), "download");
+}
+
+int tlab_gpu_stream(void** stream) {
+    if (int rc = need_ready()) return rc;
+    if (!stream) return fail(TLAB_ERR_OPTION, "null argument");
+    *stream = (void*)ctx().stream;
+    return 0;
+}
+
+int tlab_gpu_profile(int on) {
+    Context& c = ctx();
+    if (on && !c.profiling) {
+        for (auto& r : c.prof) { c.event_pool.push_back(r.a); c.event_pool.push_back(r.b); }
+        c.prof.clear();
+    }
+    c.profiling = (on != 0);
+    return 0;
+}
+
+int tlab_gpu_profile_report(double* ms_per_class, int* count_per_class, int nclass) {
+    Context& c = ctx();
+    if (!ms_per_class || !count_per_class || nclass < PC_COUNT) return fail(TLAB_ERR_OPTION, "profile report: need PC_COUNT entries");
+    if (int rc = cuda_check(cudaStreamSynchronize(c.stream), "profile report")) return rc;
+    for (int i = 0; i < nclass; i++) { ms_per_class[i] = 0.0; count_per_class[i] = 0; }
+    for (auto& r : c.prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) { ms_per_class[r.cls] += ms; count_per_class[r.cls]++; }
+        c.event_pool.push_back(r.a); c.event_pool.push_back(r.b);
+    }
+    c.prof.clear();
+    return 0;
 }
 
 int tlab_gpu_set_tuning(const char* key, int value) {

@@ -3,6 +3,7 @@
 #include "plan.h"
 #include "lines.h"
 #include <string>
+#include <vector>
 #include <cuda_runtime.h>
 
 struct tlab_plan_s {
@@ -22,6 +23,19 @@ struct Context {
     std::string last_error;
     int tune_lines_x = 0, tune_lines_yz = 0;
     tlab_plan_s* burgers_plans[3] = {nullptr, nullptr, nullptr};
+    bool profiling = false;
+    struct ProfRec { int cls; cudaEvent_t a, b; };
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+// optional per-class timing of the library's launches with CUDA events on the library stream
+enum ProfClass { PC_BURGERS_X = 0, PC_BURGERS_Y, PC_BURGERS_Z, PC_PARTIAL_X, PC_PARTIAL_Y, PC_PARTIAL_Z, PC_NEUMANN,
+                 PC_FFT, PC_POISSON_Y, PC_ELEMENTWISE, PC_TRANSPOSE, PC_COUNT };
+struct ProfScope {
+    int idx = -1;
+    explicit ProfScope(int cls);
+    ~ProfScope();
 };
 
 Context& ctx();

@@ -134,6 +134,7 @@ struct Dns {
         if (g1 == 0.0 && g2 == 0.0 && g3 == 0.0) return 0;
         const int linear = (prm.buoyancy_type == 2);
         if (linear && ns < 1) return fail(TLAB_ERR_OPTION, "linear buoyancy needs a scalar");
+        ProfScope ps(PC_ELEMENTWISE);
         buoyancy_kernel<<<ew_blocks(N), EW_THREADS, 0, ctx().stream>>>(
             hq[0], hq[1], hq[2], linear ? s[0] : nullptr, bbackground, prm.buoyancy_params[0], prm.buoyancy_params[1],
             prm.buoyancy_params[0], linear, g1, g2, g3, nx, ny, N);
@@ -169,14 +170,16 @@ struct Dns {
         launches += 3;
         // Neumann data for the pressure: hq2 at the walls (:272-281)
         const long long np = (long long)nx * nz;
-        get_planes_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(hq[1], hb, ht, nx, ny, nz);
+        { ProfScope ps(PC_ELEMENTWISE);
+        get_planes_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(hq[1], hb, ht, nx, ny, nz); }
         launches++;
         if ((rc = poisson().solve(tmp1, c1, c2, hb, ht, tmp3))) return rc;     // (:284)
         launches += 3;   // boundary planes, regular modes, singular modes (cuFFT's own kernels not counted)
         // hq -= grad p (:319-352)
         if ((rc = run_partial(1, TLAB_OPR_P1, nx, ny, nz, b0, g[0], tmp1, hq[0], nullptr, nullptr, 0.0, -1))) return rc;
         if ((rc = run_partial(3, TLAB_OPR_P1, nx, ny, nz, b0, g[2], tmp1, hq[2], nullptr, nullptr, 0.0, -1))) return rc;
-        sub_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(hq[1], tmp3, N);
+        { ProfScope ps(PC_ELEMENTWISE);
+        sub_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(hq[1], tmp3, N); }
         launches += 3;
         // boundary conditions (:356-398)
         for (int f = 0; f < 3 + ns; f++) {
@@ -190,7 +193,8 @@ struct Dns {
                 if ((rc = run_neumann_y(ibc, nx, ny, nz, g[1], h, hb, ht))) return rc;
                 launches++;
             }
-            set_planes_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(h, hb, ht, ibc & 1, (ibc >> 1) & 1, nx, ny, nz);
+            { ProfScope ps(PC_ELEMENTWISE);
+            set_planes_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(h, hb, ht, ibc & 1, (ibc >> 1) & 1, nx, ny, nz); }
             launches++;
         }
         return cuda_check(cudaGetLastError(), "rhs");
@@ -202,6 +206,7 @@ struct Dns {
         if (rc) return rc;
         if ((rc = rhs(dte))) return rc;
         cudaStream_t st = ctx().stream;
+        ProfScope ps(PC_ELEMENTWISE);
         for (int f = 0; f < 3; f++)
             rk_update_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(q[f], hq[f], dte, kcoef, scale_h, 0, 0.0, 0.0, N);
         for (int is = 0; is < ns; is++)
@@ -211,17 +216,24 @@ struct Dns {
         return cuda_check(cudaGetLastError(), "rk update");
     }
 
-    int runge_kutta(double dtime) {
+    int stage(double dtime, int sub) {
         cudaStream_t st = ctx().stream;
-        for (double* h : hq) cudaMemsetAsync(h, 0, (size_t)N * sizeof(double), st);
-        for (double* h : hs) cudaMemsetAsync(h, 0, (size_t)N * sizeof(double), st);
         const int nsub = (int)kdt.size();
-        for (int sub = 0; sub < nsub; sub++) {
-            const double dte = dtime * kdt[sub];
-            const bool last = (sub == nsub - 1);
-            int rc = substep(dte, last ? 0.0 : kco[sub], last ? 0 : 1);
-            if (rc) return rc;
+        if (sub < 0 || sub >= nsub) return fail(TLAB_ERR_OPTION, "Runge-Kutta stage out of range");
+        if (sub == 0) {
+            ProfScope ps(PC_ELEMENTWISE);
+            for (double* h : hq) cudaMemsetAsync(h, 0, (size_t)N * sizeof(double), st);
+            for (double* h : hs) cudaMemsetAsync(h, 0, (size_t)N * sizeof(double), st);
         }
+        const double dte = dtime * kdt[sub];
+        const bool last = (sub == nsub - 1);
+        return substep(dte, last ? 0.0 : kco[sub], last ? 0 : 1);
+    }
+
+    int runge_kutta(double dtime) {
+        const int nsub = (int)kdt.size();
+        for (int sub = 0; sub < nsub; sub++)
+            if (int rc = stage(dtime, sub)) return rc;
         return 0;
     }
 
@@ -331,6 +343,12 @@ int tlab_time_substep(tlab_dns_t h, double dte, double kco, int scale_h) {
 int tlab_rhs_global_incompressible_1(tlab_dns_t h, double dte) {
     if (!h) return fail(TLAB_ERR_OPTION, "null state");
     if (int rc = h->d.rhs(dte)) return rc;
+    return finish();
+}
+
+int tlab_time_rungekutta_stage(tlab_dns_t h, double dtime, int stage) {
+    if (!h) return fail(TLAB_ERR_OPTION, "tlab_time_rungekutta_stage: null state");
+    if (int rc = h->d.stage(dtime, stage)) return rc;
     return finish();
 }
 

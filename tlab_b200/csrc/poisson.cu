@@ -554,17 +554,22 @@ int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const do
     if (!ready) return fail(TLAB_ERR_OPTION, "OPR_Poisson called before OPR_Elliptic_Initialize");
     cudaStream_t st = ctx().stream;
     {
+        ProfScope ps(PC_FFT);
         const long long np = (long long)nx * nz;
         poisson_set_bcs_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(p, hb, ht, nx, ny, nz);
+        if (int rc = cufft_check(cufftExecD2Z(plan_fx, p, (cufftDoubleComplex*)c1), "cufftExecD2Z")) return rc;
+        if (nz > 1)
+            if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)c1, (cufftDoubleComplex*)c1, CUFFT_FORWARD), "cufftExecZ2Z fwd")) return rc;
     }
-    if (int rc = cufft_check(cufftExecD2Z(plan_fx, p, (cufftDoubleComplex*)c1), "cufftExecD2Z")) return rc;
-    if (nz > 1)
-        if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)c1, (cufftDoubleComplex*)c1, CUFFT_FORWARD), "cufftExecZ2Z fwd")) return rc;
-    const int threads = 128;
-    const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
-    poisson_modes_kernel<<<blocks, threads, 0, st>>>(D, c1, c2);
-    poisson_singular_kernel<<<1, 4, 0, st>>>(D, c1, c2);
-    if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
+    {
+        ProfScope ps(PC_POISSON_Y);
+        const int threads = 128;
+        const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
+        poisson_modes_kernel<<<blocks, threads, 0, st>>>(D, c1, c2);
+        poisson_singular_kernel<<<1, 4, 0, st>>>(D, c1, c2);
+        if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
+    }
+    ProfScope ps2(PC_FFT);
     if (nz > 1)
         if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)c1, (cufftDoubleComplex*)c1, CUFFT_INVERSE), "cufftExecZ2Z inv")) return rc;
     if (int rc = cufft_check(cufftExecZ2D(plan_bx, (cufftDoubleComplex*)c1, p), "cufftExecZ2D")) return rc;

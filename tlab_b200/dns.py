@@ -82,6 +82,9 @@ class Dns:
     def substep(self, dte, kco=0.0, scale_h=False):
         _lib.check(_lib.load().tlab_time_substep(self.handle, float(dte), float(kco), int(scale_h)))
 
+    def runge_kutta_stage(self, dtime, stage):
+        _lib.check(_lib.load().tlab_time_rungekutta_stage(self.handle, float(dtime), int(stage)))
+
     def runge_kutta(self, dtime):
         """TIME_RUNGEKUTTA (time.f90:185-333)"""
         _lib.check(_lib.load().tlab_time_rungekutta(self.handle, float(dtime)))

@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""Operator-level bandwidth table (BASELINE.json configs[1]: compact FD d/dx, d2/dx2 on 512^3, non-uniform y).
+
+Times OPR_Partial / OPR_Burgers / OPR_Poisson calls through the C ABI with CUDA events on the library stream
+and prints achieved GB/s against the algorithmic bytes of SURVEY.md 8(d) (P1/P2 16 B/pt, P2_P1 24, Burgers
+SELF 16 / U_IN 24, Poisson 120 with 24 alongside)."""
+import argparse
+import ctypes
+import json
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+from bench import grid_periodic, grid_tanh, load_peaks  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="512,512,512")
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--lines-x", default="0")
+    ap.add_argument("--lines-yz", default="0")
+    ap.add_argument("--poisson", action="store_true")
+    ap.add_argument("--json", default="")
+    args = ap.parse_args()
+    import torch
+    from tlab_b200 import lib as tl, opr
+    L = tl.load()
+    dev = torch.device("cuda:0")
+    nx, ny, nz = [int(v) for v in args.shape.split(",")]
+    N = nx * ny * nz
+    x, z, y = grid_periodic(nx), grid_periodic(nz), grid_tanh(ny)
+    g = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, False, name="y"), opr.FdmPlan(z, True, True, name="z")]
+    opr.OPR_Burgers_Initialize(g, 1.0 / 5000.0, [1.0])
+    u = torch.randn(N, dtype=torch.float64, device=dev)
+    v = torch.randn(N, dtype=torch.float64, device=dev)
+    r1 = torch.empty_like(u)
+    r2 = torch.empty_like(u)
+    sp = ctypes.c_void_p()
+    tl.check(L.tlab_gpu_stream(ctypes.byref(sp)))
+    stream = torch.cuda.ExternalStream(sp.value, device=dev)
+    peak, kind = load_peaks()
+    bcs = [[0, 0], [0, 0]]
+    P = [opr.OPR_Partial_X, opr.OPR_Partial_Y, opr.OPR_Partial_Z]
+    B = [opr.OPR_Burgers_X, opr.OPR_Burgers_Y, opr.OPR_Burgers_Z]
+    rows = []
+
+    def timeit(fn, nbytes, label):
+        tl.check(L.tlab_gpu_set_async(1))
+        for _ in range(args.warmup):
+            fn()
+        tl.check(L.tlab_gpu_synchronize())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.iters):
+            fn()
+        e1.record(stream)
+        tl.check(L.tlab_gpu_synchronize())
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.iters
+        gbs = nbytes / (ms * 1e-3) / 1e9
+        rows.append({"op": label, "ms": ms, "GBs": gbs, "frac_measured_peak": gbs / peak, "frac_8TBs": gbs / 8000.0})
+        print("%-34s %9.3f ms %9.1f GB/s  %5.1f%% of %s peak %.0f  (%4.1f%% of 8 TB/s)" %
+              (label, ms, gbs, 100 * gbs / peak, kind, peak, 100 * gbs / 8000.0), flush=True)
+        tl.check(L.tlab_gpu_set_async(0))
+
+    for lx in [int(s) for s in args.lines_x.split(",")]:
+        for lyz in [int(s) for s in args.lines_yz.split(",")]:
+            tl.check(L.tlab_gpu_set_tuning(b"lines_x", lx))
+            tl.check(L.tlab_gpu_set_tuning(b"lines_yz", lyz))
+            tag = " [Lx=%d Lyz=%d]" % (lx, lyz)
+            for d, nm in enumerate("xyz"):
+                timeit(lambda: P[d](opr.OPR_P1, nx, ny, nz, bcs, g[d], u, r1), 16 * N, "OPR_Partial_%s P1" % nm.upper() + tag)
+                timeit(lambda: P[d](opr.OPR_P2, nx, ny, nz, bcs, g[d], u, r1), 16 * N, "OPR_Partial_%s P2" % nm.upper() + tag)
+                timeit(lambda: P[d](opr.OPR_P2_P1, nx, ny, nz, bcs, g[d], u, r1, r2), 24 * N, "OPR_Partial_%s P2_P1" % nm.upper() + tag)
+                timeit(lambda: B[d](opr.OPR_B_SELF, 0, nx, ny, nz, bcs, u, u, r1), 16 * N, "OPR_Burgers_%s SELF" % nm.upper() + tag)
+                timeit(lambda: B[d](opr.OPR_B_U_IN, 1, nx, ny, nz, bcs, u, v, r1), 24 * N, "OPR_Burgers_%s U_IN" % nm.upper() + tag)
+    if args.poisson:
+        opr.OPR_Elliptic_Initialize(g)
+        t1 = torch.zeros((nx + 2) * ny * nz, dtype=torch.float64, device=dev)
+        t2 = torch.zeros_like(t1)
+        hb = torch.zeros(nx * nz, dtype=torch.float64, device=dev)
+        ht = torch.zeros_like(hb)
+        p = u.clone()
+        timeit(lambda: opr.OPR_Poisson(nx, ny, nz, 3, p, t1, t2, hb, ht, r1), 120 * N, "OPR_Poisson (120 B/pt model)")
+        rows[-1]["GBs_at_24B_floor"] = rows[-1]["GBs"] * 24.0 / 120.0
+    if args.json:
+        json.dump({"shape": [nx, ny, nz], "peak_GBs": peak, "peak_kind": kind, "rows": rows}, open(args.json, "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
