@@ -41,86 +41,161 @@ __device__ __forceinline__ Chunk make_chunk(int t, int T, int cbase, int crem) {
 }
 
 __device__ __forceinline__ double ldro(const double* p) { return __ldg(p); }
+__device__ __forceinline__ double2 ldro2(const double2* p) { return __ldg(p); }
 
 // ------------------------------------------------------------------------------------------------
-// factored tridiagonal solve on register chunks; sm_f / sm_b: [T*L] exchange buffers,
-// sm_p: [T*L], sm_q: [ceil(T/8)*L + L] (periodic only)
-template <bool PER>
-__device__ __forceinline__ void solve_tri(double (&f)[CHUNK], const Chunk& c, const SolveTab& S, int l, int L,
-                                          double* sm_f, double* sm_b, double* sm_p, double* sm_q) {
-    const int base = c.s0 - c.j0;     // coefficient index of register slot j is base + j
+// NS factored tridiagonal systems solved together on register chunks (shared barriers, independent
+// dependency chains).  Exchange area per system: sm_f[T*L], sm_b[T*L], sm_p[T*L], sm_q[(T8+1)*L].
+__host__ __device__ inline int exch_per_system(int T, int L) { return 3 * T * L + (((T + 7) >> 3) + 1) * L; }
+
+template <bool PER, bool FULL, int NS>
+__device__ __forceinline__ void solve_tri(double (&f)[NS][CHUNK], const Chunk& c, const SolveTab* S, int l, int L,
+                                          double* sm) {
     const int j1 = c.j0 + c.cnt;
-    // ---- forward substitution
-    {
-        double e = 0.0;
+    const int TL = c.T * L;
+    const int T8 = (c.T + 7) >> 3;
+    const int per_sys = exch_per_system(c.T, L);
+    // record of register slot j: rp[j * 2*REC_GROUP] = {alpha, beta}, rp[j * 2*REC_GROUP + 1] = {gamma, delta|pe}
+    const size_t rbase = ((size_t)(c.t / REC_GROUP) * CHUNK) * REC_GROUP + c.t % REC_GROUP;
+    constexpr int RS = 2 * REC_GROUP;
+    ChunkDesc cd[NS];
+    const double2* rp[NS];
 #pragma unroll
-        for (int j = 0; j < CHUNK; j++) {
-            if (j >= c.j0 && j < j1) {
-                const double a = ldro(S.alpha + base + j);
-                if (PER) e = f[j] * ldro(S.beta + base + j) + a * e;
-                else e = f[j] + a * e;
+    for (int s = 0; s < NS; s++) {
+        cd[s] = S[s].cd[c.t];
+        rp[s] = S[s].rec + 2 * rbase;
+    }
+
+    // ---- forward substitution: local recurrence with zero inflow
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        double e = 0.0;
+        if (cd[s].flags & CD_FWD_CONST) {
+            const double a = cd[s].a, b = cd[s].b;
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) {
+                if (PER) e = f[s][j] * b + a * e;
+                else e = f[s][j] + a * e;
+                f[s][j] = e;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) {
+                if (FULL || (j >= c.j0 && j < j1)) {
+                    const double2 ab = ldro2(rp[s] + j * RS);
+                    if (PER) e = f[s][j] * ab.y + ab.x * e;
+                    else e = f[s][j] + ab.x * e;
+                    f[s][j] = e;
+                }
             }
         }
-        sm_f[c.t * L + l] = e;
-        __syncthreads();
-        double cin = 0.0;
-        for (int k = max(0, c.t - S.Wf); k < c.t; k++) cin = sm_f[k * L + l] + ldro(S.Af + k) * cin;
-        double y = cin;
+        sm[s * per_sys + c.t * L + l] = e;
+    }
+    __syncthreads();
 #pragma unroll
-        for (int j = 0; j < CHUNK; j++) {
-            if (j >= c.j0 && j < j1) {
-                const double a = ldro(S.alpha + base + j);
-                if (PER) y = f[j] * ldro(S.beta + base + j) + a * y;
-                else y = f[j] + a * y;
-                f[j] = y;
+    for (int s = 0; s < NS; s++) {
+        const double* sm_f = sm + s * per_sys;
+        double cin = 0.0;
+        for (int k = max(0, c.t - S[s].Wf); k < c.t; k++) cin = sm_f[k * L + l] + ldro(&S[s].cd[k].Af) * cin;
+        if (c.t > 0) {
+            // inflow correction: corr_j = alpha_j corr_{j-1}, corr_{-1} = inflow
+            double corr = cin;
+            if (cd[s].flags & CD_FWD_CONST) {
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++) { corr = cd[s].a * corr; f[s][j] = f[s][j] + corr; }
+            } else {
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++)
+                    if (FULL || (j >= c.j0 && j < j1)) { corr = ldro(&rp[s][j * RS].x) * corr; f[s][j] = f[s][j] + corr; }
             }
         }
     }
-    double xN = 0.0;
+    double xN[NS];
+#pragma unroll
+    for (int s = 0; s < NS; s++) xN[s] = 0.0;
     if (PER) {
         // ---- rank-one closure of the circulant system: x_N = (y_N - sum d_i y_i) * b_N
-        double part = 0.0;
 #pragma unroll
-        for (int j = 0; j < CHUNK; j++)
-            if (j >= c.j0 && j < j1) part = part + ldro(S.pd + base + j) * f[j];
-        const int T8 = (c.T + 7) >> 3;
-        sm_p[c.t * L + l] = part;
-        if (c.t == c.T - 1) sm_q[T8 * L + l] = f[CHUNK - 1];
+        for (int s = 0; s < NS; s++) {
+            double part = 0.0;
+            if (!(cd[s].flags & CD_PD_ZERO)) {
+                const double* pdp = S[s].pd + rbase;
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++)
+                    if (FULL || (j >= c.j0 && j < j1)) part = part + ldro(pdp + j * REC_GROUP) * f[s][j];
+            }
+            double* sm_p = sm + s * per_sys + 2 * TL;
+            double* sm_q = sm_p + TL;
+            sm_p[c.t * L + l] = part;
+            if (c.t == c.T - 1) sm_q[T8 * L + l] = f[s][CHUNK - 1];
+        }
         __syncthreads();
         if (c.t < T8) {
-            double q = 0.0;
-            for (int k = c.t * 8; k < min(c.T, c.t * 8 + 8); k++) q = q + sm_p[k * L + l];
-            sm_q[c.t * L + l] = q;
-        }
-        __syncthreads();
-        double wrk = 0.0;
-        for (int k = 0; k < T8; k++) wrk = wrk + sm_q[k * L + l];
-        xN = (sm_q[T8 * L + l] - wrk) * S.bN;
-        if (c.t == c.T - 1) f[CHUNK - 1] = xN;
-    }
-    // ---- backward substitution
-    {
-        double e = 0.0;
 #pragma unroll
-        for (int j = CHUNK - 1; j >= 0; j--) {
-            if (j >= c.j0 && j < j1) {
-                const double g = ldro(S.gamma + base + j);
-                if (PER) e = (f[j] + g * e) + ldro(S.pe + base + j) * xN;
-                else e = (f[j] + g * e) * ldro(S.delta + base + j);
+            for (int s = 0; s < NS; s++) {
+                double* sm_p = sm + s * per_sys + 2 * TL;
+                double* sm_q = sm_p + TL;
+                double q = 0.0;
+                for (int k = c.t * 8; k < min(c.T, c.t * 8 + 8); k++) q = q + sm_p[k * L + l];
+                sm_q[c.t * L + l] = q;
             }
         }
-        sm_b[c.t * L + l] = e;
         __syncthreads();
-        double cin = 0.0;
-        for (int k = min(c.T - 1, c.t + S.Wb); k > c.t; k--) cin = sm_b[k * L + l] + ldro(S.Ab + k) * cin;
-        double x = cin;
 #pragma unroll
-        for (int j = CHUNK - 1; j >= 0; j--) {
-            if (j >= c.j0 && j < j1) {
-                const double g = ldro(S.gamma + base + j);
-                if (PER) x = (f[j] + g * x) + ldro(S.pe + base + j) * xN;
-                else x = (f[j] + g * x) * ldro(S.delta + base + j);
-                f[j] = x;
+        for (int s = 0; s < NS; s++) {
+            const double* sm_q = sm + s * per_sys + 3 * TL;
+            double wrk = 0.0;
+            for (int k = 0; k < T8; k++) wrk = wrk + sm_q[k * L + l];
+            xN[s] = (sm_q[T8 * L + l] - wrk) * S[s].bN;
+            if (c.t == c.T - 1) f[s][CHUNK - 1] = xN[s];
+        }
+    }
+    // ---- backward substitution
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        double e = 0.0;
+        if (cd[s].flags & CD_BWD_CONST) {
+            const double g = cd[s].g, d = cd[s].d;
+#pragma unroll
+            for (int j = CHUNK - 1; j >= 0; j--) {
+                if (PER) e = f[s][j] + g * e;
+                else e = (f[s][j] + g * e) * d;
+                f[s][j] = e;
+            }
+        } else {
+#pragma unroll
+            for (int j = CHUNK - 1; j >= 0; j--) {
+                if (FULL || (j >= c.j0 && j < j1)) {
+                    const double2 gd = ldro2(rp[s] + j * RS + 1);
+                    if (PER) e = (f[s][j] + gd.x * e) + gd.y * xN[s];
+                    else e = (f[s][j] + gd.x * e) * gd.y;
+                    f[s][j] = e;
+                }
+            }
+        }
+        sm[s * per_sys + TL + c.t * L + l] = e;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const double* sm_b = sm + s * per_sys + TL;
+        double cin = 0.0;
+        for (int k = min(c.T - 1, c.t + S[s].Wb); k > c.t; k--) cin = sm_b[k * L + l] + ldro(&S[s].cd[k].Ab) * cin;
+        if (c.t < c.T - 1) {
+            double corr = cin;
+            if (cd[s].flags & CD_BWD_CONST) {
+                const double m = PER ? cd[s].g : cd[s].g * cd[s].d;
+#pragma unroll
+                for (int j = CHUNK - 1; j >= 0; j--) { corr = m * corr; f[s][j] = f[s][j] + corr; }
+            } else {
+#pragma unroll
+                for (int j = CHUNK - 1; j >= 0; j--) {
+                    if (FULL || (j >= c.j0 && j < j1)) {
+                        const double2 gd = ldro2(rp[s] + j * RS + 1);
+                        corr = (PER ? gd.x : gd.x * gd.y) * corr;
+                        f[s][j] = f[s][j] + corr;
+                    }
+                }
             }
         }
     }
@@ -228,47 +303,53 @@ __device__ __forceinline__ void add_jacobian_term(double (&f2)[CHUNK], const dou
 }
 
 // ------------------------------------------------------------------------------------------------
-// shared-memory exchange area (doubles): [sm_f T*L][sm_b T*L][sm_p T*L][sm_q (T8+1)*L][sm_h 2*T*L]
+// shared-memory exchange area (doubles): two systems' buffers + [sm_h 2*T*L] for the Jacobian-term halo
 __host__ __device__ inline size_t exch_doubles(int T, int L) {
-    return (size_t)T * L * 5 + (size_t)(((T + 7) >> 3) + 1) * L;
+    return (size_t)2 * exch_per_system(T, L) + (size_t)2 * T * L;
 }
 
-template <int MODE, bool PER, bool NEED1>
+template <int MODE, bool PER, bool NEED1, bool FULL>
 __device__ __forceinline__ void line_core(double (&u)[CHUNK + 6], const double (&wb)[BROW_W], const double (&wt)[BROW_W],
                                           const Chunk& c, const LineArgs& a, int l, int L, double* sm,
-                                          double (&d1)[CHUNK], double (&d2)[CHUNK]) {
-    double* sm_f = sm;
-    double* sm_b = sm_f + c.T * L;
-    double* sm_p = sm_b + c.T * L;
-    double* sm_q = sm_p + c.T * L;
-    double* sm_h = sm_q + (((c.T + 7) >> 3) + 1) * L;
+                                          double (&d)[2][CHUNK]) {
+    // d[0]: first derivative, d[1]: second derivative
+    double* sm_h = sm + 2 * exch_per_system(c.T, L);
     constexpr bool WANT1 = (MODE == MODE_P1) || (MODE == MODE_P2_P1) || (MODE == MODE_BURGERS) ||
                            (MODE == MODE_NEUMANN) || NEED1;
     constexpr bool WANT2 = (MODE == MODE_P2) || (MODE == MODE_P2_P1) || (MODE == MODE_BURGERS);
     if (WANT1) {
-        rhs_interior<false>(u, d1, a.rhs1);
+        rhs_interior<false>(u, d[0], a.rhs1);
         if (!PER) {
-            if (c.t == 0) rhs_bottom(wb, d1, a.rhs1);
-            if (c.t == c.T - 1) rhs_top(wt, d1, a.rhs1);
+            if (c.t == 0) rhs_bottom(wb, d[0], a.rhs1);
+            if (c.t == c.T - 1) rhs_top(wt, d[0], a.rhs1);
         }
     }
     if (WANT2) {
-        rhs_interior<true>(u, d2, a.rhs2);
+        rhs_interior<true>(u, d[1], a.rhs2);
         if (!PER) {
-            if (c.t == 0) rhs_bottom(wb, d2, a.rhs2);
-            if (c.t == c.T - 1) rhs_top(wt, d2, a.rhs2);
+            if (c.t == 0) rhs_bottom(wb, d[1], a.rhs2);
+            if (c.t == c.T - 1) rhs_top(wt, d[1], a.rhs2);
         }
     }
-    if (WANT1) solve_tri<PER>(d1, c, a.lu1, l, L, sm_f, sm_b, sm_p, sm_q);
-    if (WANT2) {
-        if (NEED1) add_jacobian_term(d2, d1, c, a.rhs_d1, a.n, l, L, sm_h);
-        solve_tri<PER>(d2, c, a.lu2, l, L, sm_f, sm_b, sm_p, sm_q);
+    if (WANT1 && WANT2 && !NEED1) {
+        const SolveTab S[2] = {a.lu1, a.lu2};
+        solve_tri<PER, FULL, 2>(d, c, S, l, L, sm);
+    } else {
+        if (WANT1) {
+            double (&d1)[1][CHUNK] = reinterpret_cast<double (&)[1][CHUNK]>(d[0]);
+            solve_tri<PER, FULL, 1>(d1, c, &a.lu1, l, L, sm);
+        }
+        if (WANT2) {
+            if (NEED1) add_jacobian_term(d[1], d[0], c, a.rhs_d1, a.n, l, L, sm_h);
+            double (&d2)[1][CHUNK] = reinterpret_cast<double (&)[1][CHUNK]>(d[1]);
+            solve_tri<PER, FULL, 1>(d2, c, &a.lu2, l, L, sm);
+        }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // y / z directions: lines strided in memory, contiguous across lines
-template <int MODE, bool PER, bool NEED1>
+template <int MODE, bool PER, bool NEED1, bool FULL>
 __global__ void __launch_bounds__(512) line_kernel_strided(LineArgs a) {
     extern __shared__ double sm[];
     const int L = a.L;
@@ -284,14 +365,39 @@ __global__ void __launch_bounds__(512) line_kernel_strided(LineArgs a) {
     const int n = a.n;
 
     double u[CHUNK + 6];
+    if (FULL) {
+        // every chunk holds CHUNK points: 16 loads at a fixed stride plus two 3-point halos (wrapped or zero)
+        const double* __restrict__ pc = up + (long long)c.s0 * st;
+        const double* __restrict__ p2 = (a.u2 != nullptr) ? a.u2 + lbase + (long long)c.s0 * st : nullptr;
+        const bool lok = PER || c.t > 0, rok = PER || c.t < c.T - 1;
+        const long long loff = (c.t > 0) ? -3 * st : (long long)(n - 3 - c.s0) * st;
+        const long long roff = (c.t < c.T - 1) ? (long long)CHUNK * st : -(long long)c.s0 * st;
 #pragma unroll
-    for (int k = 0; k < CHUNK + 6; k++) {
-        int p = c.s0 - 3 + (k - c.j0);
-        const bool in_win = (k >= c.j0) && (k < c.j0 + c.cnt + 6);
-        if (PER) p = (p < 0) ? p + n : (p >= n ? p - n : p);
-        const bool ok = in_win && p >= 0 && p < n;
-        u[k] = ok ? __ldcs(up + (long long)p * st) : 0.0;
-        if (a.u2 != nullptr && ok) u[k] = u[k] + __ldcs(a.u2 + lbase + (long long)p * st) * a.scale;
+        for (int j = 0; j < CHUNK; j++) u[j + 3] = __ldcs(pc + j * st);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            u[k] = lok ? __ldcs(pc + loff + k * st) : 0.0;
+            u[CHUNK + 3 + k] = rok ? __ldcs(pc + roff + k * st) : 0.0;
+        }
+        if (p2 != nullptr) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) u[j + 3] = u[j + 3] + __ldcs(p2 + j * st) * a.scale;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (lok) u[k] = u[k] + __ldcs(p2 + loff + k * st) * a.scale;
+                if (rok) u[CHUNK + 3 + k] = u[CHUNK + 3 + k] + __ldcs(p2 + roff + k * st) * a.scale;
+            }
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CHUNK + 6; k++) {
+            int p = c.s0 - 3 + (k - c.j0);
+            const bool in_win = (k >= c.j0) && (k < c.j0 + c.cnt + 6);
+            if (PER) p = (p < 0) ? p + n : (p >= n ? p - n : p);
+            const bool ok = in_win && p >= 0 && p < n;
+            u[k] = ok ? __ldcs(up + (long long)p * st) : 0.0;
+            if (a.u2 != nullptr && ok) u[k] = u[k] + __ldcs(a.u2 + lbase + (long long)p * st) * a.scale;
+        }
     }
     double wb[BROW_W], wt[BROW_W];
     if (!PER) {
@@ -301,8 +407,10 @@ __global__ void __launch_bounds__(512) line_kernel_strided(LineArgs a) {
             wt[k] = (c.t == c.T - 1) ? u[3 + CHUNK - 1 - k] : 0.0;
         }
     }
-    double d1[CHUNK], d2[CHUNK];
-    line_core<MODE, PER, NEED1>(u, wb, wt, c, a, l, L, sm, d1, d2);
+    double dd[2][CHUNK];
+    line_core<MODE, PER, NEED1, FULL>(u, wb, wt, c, a, l, L, sm, dd);
+    double (&d1)[CHUNK] = dd[0];
+    double (&d2)[CHUNK] = dd[1];
 
     const int j1 = c.j0 + c.cnt;
     if (MODE == MODE_NEUMANN) {
@@ -321,23 +429,42 @@ __global__ void __launch_bounds__(512) line_kernel_strided(LineArgs a) {
         }
         return;
     }
-    double* __restrict__ o1 = a.out1 + lbase;
-    double* __restrict__ o2 = (MODE == MODE_P2_P1) ? a.out2 + lbase : nullptr;
-    const double* __restrict__ vp = (MODE == MODE_BURGERS) ? a.vel + lbase : nullptr;
+    double* __restrict__ o1 = a.out1 + lbase + (long long)(c.s0 - c.j0) * st;
+    double* __restrict__ o2 = (MODE == MODE_P2_P1) ? a.out2 + lbase + (long long)(c.s0 - c.j0) * st : nullptr;
+    const double* __restrict__ vp = (MODE == MODE_BURGERS) ? a.vel + lbase + (long long)(c.s0 - c.j0) * st : nullptr;
+    if (!active) return;
+    double vv[CHUNK];
+    if (MODE == MODE_BURGERS) {
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++)
+            if (FULL || (j >= c.j0 && j < j1)) vv[j] = __ldcs(vp + j * st);
+        if (a.accumulate != 0) {
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++)
+                if (FULL || (j >= c.j0 && j < j1)) {
+                    const double r = d2[j] - vv[j] * d1[j];
+                    vv[j] = __ldcs(o1 + j * st);
+                    d2[j] = (a.accumulate > 0) ? vv[j] + r : vv[j] - r;
+                }
+        } else {
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++)
+                if (FULL || (j >= c.j0 && j < j1)) d2[j] = d2[j] - vv[j] * d1[j];
+        }
+    } else if (MODE == MODE_P1 && a.accumulate != 0) {
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++)
+            if (FULL || (j >= c.j0 && j < j1)) {
+                const double o = __ldcs(o1 + j * st);
+                d1[j] = (a.accumulate > 0) ? o + d1[j] : o - d1[j];
+            }
+    }
 #pragma unroll
     for (int j = 0; j < CHUNK; j++) {
-        if (active && j >= c.j0 && j < j1) {
-            const long long off = (long long)(c.s0 + j - c.j0) * st;
-            if (MODE == MODE_P1) o1[off] = (a.accumulate == 0) ? d1[j] : (a.accumulate > 0 ? o1[off] + d1[j] : o1[off] - d1[j]);
-            if (MODE == MODE_P2) o1[off] = d2[j];
-            if (MODE == MODE_P2_P1) { o1[off] = d2[j]; o2[off] = d1[j]; }
-            if (MODE == MODE_BURGERS) {
-                const double v = __ldcs(vp + off);
-                double r = d2[j] - v * d1[j];
-                if (a.accumulate > 0) r = o1[off] + r;
-                else if (a.accumulate < 0) r = o1[off] - r;
-                o1[off] = r;
-            }
+        if (FULL || (j >= c.j0 && j < j1)) {
+            if (MODE == MODE_P1) __stcs(o1 + j * st, d1[j]);
+            if (MODE == MODE_P2 || MODE == MODE_BURGERS) __stcs(o1 + j * st, d2[j]);
+            if (MODE == MODE_P2_P1) { __stcs(o1 + j * st, d2[j]); __stcs(o2 + j * st, d1[j]); }
         }
     }
 }
@@ -346,7 +473,7 @@ __global__ void __launch_bounds__(512) line_kernel_strided(LineArgs a) {
 // x direction: lines contiguous in memory; a tile of L lines is staged through padded shared memory
 __device__ __forceinline__ int xpos(int i) { return i + (i >> 4); }
 
-template <int MODE, bool PER, bool NEED1>
+template <int MODE, bool PER, bool NEED1, bool FULL>
 __global__ void __launch_bounds__(512) line_kernel_contig(LineArgs a) {
     extern __shared__ double sm[];
     const int L = a.L;
@@ -394,13 +521,28 @@ __global__ void __launch_bounds__(512) line_kernel_contig(LineArgs a) {
     const int lr = (l < nl) ? l : 0;               // inactive lines redo line 0 (keeps barriers uniform)
     const double* row = tile + lr * S;
     double u[CHUNK + 6];
+    if (FULL) {
+        // s0 = 16 t, so xpos(s0 + j) = 17 t + j: the chunk and both halos sit at fixed offsets
+        const double* pc = row + c.s0 + c.t;
+        const bool lok = PER || c.t > 0, rok = PER || c.t < c.T - 1;
+        const double* pl = (c.t > 0) ? pc - 4 : row + (n + c.T - 4);
+        const double* pr = (c.t < c.T - 1) ? pc + CHUNK + 1 : row;
 #pragma unroll
-    for (int k = 0; k < CHUNK + 6; k++) {
-        int p = c.s0 - 3 + (k - c.j0);
-        const bool in_win = (k >= c.j0) && (k < c.j0 + c.cnt + 6);
-        if (PER) p = (p < 0) ? p + n : (p >= n ? p - n : p);
-        const bool ok = in_win && p >= 0 && p < n;
-        u[k] = ok ? row[xpos(ok ? p : 0)] : 0.0;
+        for (int j = 0; j < CHUNK; j++) u[j + 3] = pc[j];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            u[k] = lok ? pl[k] : 0.0;
+            u[CHUNK + 3 + k] = rok ? pr[k] : 0.0;
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < CHUNK + 6; k++) {
+            int p = c.s0 - 3 + (k - c.j0);
+            const bool in_win = (k >= c.j0) && (k < c.j0 + c.cnt + 6);
+            if (PER) p = (p < 0) ? p + n : (p >= n ? p - n : p);
+            const bool ok = in_win && p >= 0 && p < n;
+            u[k] = ok ? row[xpos(ok ? p : 0)] : 0.0;
+        }
     }
     double wb[BROW_W], wt[BROW_W];
     if (!PER) {
@@ -410,8 +552,10 @@ __global__ void __launch_bounds__(512) line_kernel_contig(LineArgs a) {
             wt[k] = (c.t == c.T - 1) ? u[3 + CHUNK - 1 - k] : 0.0;
         }
     }
-    double d1[CHUNK], d2[CHUNK];
-    line_core<MODE, PER, NEED1>(u, wb, wt, c, a, l, L, sm, d1, d2);
+    double dd[2][CHUNK];
+    line_core<MODE, PER, NEED1, FULL>(u, wb, wt, c, a, l, L, sm, dd);
+    double (&d1)[CHUNK] = dd[0];
+    double (&d2)[CHUNK] = dd[1];
     // all halo reads of the tile happened before the first barrier inside line_core; results may overwrite it
 
     const int j1 = c.j0 + c.cnt;
@@ -423,8 +567,8 @@ __global__ void __launch_bounds__(512) line_kernel_contig(LineArgs a) {
         if (l < nl) {
 #pragma unroll
             for (int j = 0; j < CHUNK; j++) {
-                if (j >= c.j0 && j < j1) {
-                    const int pp = xpos(c.s0 + j - c.j0);
+                if (FULL || (j >= c.j0 && j < j1)) {
+                    const int pp = FULL ? (c.s0 + c.t + j) : xpos(c.s0 + j - c.j0);
                     double r;
                     if (MODE == MODE_P1) r = d1[j];
                     else if (MODE == MODE_P2) r = d2[j];
@@ -462,7 +606,7 @@ __global__ void __launch_bounds__(512) line_kernel_contig(LineArgs a) {
     }
 }
 
-template <int MODE, bool PER, bool NEED1>
+template <int MODE, bool PER, bool NEED1, bool FULL>
 cudaError_t launch_one(const LineArgs& a, bool contig, cudaStream_t stream) {
     const int threads = a.L * a.T;
     const long long blocks = (a.nlines + a.L - 1) / a.L;
@@ -470,12 +614,12 @@ cudaError_t launch_one(const LineArgs& a, bool contig, cudaStream_t stream) {
     if (contig) {
         const bool two = (MODE == MODE_BURGERS) && (a.vel != a.u);
         smem += (size_t)a.L * a.xstride * sizeof(double) * (two ? 2 : 1);
-        auto k = line_kernel_contig<MODE, PER, NEED1>;
+        auto k = line_kernel_contig<MODE, PER, NEED1, FULL>;
         cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         k<<<(unsigned)blocks, threads, smem, stream>>>(a);
     } else {
-        auto k = line_kernel_strided<MODE, PER, NEED1>;
+        auto k = line_kernel_strided<MODE, PER, NEED1, FULL>;
         if (smem > 48 * 1024) {
             cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
@@ -487,9 +631,15 @@ cudaError_t launch_one(const LineArgs& a, bool contig, cudaStream_t stream) {
 
 template <int MODE>
 cudaError_t launch_mode(const LineArgs& a, bool per, bool need1, bool contig, cudaStream_t s) {
-    if (per) return launch_one<MODE, true, false>(a, contig, s);
-    if (need1) return launch_one<MODE, false, true>(a, contig, s);
-    return launch_one<MODE, false, false>(a, contig, s);
+    const bool full = (a.crem == 0 && a.cbase == CHUNK);      // every chunk holds exactly CHUNK points
+    if (full) {
+        if (per) return launch_one<MODE, true, false, true>(a, contig, s);
+        if (need1) return launch_one<MODE, false, true, true>(a, contig, s);
+        return launch_one<MODE, false, false, true>(a, contig, s);
+    }
+    if (per) return launch_one<MODE, true, false, false>(a, contig, s);
+    if (need1) return launch_one<MODE, false, true, false>(a, contig, s);
+    return launch_one<MODE, false, false, false>(a, contig, s);
 }
 
 }  // namespace

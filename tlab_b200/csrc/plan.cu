@@ -37,31 +37,66 @@ int window(const std::vector<double>& A, bool forward) {
     return std::max(T - 1, 0);
 }
 
+template <class T>
+const T* upload_t(DevPlan& p, const std::vector<T>& v) {
+    T* d = nullptr;
+    if (cudaMalloc(&d, std::max<size_t>(v.size(), 1) * sizeof(T)) != cudaSuccess) return nullptr;
+    cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    p.allocs.push_back(d);
+    return d;
+}
+
+bool nearly_const(const std::vector<double>& v, int s0, int c) {
+    double lo = v[s0], hi = v[s0];
+    for (int j = 1; j < c; j++) { lo = std::min(lo, v[s0 + j]); hi = std::max(hi, v[s0 + j]); }
+    return (hi - lo) <= std::ldexp(std::max(std::fabs(lo), std::fabs(hi)), -50);
+}
+
 void finish_solve(DevPlan& p, SolveTab& s, std::vector<double>& alpha, std::vector<double>& beta,
                   std::vector<double>& gamma, std::vector<double>& delta, std::vector<double>& pd,
                   std::vector<double>& pe, bool periodic) {
     const int T = p.T;
     std::vector<double> Af(T, 1.0), Ab(T, 1.0);
+    const int Tp = (T + REC_GROUP - 1) / REC_GROUP * REC_GROUP;
+    std::vector<double2> rec((size_t)Tp * CHUNK * 2, make_double2(0.0, 1.0));
+    std::vector<double> pdv((size_t)Tp * CHUNK, 0.0);
+    std::vector<ChunkDesc> cd(T);
+    double pdmax = 0.0, pemax = 0.0;
+    for (size_t i = 0; i < pd.size(); i++) { pdmax = std::max(pdmax, std::fabs(pd[i])); pemax = std::max(pemax, std::fabs(pe[i])); }
     for (int t = 0; t < T; t++) {
-        int s0 = chunk_start(p, t), c = chunk_cnt(p, t);
+        const int s0 = chunk_start(p, t), c = chunk_cnt(p, t);
+        const int j0 = (t == T - 1) ? CHUNK - c : 0;
         for (int j = 0; j < c; j++) {
-            Af[t] *= alpha[s0 + j];
-            Ab[t] *= periodic ? gamma[s0 + j] : gamma[s0 + j] * delta[s0 + j];
+            const size_t r = ((size_t)(t / REC_GROUP) * CHUNK + (j0 + j)) * REC_GROUP + t % REC_GROUP;
+            rec[2 * r] = make_double2(alpha[s0 + j], beta[s0 + j]);
+            rec[2 * r + 1] = make_double2(gamma[s0 + j], periodic ? pe[s0 + j] : delta[s0 + j]);
+            pdv[r] = pd[s0 + j];
         }
+        double w = 1.0;
+        for (int j = 0; j < c; j++) w *= alpha[s0 + j];
+        Af[t] = w;
+        w = 1.0;
+        for (int j = c - 1; j >= 0; j--) w *= periodic ? gamma[s0 + j] : gamma[s0 + j] * delta[s0 + j];
+        Ab[t] = w;
+        ChunkDesc& d = cd[t];
+        d.a = alpha[s0]; d.b = beta[s0]; d.g = gamma[s0]; d.d = periodic ? 1.0 : delta[s0];
+        d.Af = Af[t]; d.Ab = Ab[t]; d.flags = 0; d.pad = 0;
+        // terms below 2^-80 of the largest coefficient are dropped, like the look-back tails
+        bool pd0 = true, pe0 = true;
+        for (int j = 0; j < c; j++) {
+            if (std::fabs(pd[s0 + j]) > std::ldexp(pdmax, -80)) pd0 = false;
+            if (std::fabs(pe[s0 + j]) > std::ldexp(pemax, -80)) pe0 = false;
+        }
+        if (!periodic) { pd0 = true; pe0 = true; }
+        if (c == CHUNK && nearly_const(alpha, s0, c) && nearly_const(beta, s0, c)) d.flags |= CD_FWD_CONST;
+        if (c == CHUNK && nearly_const(gamma, s0, c) && (periodic ? pe0 : nearly_const(delta, s0, c))) d.flags |= CD_BWD_CONST;
+        if (pd0) d.flags |= CD_PD_ZERO;
     }
     s.Wf = window(Af, true);
     s.Wb = window(Ab, false);
-    s.alpha = upload(p, alpha);
-    s.gamma = upload(p, gamma);
-    s.Af = upload(p, Af);
-    s.Ab = upload(p, Ab);
-    if (periodic) {
-        s.beta = upload(p, beta);
-        s.pd = upload(p, pd);
-        s.pe = upload(p, pe);
-    } else {
-        s.delta = upload(p, delta);
-    }
+    s.rec = upload_t(p, rec);
+    s.cd = upload_t(p, cd);
+    s.pd = periodic ? upload(p, pdv) : nullptr;
 }
 
 // lu columns c0+1..c0+3 (c0+1..c0+5 periodic); rows nmin..nmax active; scale = diffusivity (1 = none)

@@ -13,18 +13,29 @@ constexpr int BROW_W = 8;        // columns a special row may touch (counted fro
 
 // One LU-factored tridiagonal system, rewritten as two first-order linear recurrences
 //   forward : y_i = f_i * beta_i + alpha_i * y_{i-1}
-//   backward: x_i = (y_i + gamma_i * x_{i+1} [+ pe_i * x_N]) * delta_i
+//   backward: x_i = (y_i + gamma_i * x_{i+1}) * delta_i            (non-periodic)
+//             x_i = (y_i + gamma_i * x_{i+1}) + pe_i * x_N         (circulant)
 // plus, for circulant systems, the rank-one closure x_N = (y_N - sum_i pd_i y_i) * bN.
 // Rows excluded by a homogeneous Neumann condition have alpha = gamma = 0 and a zero rhs row.
+// Per chunk, a descriptor says whether the coefficients are constant over the chunk (interior of a
+// uniform grid: the LU factors have converged), in which case the threads use scalars instead of tables.
+struct ChunkDesc {
+    double a, b, g, d;      // constant-chunk coefficients: alpha, beta, gamma, delta
+    double Af, Ab;          // product of the forward / backward multipliers over the chunk
+    int flags;              // CD_* bits
+    int pad;
+};
+enum { CD_FWD_CONST = 1, CD_BWD_CONST = 2, CD_PD_ZERO = 4 };
+
+// Coefficient records {alpha, beta, gamma, delta|pe} are stored per (chunk, register slot) and interleaved in
+// groups of REC_GROUP chunks: record (t, j) sits at index ((t / G) * CHUNK + j) * G + t % G.  The chunks of a warp
+// (tid = l + L*t) then read one 128-byte line per load, at an address that is a per-thread base plus a
+// compile-time offset.
+constexpr int REC_GROUP = 4;
 struct SolveTab {
-    const double* alpha = nullptr;
-    const double* beta = nullptr;    // periodic only
-    const double* gamma = nullptr;
-    const double* delta = nullptr;   // non-periodic only
-    const double* pd = nullptr;      // periodic only
-    const double* pe = nullptr;      // periodic only
-    const double* Af = nullptr;      // [T] product of alpha over each chunk
-    const double* Ab = nullptr;      // [T] product of gamma*delta over each chunk
+    const double2* rec = nullptr;    // [T padded][CHUNK] x {alpha, beta}, {gamma, delta|pe}, interleaved
+    const double* pd = nullptr;      // same indexing (one double per record), circulant only
+    const ChunkDesc* cd = nullptr;   // [T]
     double bN = 0.0;
     int Wf = 0, Wb = 0;              // look-back windows (in chunks), see DESIGN.md "chunked substitution"
 };

@@ -25,6 +25,7 @@ def main():
     ap.add_argument("--lines-yz", default="0")
     ap.add_argument("--poisson", action="store_true")
     ap.add_argument("--json", default="")
+    ap.add_argument("--only", default="", help="regular expression selecting the operator labels to run")
     args = ap.parse_args()
     import torch
     from tlab_b200 import lib as tl, opr
@@ -48,7 +49,11 @@ def main():
     B = [opr.OPR_Burgers_X, opr.OPR_Burgers_Y, opr.OPR_Burgers_Z]
     rows = []
 
+    import re
+
     def timeit(fn, nbytes, label):
+        if args.only and not re.search(args.only, label):
+            return
         tl.check(L.tlab_gpu_set_async(1))
         for _ in range(args.warmup):
             fn()
