@@ -141,13 +141,27 @@ int tlab_boundary_bcs_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_t gy,
                                 double* bcs_ht);
 
 /* OPR_Elliptic_Initialize, src/operators/opr_elliptic.f90:86-250 (FourierXZ_Factorize): eigenvalues from the
- * x/z modified wavenumbers, integral-operator tables in y, cuFFT plans, fundamental solutions per mode */
-int tlab_opr_elliptic_init(tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz);
+ * x/z modified wavenumbers, integral-operator tables in y, cuFFT plans, fundamental solutions per mode.
+ * kmax_local: thickness of this rank's z slab (0 or gz's size when the domain is not split) */
+int tlab_opr_elliptic_init(tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz, int kmax_local);
 /* OPR_Poisson(nx, ny, nz, ibc, p, tmp1, tmp2, bcs_hb, bcs_ht, dpdy), opr_elliptic.f90:263-364.
  * p: forcing in, solution out; tmp1, tmp2: work arrays of (nx+2)*ny*nz doubles (the reference's
  * isize_txc_field); dpdy may be NULL.  Only ibc = BCS_NN. */
 int tlab_opr_poisson(int nx, int ny, int nz, int ibc, double* p, double* tmp1, double* tmp2,
                      const double* bcs_hb, const double* bcs_ht, double* dpdy_or_null);
+
+/* ---- domain decomposition (z slabs, one process per GPU) -------------------------------------- */
+/* TLabMPI_Initialize + TLabMPI_Trp_Initialize, src/base/tlab_mpi_procs.f90:17-116, tlab_mpi_transpose.f90:68-200,
+ * for ims_npro_k = nranks, ims_npro_i = 1.  Rank 0 obtains a 128-byte NCCL id, the host broadcasts it
+ * (MPI_Bcast / torch.distributed), every rank calls tlab_mpi_init before creating plans that use it. */
+int tlab_mpi_get_unique_id(void* id_out_128);
+int tlab_mpi_init(int rank, int nranks, const void* id_128);
+int tlab_mpi_finalize(void);
+int tlab_mpi_rank(int* rank, int* nranks);
+/* TLabMPI_Trp_ExecK_Forward / _Backward (real or complex), tlab_mpi_transpose.f90:343-553: slab a(nlines_total, kmax)
+ * <-> pencil b(nlines_total/P, kmax*P); a and b are distinct device arrays of nlines_total*kmax elements */
+int tlab_trp_exec_k_forward(const double* a, double* b, int nlines_total, int kmax, int is_complex);
+int tlab_trp_exec_k_backward(const double* b, double* a, int nlines_total, int kmax, int is_complex);
 
 /* ---- time advance --------------------------------------------------------------------------- */
 /* Device-resident state: allocates q(3), s(nscal), hq, hs and work arrays (TLab_Initialize_Memory,

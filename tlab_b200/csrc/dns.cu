@@ -14,6 +14,7 @@
 #include "../../include/tlab_gpu.h"
 #include "context.h"
 #include "poisson.h"
+#include "trp.h"
 #include <vector>
 #include <string>
 #include <cstring>
@@ -113,6 +114,9 @@ struct Dns {
     double *tmp1 = nullptr, *tmp3 = nullptr, *c1 = nullptr, *c2 = nullptr;
     double *hb = nullptr, *ht = nullptr;
     double* bbackground = nullptr;
+    // z-slab decomposition: nz is the local slab thickness, nzg the global extent, pencils hold N points each
+    int P = 1, nzg = 0;
+    double *zs = nullptr, *zw = nullptr, *zr = nullptr;
     std::vector<double> kdt, ktime, kco;
     std::vector<void*> allocs;
     double* host_stage = nullptr;        // pinned staging buffer for the *_host entry points
@@ -142,16 +146,46 @@ struct Dns {
         return 0;
     }
 
+    // Burgers operator along z, accumulated into out; with a split domain through the z pencils
+    int burgers_z(int is, const double* sf, const double* w, double* out, bool self) {
+        if (P == 1) return run_burgers(3, is, nx, ny, nz, 0, g[2], sf, w, out, +1);
+        const long long nxy = (long long)nx * ny;
+        const int nl = (int)(nxy / P);
+        int rc = 0;
+        const double* zsf = zw;
+        if (!self) {
+            if ((rc = trp().forward(sf, nullptr, 0.0, zs, nxy, nz))) return rc;
+            zsf = zs;
+        }
+        if ((rc = run_burgers(3, is, nl, 1, nzg, 0, g[2], zsf, zw, zr, 0))) return rc;
+        return trp().backward(zr, out, nxy, nz, +1);
+    }
+
+    // out (+|-)= d/dz (a + scale*a2)
+    int partial_z(const double* a, const double* a2, double scale, double* out, int accumulate) {
+        if (P == 1) return run_partial(3, TLAB_OPR_P1, nx, ny, nz, 0, g[2], a, out, nullptr, a2, scale, accumulate);
+        const long long nxy = (long long)nx * ny;
+        const int nl = (int)(nxy / P);
+        int rc = 0;
+        if ((rc = trp().forward(a, a2, scale, zs, nxy, nz))) return rc;
+        if ((rc = run_partial(3, TLAB_OPR_P1, nl, 1, nzg, 0, g[2], zs, zr, nullptr))) return rc;
+        return trp().backward(zr, out, nxy, nz, accumulate);
+    }
+
     int rhs(double dte) {
         cudaStream_t st = ctx().stream;
         const int b0 = 0;   // bcs = 0: biased, non-zero (rhs_global_incompressible_1.f90:67)
         int rc = 0;
         auto B = [&](int dir, int is, const double* sf, const double* vel, double* out) {
             if (rc) return;
-            rc = run_burgers(dir, is, nx, ny, nz, b0, g[dir - 1], sf, vel, out, +1);
+            if (dir == 3) rc = burgers_z(is, sf, vel, out, sf == vel);
+            else rc = run_burgers(dir, is, nx, ny, nz, b0, g[dir - 1], sf, vel, out, +1);
             launches++;
         };
         double *u = q[0], *v = q[1], *w = q[2];
+        if (P > 1 && nzg > 1) {     // transposed w is shared by the four z operators (tmp6 of the reference)
+            if ((rc = trp().forward(w, nullptr, 0.0, zw, (long long)nx * ny, nz))) return rc;
+        }
         // hq1 += Bx(u,u) + By(u,v) + Bz(u,w)          (:98-111)
         B(1, 0, u, u, hq[0]); B(2, 0, u, v, hq[0]); B(3, 0, u, w, hq[0]);
         // hq2 += By(v,v) + Bx(v,u) + Bz(v,w)          (:99,115-123)
@@ -166,7 +200,7 @@ struct Dns {
         const double dummy = 1.0 / dte;
         if ((rc = run_partial(2, TLAB_OPR_P1, nx, ny, nz, b0, g[1], hq[1], tmp1, nullptr, v, dummy, 0))) return rc;
         if ((rc = run_partial(1, TLAB_OPR_P1, nx, ny, nz, b0, g[0], hq[0], tmp1, nullptr, u, dummy, +1))) return rc;
-        if ((rc = run_partial(3, TLAB_OPR_P1, nx, ny, nz, b0, g[2], hq[2], tmp1, nullptr, w, dummy, +1))) return rc;
+        if ((rc = partial_z(hq[2], w, dummy, tmp1, +1))) return rc;
         launches += 3;
         // Neumann data for the pressure: hq2 at the walls (:272-281)
         const long long np = (long long)nx * nz;
@@ -177,7 +211,7 @@ struct Dns {
         launches += 3;   // boundary planes, regular modes, singular modes (cuFFT's own kernels not counted)
         // hq -= grad p (:319-352)
         if ((rc = run_partial(1, TLAB_OPR_P1, nx, ny, nz, b0, g[0], tmp1, hq[0], nullptr, nullptr, 0.0, -1))) return rc;
-        if ((rc = run_partial(3, TLAB_OPR_P1, nx, ny, nz, b0, g[2], tmp1, hq[2], nullptr, nullptr, 0.0, -1))) return rc;
+        if ((rc = partial_z(tmp1, nullptr, 0.0, hq[2], -1))) return rc;
         { ProfScope ps(PC_ELEMENTWISE);
         sub_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(hq[1], tmp3, N); }
         launches += 3;
@@ -274,18 +308,22 @@ int tlab_dns_create(const tlab_dns_params* prm, tlab_plan_t gx, tlab_plan_t gy, 
     if (prm->nscal < 0 || prm->nscal > TLAB_MAX_SCAL) return fail(TLAB_ERR_OPTION, "tlab_dns_create: too many scalars");
     if (prm->rkm_mode != TLAB_RKM_EXP3 && prm->rkm_mode != TLAB_RKM_EXP4)
         return fail(TLAB_ERR_UNDEVELOP, "only the explicit RK3 / RK4(5) schemes are implemented");
-    if (gx->p.n != prm->nx || gy->p.n != prm->ny || gz->p.n != prm->nz)
-        return fail(TLAB_ERR_DIMGRID, "tlab_dns_create: plan sizes differ from nx, ny, nz");
+    const int P = trp().P;
+    if (gx->p.n != prm->nx || gy->p.n != prm->ny || gz->p.n != prm->nz * P)
+        return fail(TLAB_ERR_DIMGRID, "tlab_dns_create: plan sizes differ from nx, ny, nz (nz = local slab thickness)");
+    if (P > 1 && ((long long)prm->nx * prm->ny) % P)
+        return fail(TLAB_ERR_PARPARTITION, "tlab_dns_create: nx*ny is not a multiple of the number of ranks");
     tlab_dns_s* h = new tlab_dns_s();
     Dns& d = h->d;
     d.prm = *prm;
     d.g[0] = gx; d.g[1] = gy; d.g[2] = gz;
     d.nx = prm->nx; d.ny = prm->ny; d.nz = prm->nz; d.ns = prm->nscal;
+    d.P = P; d.nzg = gz->p.n;
     d.N = (long long)d.nx * d.ny * d.nz;
     d.Nt = (long long)(d.nx + 2) * d.ny * d.nz;
     rk_tables(prm->rkm_mode, d.kdt, d.ktime, d.kco);
     int rc = tlab_opr_burgers_init(gx, gy, gz, prm->visc, prm->nscal, prm->schmidt);
-    if (!rc) rc = tlab_opr_elliptic_init(gx, gy, gz);
+    if (!rc) rc = tlab_opr_elliptic_init(gx, gy, gz, prm->nz);
     d.q.resize(3); d.hq.resize(3); d.s.resize(d.ns); d.hs.resize(d.ns);
     for (int i = 0; i < 3 && !rc; i++) { rc = d.alloc(&d.q[i], d.N); if (!rc) rc = d.alloc(&d.hq[i], d.N); }
     for (int i = 0; i < d.ns && !rc; i++) { rc = d.alloc(&d.s[i], d.N); if (!rc) rc = d.alloc(&d.hs[i], d.N); }
@@ -296,6 +334,11 @@ int tlab_dns_create(const tlab_dns_params* prm, tlab_plan_t gx, tlab_plan_t gy, 
     if (!rc) rc = d.alloc(&d.hb, (long long)d.nx * d.nz);
     if (!rc) rc = d.alloc(&d.ht, (long long)d.nx * d.nz);
     if (!rc) rc = d.alloc(&d.bbackground, d.ny);
+    if (P > 1) {
+        if (!rc) rc = d.alloc(&d.zs, d.N);
+        if (!rc) rc = d.alloc(&d.zw, d.N);
+        if (!rc) rc = d.alloc(&d.zr, d.N);
+    }
     if (!rc && bbackground_host)
         rc = cuda_check(cudaMemcpyAsync(d.bbackground, bbackground_host, d.ny * sizeof(double), cudaMemcpyHostToDevice, ctx().stream), "bbackground");
     if (!rc) rc = cuda_check(cudaStreamSynchronize(ctx().stream), "tlab_dns_create");
@@ -387,7 +430,7 @@ int tlab_time_rk_coefficients(int rkm_mode, double* kdt, double* ktime, double* 
 
 int tlab_dns_launch_count(tlab_dns_t h, long long* count) {
     if (!h || !count) return fail(TLAB_ERR_OPTION, "tlab_dns_launch_count: null argument");
-    *count = h->d.launches;
+    *count = h->d.launches + trp().launches;
     return 0;
 }
 

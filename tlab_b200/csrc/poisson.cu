@@ -16,6 +16,7 @@
 #include "../../include/tlab_gpu.h"
 #include "context.h"
 #include "poisson.h"
+#include "trp.h"
 #include <cufft.h>
 #include <cmath>
 #include <vector>
@@ -491,19 +492,24 @@ void Poisson::release() {
     ready = false;
 }
 
-int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz) {
+int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz, int nz_local) {
     release();
     if (!gx || !gy || !gz) return fail(TLAB_ERR_OPTION, "OPR_Elliptic_Initialize: null plan");
     if (!gx->p.periodic || (gz->p.n > 1 && !gz->p.periodic))
         return fail(TLAB_ERR_OPTION, "OPR_Poisson (Fourier) needs periodic x and z");
     if (gy->p.periodic || gy->p.n < 16) return fail(TLAB_ERR_OPTION, "OPR_Poisson needs a non-periodic y with >= 16 points");
-    nx = gx->p.n; ny = gy->p.n; nz = gz->p.n;
+    nx = gx->p.n; ny = gy->p.n; nzg = gz->p.n;
+    nz = (nz_local > 0) ? nz_local : nzg;                                    // local slab thickness (kmax)
+    P = trp().P;
+    if (nz * P != nzg) return fail(TLAB_ERR_PARPARTITION, "OPR_Poisson: kmax times the number of ranks differs from the grid size in z");
+    const int koff = trp().rank * nz;                                        // ims_offset_k
     if (nx % 2) return fail(TLAB_ERR_DIMGRID, "OPR_Poisson needs an even number of points in x");
     nxh = nx / 2 + 1;
+    if (P > 1 && ((long long)nxh * ny) % P) return fail(TLAB_ERR_PARPARTITION, "OPR_Poisson: (nx/2+1)*ny is not a multiple of the number of ranks");
     D.nxh = nxh; D.ny = ny; D.nz = nz; D.nmodes = (long long)nxh * nz;
-    D.norm = 1.0 / double((long long)nx * nz);                               // opr_elliptic.f90:130
+    D.norm = 1.0 / double((long long)nx * nzg);                              // opr_elliptic.f90:130
     D.i_sing0 = 0; D.i_sing1 = nx / 2;                                       // opr_elliptic.f90:148-149 (0-based)
-    D.k_sing0 = 0; D.k_sing1 = nz / 2;
+    D.k_sing0 = 0 - koff; D.k_sing1 = nzg / 2 - koff;                        // task-local indices (:177-178)
     // lambda(k,i) = mwn_x(i)^2 + mwn_z(k)^2 from the first-derivative modified wavenumbers (:199-203)
     std::vector<double> lam((size_t)D.nmodes);
     const std::vector<double>& mx = gx->p.h.der1.mwn;
@@ -511,7 +517,7 @@ int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz) {
     for (int k = 0; k < nz; k++)
         for (int i = 0; i < nxh; i++) {
             double l = mx[i] * mx[i];
-            if (nz > 1) l = l + mz[k] * mz[k];
+            if (nzg > 1) l = l + mz[koff + k] * mz[koff + k];
             lam[(size_t)i + (size_t)nxh * k] = l;
         }
     D.lambda = up(allocs, lam.data(), lam.size());
@@ -535,11 +541,21 @@ int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz) {
     if (int rc = cufft_check(cufftPlanMany(&plan_bx, 1, n1, n1, 1, nxh, n1, 1, nx, CUFFT_Z2D, ny * nz), "cufftPlanMany Z2D")) return rc;
     cufftSetStream(plan_fx, st);
     cufftSetStream(plan_bx, st);
-    if (nz > 1) {
-        int n3[1] = {nz};
-        const int howmany = nxh * ny;
+    if (nzg > 1) {
+        // slab layout (P = 1) or z-pencil layout after the K-transpose (P > 1): lines interleaved, stride = howmany
+        int n3[1] = {nzg};
+        const int howmany = (int)(((long long)nxh * ny) / P);
         if (int rc = cufft_check(cufftPlanMany(&plan_z, 1, n3, n3, howmany, 1, n3, howmany, 1, CUFFT_Z2Z, howmany), "cufftPlanMany Z2Z")) return rc;
         cufftSetStream(plan_z, st);
+    }
+    if (P > 1) {
+        double* c3buf = nullptr;
+        if (cudaMalloc(&c3buf, (size_t)2 * nxh * ny * nz * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(TLAB_ERR_ALLOC, "OPR_Elliptic_Initialize: out of device memory (pencil buffer)");
+        }
+        allocs.push_back(c3buf);
+        c3 = c3buf;
     }
     const int threads = 128;
     const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
@@ -553,14 +569,28 @@ int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz) {
 int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const double* ht, double* dpdy) {
     if (!ready) return fail(TLAB_ERR_OPTION, "OPR_Poisson called before OPR_Elliptic_Initialize");
     cudaStream_t st = ctx().stream;
+    const long long nlc = 2LL * nxh * ny;          // doubles per z-plane of the half spectrum
+    // z transform of a slab spectrum held in `c`, using `w` as pencil work space when the domain is split
+    auto fft_z = [&](double* c, double* w, int dir) -> int {
+        if (nzg <= 1) return 0;
+        if (P == 1) {
+            ProfScope ps(PC_FFT);
+            return cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)c, (cufftDoubleComplex*)c, dir), "cufftExecZ2Z");
+        }
+        if (int rc = trp().forward(c, nullptr, 0.0, w, nlc, nz)) return rc;
+        {
+            ProfScope ps(PC_FFT);
+            if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)w, (cufftDoubleComplex*)w, dir), "cufftExecZ2Z")) return rc;
+        }
+        return trp().backward(w, c, nlc, nz, 0);
+    };
     {
         ProfScope ps(PC_FFT);
         const long long np = (long long)nx * nz;
         poisson_set_bcs_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(p, hb, ht, nx, ny, nz);
         if (int rc = cufft_check(cufftExecD2Z(plan_fx, p, (cufftDoubleComplex*)c1), "cufftExecD2Z")) return rc;
-        if (nz > 1)
-            if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)c1, (cufftDoubleComplex*)c1, CUFFT_FORWARD), "cufftExecZ2Z fwd")) return rc;
     }
+    if (int rc = fft_z(c1, P > 1 ? c2 : nullptr, CUFFT_FORWARD)) return rc;
     {
         ProfScope ps(PC_POISSON_Y);
         const int threads = 128;
@@ -569,13 +599,14 @@ int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const do
         poisson_singular_kernel<<<1, 4, 0, st>>>(D, c1, c2);
         if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
     }
-    ProfScope ps2(PC_FFT);
-    if (nz > 1)
-        if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)c1, (cufftDoubleComplex*)c1, CUFFT_INVERSE), "cufftExecZ2Z inv")) return rc;
-    if (int rc = cufft_check(cufftExecZ2D(plan_bx, (cufftDoubleComplex*)c1, p), "cufftExecZ2D")) return rc;
+    if (int rc = fft_z(c1, c3, CUFFT_INVERSE)) return rc;
+    {
+        ProfScope ps(PC_FFT);
+        if (int rc = cufft_check(cufftExecZ2D(plan_bx, (cufftDoubleComplex*)c1, p), "cufftExecZ2D")) return rc;
+    }
     if (dpdy) {
-        if (nz > 1)
-            if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)c2, (cufftDoubleComplex*)c2, CUFFT_INVERSE), "cufftExecZ2Z inv")) return rc;
+        if (int rc = fft_z(c2, c3, CUFFT_INVERSE)) return rc;
+        ProfScope ps(PC_FFT);
         if (int rc = cufft_check(cufftExecZ2D(plan_bx, (cufftDoubleComplex*)c2, dpdy), "cufftExecZ2D")) return rc;
     }
     return 0;
@@ -592,9 +623,9 @@ using namespace tlab;
 
 extern "C" {
 
-int tlab_opr_elliptic_init(tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz) {
+int tlab_opr_elliptic_init(tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz, int kmax_local) {
     if (int rc = tlab_gpu_init(-1)) return rc;
-    return poisson().init(gx, gy, gz);
+    return poisson().init(gx, gy, gz, kmax_local);
 }
 
 int tlab_opr_poisson(int nx, int ny, int nz, int ibc, double* p, double* tmp1, double* tmp2, const double* bcs_hb,

@@ -29,11 +29,13 @@ struct PoissonDev {
 
 struct Poisson {
     bool ready = false;
-    int nx = 0, ny = 0, nz = 0, nxh = 0;
+    int nx = 0, ny = 0, nz = 0, nxh = 0;   // nz: local slab thickness
+    int nzg = 0, P = 1;                     // global extent in z, ranks in z
+    double* c3 = nullptr;                   // pencil work array (P > 1)
     PoissonDev D;
     cufftHandle plan_fx = 0, plan_bx = 0, plan_z = 0;
     std::vector<void*> allocs;
-    int init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz);
+    int init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz, int nz_local);
     int solve(double* p, double* c1, double* c2, const double* hb, const double* ht, double* dpdy);
     void release();
 };

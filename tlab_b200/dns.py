@@ -29,10 +29,11 @@ class Dns:
     def __init__(self, g, visc, schmidt, rkm_mode=RKM_EXP4, buoyancy_type="none", buoyancy_params=(0.0, 0.0),
                  buoyancy_vector=(0.0, 0.0, 0.0), bbackground=None,
                  bcs_flow_jmin=(DNS_BCS_DIRICHLET,) * 3, bcs_flow_jmax=(DNS_BCS_DIRICHLET,) * 3,
-                 bcs_scal_jmin=None, bcs_scal_jmax=None, scal_limit=True, scal_min=0.0, scal_max=1.0):
+                 bcs_scal_jmin=None, bcs_scal_jmax=None, scal_limit=True, scal_min=0.0, scal_max=1.0, kmax=None):
+        """kmax: thickness of this rank's z slab (None: the whole domain, single process)."""
         L = _lib.load()
         self.g = g
-        self.nx, self.ny, self.nz = g[0].size, g[1].size, g[2].size
+        self.nx, self.ny, self.nz = g[0].size, g[1].size, (g[2].size if kmax is None else int(kmax))
         self.inb_scal = len(schmidt)
         p = DnsParams()
         p.nx, p.ny, p.nz, p.nscal, p.rkm_mode = self.nx, self.ny, self.nz, self.inb_scal, rkm_mode

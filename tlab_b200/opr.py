@@ -151,10 +151,10 @@ def BOUNDARY_BCS_NEUMANN_Y(ibc, nx, ny, nz, g, u, bcs_hb, bcs_ht):
     _call(_lib.load().tlab_boundary_bcs_neumann_y, ibc, nx, ny, nz, g.handle, _ptr(u), _ptr(bcs_hb), _ptr(bcs_ht))
 
 
-def OPR_Elliptic_Initialize(g):
-    """opr_elliptic.f90:86-250 (FourierXZ_Factorize); g = (gx, gy, gz)"""
+def OPR_Elliptic_Initialize(g, kmax=0):
+    """opr_elliptic.f90:86-250 (FourierXZ_Factorize); g = (gx, gy, gz); kmax = local slab thickness (0: whole domain)"""
     _sync()
-    _lib.check(_lib.load().tlab_opr_elliptic_init(g[0].handle, g[1].handle, g[2].handle))
+    _lib.check(_lib.load().tlab_opr_elliptic_init(g[0].handle, g[1].handle, g[2].handle, int(kmax)))
 
 
 def OPR_Poisson(nx, ny, nz, ibc, p, tmp1, tmp2, bcs_hb, bcs_ht, dpdy=None):
