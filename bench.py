@@ -33,6 +33,9 @@ WORKLOADS = {
     "tiny": (64, 48, 32),
 }
 ALG_BYTES_PER_PT_SUBSTEP = 995.0          # 124.4 sweeps of 8 B
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel classes from the committed
+# ncu --set full captures (profiles/), scaled to the C3 grid (bytes per point x points); None if not captured
+TRAFFIC_NCU = {}
 PHYS = dict(visc=1.0 / 5000.0, schmidt=[1.0], dtime=1.0e-3)
 
 
@@ -218,19 +221,25 @@ def run_gpu(args):
     nx, ny, nz = WORKLOADS[args.workload]
     if args.nx:
         nx, ny, nz = args.nx, args.ny, args.nz
+    from tlab_b200 import mpi
+    kmax, koff = nz, 0
     if world > 1:
-        raise SystemExit("bench.py: multi-GPU z-slab path not enabled in this build")
+        mpi.init_from_torch_distributed()
+        kmax, koff = mpi.slab(nz, rank, world)
     x, z, y = grid_periodic(nx), grid_periodic(nz), grid_tanh(ny)
     g = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, False, name="y"), opr.FdmPlan(z, True, True, name="z")]
     D, Nn = GD.DNS_BCS_DIRICHLET, GD.DNS_BCS_NEUMANN
     sim = GD.Dns(g, visc=PHYS["visc"], schmidt=PHYS["schmidt"], rkm_mode=GD.RKM_EXP4, buoyancy_type="linear",
                  buoyancy_params=(1.0, 0.0), buoyancy_vector=(0.0, 1.0, 0.0),
-                 bcs_flow_jmin=(D, D, D), bcs_flow_jmax=(Nn, D, Nn), bcs_scal_jmin=(D,), bcs_scal_jmax=(Nn,))
-    N = nx * ny * nz
-    shape = (nz, ny, nx)
+                 bcs_flow_jmin=(D, D, D), bcs_flow_jmax=(Nn, D, Nn), bcs_scal_jmin=(D,), bcs_scal_jmax=(Nn,),
+                 kmax=(kmax if world > 1 else None))
+    Nglobal = nx * ny * nz
+    N = nx * ny * kmax                       # points of this rank's slab
+    shape = (kmax, ny, nx)
+    z_loc = z[koff:koff + kmax]
     names = ["q1", "q2", "q3", "s1"]
     for i, nm in enumerate(names):
-        f = synth_field(torch, dev, shape, x, y, z, 20261017 + i, 0.05)
+        f = synth_field(torch, dev, shape, x, y, z_loc, 20261017 + i, 0.05)
         if nm == "s1":
             f = 0.5 + f
         torch.cuda.synchronize()
@@ -257,12 +266,20 @@ def run_gpu(args):
     tl.check(L.tlab_gpu_profile(1))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
     e0.record(stream)
     substeps(args.warmup, args.steps)
     e1.record(stream)
     tl.check(L.tlab_gpu_synchronize())
     torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
+    if world > 1:
+        dist.barrier()
+        tmax = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total = float(tmax.item())
     clocks = sampler.stop()
     launches = sim.launch_count() - launches0
     ms_cls = (ctypes.c_double * 11)()
@@ -274,7 +291,7 @@ def run_gpu(args):
     breakdown = {n_: {"ms_per_step": ms_cls[i] / args.steps, "launches_per_step": cnt_cls[i] / args.steps}
                  for i, n_ in enumerate(cls_names) if cnt_cls[i] > 0}
     ms_per_step = ms_total / args.steps
-    value = N / (ms_per_step * 1e-3) / 1e9
+    value = Nglobal / (ms_per_step * 1e-3) / 1e9
 
     # roofline of the dominant kernel class (by device time inside the timed region)
     peak, peak_kind = load_peaks()
@@ -284,10 +301,10 @@ def run_gpu(args):
     avg_ms = ms_cls[cls_names.index(dom)] / cnt_cls[cls_names.index(dom)]
     achieved = line_classes[dom] * N / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": TRAFFIC_NCU.get(dom),
                 "algorithmic_bytes_per_launch": line_classes[dom] * N, "avg_launch_ms": avg_ms,
-                "substep": {"algorithmic_bytes": ALG_BYTES_PER_PT_SUBSTEP * N,
-                            "achieved": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9,
+                "substep": {"algorithmic_bytes_per_gpu": ALG_BYTES_PER_PT_SUBSTEP * N,
+                            "achieved_per_gpu": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9,
                             "frac": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9 / peak}}
 
     # end to end: one full RK step (5 substeps) from and to pinned host buffers through the C ABI
@@ -308,15 +325,21 @@ def run_gpu(args):
         a1.record(stream)
         torch.cuda.synchronize()
         ms_e2e = a0.elapsed_time(a1) / (reps * nstage)
-        e2e = {"value": N / (ms_e2e * 1e-3) / 1e9, "unit": "Gpts/s", "h2d_bytes_per_step": 4 * N * 8 / nstage,
-               "d2h_bytes_per_step": 4 * N * 8 / nstage, "ms_per_step": ms_e2e,
+        if world > 1:
+            tmax = torch.tensor([ms_e2e], dtype=torch.float64, device=dev)
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            ms_e2e = float(tmax.item())
+        e2e = {"value": Nglobal / (ms_e2e * 1e-3) / 1e9, "unit": "Gpts/s", "h2d_bytes_per_step": 4 * Nglobal * 8 / nstage,
+               "d2h_bytes_per_step": 4 * Nglobal * 8 / nstage, "ms_per_step": ms_e2e,
                "call": "tlab_time_rungekutta_host: 4 fields up, 5 substeps, 4 fields down"}
         del qh, sh
     except Exception as ex:           # e.g. not enough pinned host memory
         e2e = {"value": None, "unit": "Gpts/s", "error": str(ex)}
+        if world > 1:
+            raise
 
     cpu = None
-    if rank == 0 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu:
         rate, cores, desc = cpu_port_rate((128, 64, 128), 1, None)
         cpu = {"value": rate, "unit": "Gpts/s", "cores": cores, "kind": "port", "sample": desc}
 
@@ -333,6 +356,7 @@ def run_gpu(args):
         print(json.dumps(out))
     sim.close()
     if world > 1:
+        mpi.finalize()
         dist.destroy_process_group()
 
 

@@ -136,6 +136,21 @@ int tlab_fdm_der1_solve(tlab_plan_t g, int nlines, int ibc, const double* u, dou
 int tlab_fdm_der2_solve(tlab_plan_t g, int nlines, int is_or_minus1, const double* u, const double* du_ignored,
                         double* result);
 
+/* thomas3 / thomas5 substitution stages on device arrays in the reference's lines-first layout f(len, nmax);
+ * a..e are the factored diagonals produced by TRIDFS / TRIDPFS / PENTADFS / PENTADFS2:
+ * TRIDSS(nmax, len, a, b, c, f), src/utils/linear3.f90:56-150; TRIDPSS(nmax, len, a, b, c, d, e, f, wrk), :321-442;
+ * PENTADSS(nmax, len, a, b, c, d, e, f), src/utils/linear5.f90:76-131; PENTADSS2, :209-244 */
+int tlab_tridss(int nmax, int len, const double* a, const double* b, const double* c, double* f);
+int tlab_tridpss(int nmax, int len, const double* a, const double* b, const double* c, const double* d,
+                 const double* e, double* f, double* wrk_or_null);
+int tlab_pentadss(int nmax, int len, const double* a, const double* b, const double* c, const double* d,
+                  const double* e, double* f);
+int tlab_pentadss2(int nmax, int len, const double* a, const double* b, const double* c, const double* d,
+                   const double* e, double* f);
+/* TLab_Transpose(a, nra, nca, ma, b, mb) and _COMPLEX, src/utils/tlab_transpose.f90:14-82,148-210: b(k,j) = a(j,k) */
+int tlab_transpose(const double* a, int nra, int nca, int ma, double* b, int mb);
+int tlab_transpose_complex(const double* a, int nra, int nca, int ma, double* b, int mb);
+
 /* BOUNDARY_BCS_NEUMANN_Y(ibc, nx, ny, nz, g, u, bcs_hb, bcs_ht, tmp1), src/tools/dns/boundary_bcs.f90:368-473 */
 int tlab_boundary_bcs_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_t gy, const double* u, double* bcs_hb,
                                 double* bcs_ht);

@@ -1,0 +1,44 @@
+"""gloo worker (CPU, world_size 2): the K-transpose layout of tlab_b200.mpi against the global-array definition."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    from tlab_b200 import mpi
+    nxy, nz = 24, 8
+    kmax, koff = mpi.slab(nz, rank, world)
+    rng = np.random.default_rng(5)
+    full = rng.standard_normal((nz, nxy))                 # Fortran a(nxy, nz) = C (nz, nxy)
+    a = torch.from_numpy(full[koff:koff + kmax].copy())
+    b = mpi.trp_k_forward_ref(a)                          # pencil (nz, nxy/P): lines rank*nl .. (rank+1)*nl
+    nl = nxy // world
+    expect = full[:, rank * nl:(rank + 1) * nl]
+    assert np.array_equal(b.numpy(), expect), "forward map (tlab_mpi_transpose.f90:301-325)"
+    back = mpi.trp_k_backward_ref(b, kmax)
+    assert torch.equal(back, a), "backward is the inverse"
+    # complex data: (re, im) pairs travel together
+    cf = rng.standard_normal((nz, nxy)) + 1j * rng.standard_normal((nz, nxy))
+    ca = torch.from_numpy(np.ascontiguousarray(cf[koff:koff + kmax]).view(np.float64).copy())   # (kmax, 2*nxy)
+    # treat complex elements as blocks of 2 doubles: partition by complex lines
+    cb = mpi.trp_k_forward_ref(ca.reshape(kmax, nxy, 2).reshape(kmax, nxy * 2))
+    got = cb.numpy().reshape(nz, nl, 2)
+    exp = np.ascontiguousarray(cf[:, rank * nl:(rank + 1) * nl]).view(np.float64).reshape(nz, nl, 2)
+    assert np.array_equal(got, exp)
+    # pack/unpack are inverse permutations
+    assert torch.equal(mpi.unpack_k(mpi.pack_k(a, world)), a)
+    if rank == 0:
+        print("DIST_CPU_OK", flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
