@@ -34,8 +34,9 @@ def test_thomas_substitution_stages(cuda):
     ref = f.copy()
     fdm.tridss(la, lb, lc, ref)
     fd = _dev(torch, cuda, f)
+    ds = [_dev(torch, cuda, v) for v in (la, lb, lc)]     # keep the device copies alive during the call
     torch.cuda.synchronize()
-    tl.check(L.tlab_tridss(n, m, _p(_dev(torch, cuda, la)), _p(_dev(torch, cuda, lb)), _p(_dev(torch, cuda, lc)), _p(fd)))
+    tl.check(L.tlab_tridss(n, m, *[_p(v) for v in ds], _p(fd)))
     assert rel_l2(fd.cpu().numpy(), ref) <= 1e-13
     # TRIDPSS
     pa, pb, pc, pd, pe = a.copy(), b.copy(), c.copy(), np.zeros(n), np.zeros(n)
