@@ -208,7 +208,7 @@ struct Dns {
         get_planes_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(hq[1], hb, ht, nx, ny, nz); }
         launches++;
         if ((rc = poisson().solve(tmp1, c1, c2, hb, ht, tmp3))) return rc;     // (:284)
-        launches += 3;   // boundary planes, regular modes, singular modes (cuFFT's own kernels not counted)
+        launches += 2;   // boundary planes, per-mode y solves (cuFFT's own kernels not counted)
         // hq -= grad p (:319-352)
         if ((rc = run_partial(1, TLAB_OPR_P1, nx, ny, nz, b0, g[0], tmp1, hq[0], nullptr, nullptr, 0.0, -1))) return rc;
         if ((rc = partial_z(tmp1, nullptr, 0.0, hq[2], -1))) return rc;

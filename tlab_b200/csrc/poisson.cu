@@ -21,6 +21,10 @@
 #include <cmath>
 #include <vector>
 
+#ifndef POISSON_MIN_BLOCKS
+#define POISSON_MIN_BLOCKS 4
+#endif
+
 namespace tlab {
 
 namespace {
@@ -248,9 +252,10 @@ __device__ __forceinline__ bool mode_is_singular(const PoissonDev& D, int i, int
     return (i == D.i_sing0 || i == D.i_sing1) && (k == D.k_sing0 || k == D.k_sing1);
 }
 
-// scratch planes: [row][mode]
-__device__ __forceinline__ LineRef plane(double* base, long long nmodes, long long m) {
-    LineRef r; r.p = base + m; r.js = nmodes; return r;
+// scratch planes, blocked by 32 modes: element (row, m) at ((m / 32) * ny + row) * 32 + m % 32, so that a warp
+// marching along y streams through one contiguous region per array (DRAM page and TLB friendly)
+__device__ __forceinline__ LineRef plane(double* base, int ny, long long m) {
+    LineRef r; r.p = base + (m >> 5) * ((long long)ny * 32) + (m & 31); r.js = 32; return r;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -262,34 +267,34 @@ __global__ void poisson_fundamental_kernel(PoissonDev D) {
     if (mode_is_singular(D, i, k)) return;
     const double lam = sqrt(D.lambda[m]);
     const long long NM = D.nmodes;
-    const long long plane_sz = NM * D.ny;
+    const long long plane_sz = D.plane_sz;
     const int n = D.ny;
     // stage 1: v1 (forcing delta at row n, v1(1) = 0) and e- (no forcing, e-(1) = 1)
     {
         LineRef f[2] = {{nullptr, 0}, {nullptr, 0}};
         double fend[2] = {1.0, 0.0}, bc[2] = {0.0, 1.0};
-        LineRef res[2] = {plane(D.fund + 0 * plane_sz, NM, m), plane(D.fund + 1 * plane_sz, NM, m)};
-        LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, NM, m), plane(D.scr + 1 * plane_sz, NM, m)};
-        int1_solve<2>(D.smin, lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, NM, m),
-                      plane(D.scr + 4 * plane_sz, NM, m), plane(D.scr + 5 * plane_sz, NM, m), nullptr);
+        LineRef res[2] = {plane(D.fund + 0 * plane_sz, D.ny, m), plane(D.fund + 1 * plane_sz, D.ny, m)};
+        LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, D.ny, m), plane(D.scr + 1 * plane_sz, D.ny, m)};
+        int1_solve<2>(D.smin, lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, D.ny, m),
+                      plane(D.scr + 4 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), nullptr);
     }
     // stage 2: u1, s+, e+ from (v1, e-, 0) with values (0, 0, 1) at row n
     double der[3];
     {
-        LineRef v1 = plane(D.fund + 0 * plane_sz, NM, m), em = plane(D.fund + 1 * plane_sz, NM, m);
+        LineRef v1 = plane(D.fund + 0 * plane_sz, D.ny, m), em = plane(D.fund + 1 * plane_sz, D.ny, m);
         LineRef f[3] = {v1, em, {nullptr, 0}};
         double fend[3] = {v1.get(1), em.get(1), 0.0}, bc[3] = {0.0, 0.0, 1.0};
-        LineRef res[3] = {plane(D.fund + 2 * plane_sz, NM, m), plane(D.fund + 3 * plane_sz, NM, m),
-                          plane(D.fund + 4 * plane_sz, NM, m)};
-        LineRef ysc[3] = {plane(D.scr + 0 * plane_sz, NM, m), plane(D.scr + 1 * plane_sz, NM, m),
-                          plane(D.scr + 2 * plane_sz, NM, m)};
-        int1_solve<3>(D.smax, -lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, NM, m),
-                      plane(D.scr + 4 * plane_sz, NM, m), plane(D.scr + 5 * plane_sz, NM, m), der);
+        LineRef res[3] = {plane(D.fund + 2 * plane_sz, D.ny, m), plane(D.fund + 3 * plane_sz, D.ny, m),
+                          plane(D.fund + 4 * plane_sz, D.ny, m)};
+        LineRef ysc[3] = {plane(D.scr + 0 * plane_sz, D.ny, m), plane(D.scr + 1 * plane_sz, D.ny, m),
+                          plane(D.scr + 2 * plane_sz, D.ny, m)};
+        int1_solve<3>(D.smax, -lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, D.ny, m),
+                      plane(D.scr + 4 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), der);
     }
     // boundary system (opr_odes.f90:329-348), stored LU-decomposed
-    const double v1n = plane(D.fund + 0 * plane_sz, NM, m).get(n), emn = plane(D.fund + 1 * plane_sz, NM, m).get(n);
-    const double u11 = plane(D.fund + 2 * plane_sz, NM, m).get(1), sp1 = plane(D.fund + 3 * plane_sz, NM, m).get(1);
-    const double ep1 = plane(D.fund + 4 * plane_sz, NM, m).get(1);
+    const double v1n = plane(D.fund + 0 * plane_sz, D.ny, m).get(n), emn = plane(D.fund + 1 * plane_sz, D.ny, m).get(n);
+    const double u11 = plane(D.fund + 2 * plane_sz, D.ny, m).get(1), sp1 = plane(D.fund + 3 * plane_sz, D.ny, m).get(1);
+    const double ep1 = plane(D.fund + 4 * plane_sz, D.ny, m).get(1);
     double a11 = 1.0 + lam * sp1, a21 = emn, a31 = der[1];
     double a12 = lam * ep1, a22 = lam, a32 = der[2];
     double a13 = lam * u11, a23 = v1n, a33 = der[0];
@@ -307,14 +312,16 @@ __global__ void poisson_fundamental_kernel(PoissonDev D) {
 
 // -------------------------------------------------------------------------------------------------
 // per call: regular modes, Neumann/Neumann (OPR_ODE2_Factorize_NN)
-__global__ void __launch_bounds__(128) poisson_modes_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv) {
+__device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ cf, double* __restrict__ cv, int i, int k);
+
+__global__ void __launch_bounds__(128, POISSON_MIN_BLOCKS) poisson_modes_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= D.nmodes) return;
     const int i = (int)(m % D.nxh), k = (int)(m / D.nxh);
-    if (mode_is_singular(D, i, k)) return;
+    if (mode_is_singular(D, i, k)) { poisson_singular_mode(D, cf, cv, i, k); return; }
     const double lam = sqrt(D.lambda[m]);
     const long long NM = D.nmodes;
-    const long long plane_sz = NM * D.ny;
+    const long long plane_sz = D.plane_sz;
     const int n = D.ny;
     // complex lines of this mode inside c(kx, y, kz): re/im interleaved
     const long long off = 2 * ((long long)i + (long long)D.nxh * D.ny * k);
@@ -324,9 +331,9 @@ __global__ void __launch_bounds__(128) poisson_modes_kernel(PoissonDev D, double
     const double norm = D.norm;
     const double bcb[2] = {fre.get(1) * norm, fim.get(1) * norm};      // bcs(1:2,1) = f(1:2)
     const double bct[2] = {fre.get(n) * norm, fim.get(n) * norm};      // bcs(1:2,2) = f(2ny-1:2ny)
-    LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, NM, m), plane(D.scr + 1 * plane_sz, NM, m)};
-    LineRef csc = plane(D.scr + 2 * plane_sz, NM, m), dsc = plane(D.scr + 3 * plane_sz, NM, m),
-            esc = plane(D.scr + 4 * plane_sz, NM, m);
+    LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, D.ny, m), plane(D.scr + 1 * plane_sz, D.ny, m)};
+    LineRef csc = plane(D.scr + 2 * plane_sz, D.ny, m), dsc = plane(D.scr + 3 * plane_sz, D.ny, m),
+            esc = plane(D.scr + 4 * plane_sz, D.ny, m);
     const double zero2[2] = {0.0, 0.0};
     // v^(0): v' + lam v = f, f(n) = 0, v(1) = 0
     {
@@ -345,9 +352,9 @@ __global__ void __launch_bounds__(128) poisson_modes_kernel(PoissonDev D, double
     const double a11 = A[0 * NM + m], a21 = A[1 * NM + m], a31 = A[2 * NM + m];
     const double a12 = A[3 * NM + m], a22 = A[4 * NM + m], a32 = A[5 * NM + m];
     const double a13 = A[6 * NM + m], a23 = A[7 * NM + m], a33 = A[8 * NM + m];
-    LineRef v1 = plane(D.fund + 0 * plane_sz, NM, m), em = plane(D.fund + 1 * plane_sz, NM, m);
-    LineRef u1 = plane(D.fund + 2 * plane_sz, NM, m), sp = plane(D.fund + 3 * plane_sz, NM, m),
-            ep = plane(D.fund + 4 * plane_sz, NM, m);
+    LineRef v1 = plane(D.fund + 0 * plane_sz, D.ny, m), em = plane(D.fund + 1 * plane_sz, D.ny, m);
+    LineRef u1 = plane(D.fund + 2 * plane_sz, D.ny, m), sp = plane(D.fund + 3 * plane_sz, D.ny, m),
+            ep = plane(D.fund + 4 * plane_sz, D.ny, m);
     LineRef ul[2] = {fre, fim}, vl[2] = {vre, vim};
 #pragma unroll
     for (int l = 0; l < 2; l++) {
@@ -378,17 +385,11 @@ __global__ void __launch_bounds__(128) poisson_modes_kernel(PoissonDev D, double
 }
 
 // per call: the (up to four) singular modes, OPR_ODE2_Factorize_NN_Sing -> _DN_Sing
-__global__ void poisson_singular_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv) {
-    const int t = threadIdx.x;
-    const int i = (t & 1) ? D.i_sing1 : D.i_sing0;
-    const int k = (t & 2) ? D.k_sing1 : D.k_sing0;
-    if (i < 0 || i >= D.nxh || k < 0 || k >= D.nz) return;
-    if ((t & 1) && D.i_sing1 == D.i_sing0) return;
-    if ((t & 2) && D.k_sing1 == D.k_sing0) return;
+__device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ cf, double* __restrict__ cv, int i, int k) {
     const long long m = (long long)i + (long long)D.nxh * k;
     const double lam = sqrt(D.lambda[m]);
     const long long NM = D.nmodes;
-    const long long plane_sz = NM * D.ny;
+    const long long plane_sz = D.plane_sz;
     const int n = D.ny;
     const long long off = 2 * ((long long)i + (long long)D.nxh * D.ny * k);
     const long long js = 2LL * D.nxh;
@@ -396,11 +397,11 @@ __global__ void poisson_singular_kernel(PoissonDev D, double* __restrict__ cf, d
     LineRef vre = {cv + off, js}, vim = {cv + off + 1, js};
     const double norm = D.norm;
     const double bct[2] = {fre.get(n) * norm, fim.get(n) * norm};
-    LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, NM, m), plane(D.scr + 1 * plane_sz, NM, m)};
-    LineRef csc = plane(D.scr + 2 * plane_sz, NM, m), dsc = plane(D.scr + 3 * plane_sz, NM, m),
-            esc = plane(D.scr + 4 * plane_sz, NM, m);
+    LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, D.ny, m), plane(D.scr + 1 * plane_sz, D.ny, m)};
+    LineRef csc = plane(D.scr + 2 * plane_sz, D.ny, m), dsc = plane(D.scr + 3 * plane_sz, D.ny, m),
+            esc = plane(D.scr + 4 * plane_sz, D.ny, m);
     // fundamental lines of this mode live in the (otherwise unused) fund planes of the mode
-    LineRef v1 = plane(D.fund + 0 * plane_sz, NM, m), u1 = plane(D.fund + 2 * plane_sz, NM, m);
+    LineRef v1 = plane(D.fund + 0 * plane_sz, D.ny, m), u1 = plane(D.fund + 2 * plane_sz, D.ny, m);
     const double zero2[2] = {0.0, 0.0};
     // v^(0): v' = f with f(1) = 0, v(n) = bcs(:,2)
     {
@@ -523,7 +524,8 @@ int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz, int nz_loca
     D.lambda = up(allocs, lam.data(), lam.size());
     if (int rc = make_side(gy->p.h.der1, BCS_MIN, D.smin, allocs)) return fail(rc, "integral operator (BCS_MIN) setup failed");
     if (int rc = make_side(gy->p.h.der1, BCS_MAX, D.smax, allocs)) return fail(rc, "integral operator (BCS_MAX) setup failed");
-    const size_t plane_sz = (size_t)D.nmodes * ny;
+    const size_t plane_sz = (size_t)((D.nmodes + 31) / 32 * 32) * ny;
+    D.plane_sz = (long long)plane_sz;
     double *fund = nullptr, *scr = nullptr, *amat = nullptr;
     if (cudaMalloc(&fund, 5 * plane_sz * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&scr, 6 * plane_sz * sizeof(double)) != cudaSuccess ||
@@ -596,7 +598,6 @@ int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const do
         const int threads = 128;
         const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
         poisson_modes_kernel<<<blocks, threads, 0, st>>>(D, c1, c2);
-        poisson_singular_kernel<<<1, 4, 0, st>>>(D, c1, c2);
         if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
     }
     if (int rc = fft_z(c1, c3, CUFFT_INVERSE)) return rc;
