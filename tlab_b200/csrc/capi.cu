@@ -278,6 +278,7 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     if (!key) return fail(TLAB_ERR_OPTION, "null key");
     if (!std::strcmp(key, "lines_x")) ctx().tune_lines_x = value;
     else if (!std::strcmp(key, "lines_yz")) ctx().tune_lines_yz = value;
+    else if (!std::strcmp(key, "prefetch")) set_prefetch(value != 0);
     else return fail(TLAB_ERR_OPTION, std::string("unknown tuning key ") + key);
     return 0;
 }

@@ -20,6 +20,7 @@
 // memory) the tile is staged through padded shared memory.
 #include "lines.h"
 #include <cstdio>
+#include <algorithm>
 
 namespace tlab {
 
@@ -470,6 +471,159 @@ __global__ void __launch_bounds__(512) line_kernel_strided(LineArgs a) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// y / z directions, persistent variant with asynchronous prefetch (full chunks, whole tiles only).
+// Each CTA loops over tiles of L lines.  The pencils of a tile are brought into shared memory with
+// cp.async (16-byte pieces, coalesced over the L contiguous lines); while a tile is being solved in
+// registers, the next tile's input and this tile's velocity / accumulation target are already in flight,
+// so that the DRAM latency is paid behind the arithmetic instead of in front of it.
+// Tile layout in shared memory: row i of line l at (i / 16) * CS + (i % 16) * L + l, CS = 16 L + pad, which
+// makes the chunk reads of a warp (lanes = L lines x 32/L chunks) bank-conflict free.
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__host__ __device__ inline int pf_chunk_stride(int L) { return CHUNK * L + (L >= 16 ? 0 : L); }
+
+__device__ __forceinline__ void pf_issue_tile(double* tile, const double* __restrict__ g, long long st, int n, int L, int CS) {
+    const int ppr = L >> 1;                        // 16-byte pieces per row
+    const int total = n * ppr;
+    for (int q = threadIdx.x; q < total; q += blockDim.x) {
+        const int i = q / ppr, lp = (q - i * ppr) * 2;
+        cp_async16(tile + (i >> 4) * CS + (i & 15) * L + lp, g + (long long)i * st + lp);
+    }
+}
+
+template <int MODE, bool PER, bool NEED1>
+__global__ void __launch_bounds__(512) line_kernel_strided_pf(LineArgs a) {
+    extern __shared__ double sm[];
+    const int L = a.L;
+    const int l = threadIdx.x % L;
+    const int t = threadIdx.x / L;
+    const Chunk c = make_chunk(t, a.T, a.cbase, a.crem);       // full chunks: s0 = 16 t, cnt = 16, j0 = 0
+    const long long st = a.stride;
+    const int n = a.n;
+    const int CS = pf_chunk_stride(L);
+    const int tile_doubles = a.T * CS;
+    double* bufU = sm + exch_doubles(a.T, L);
+    double* bufV = bufU + tile_doubles;            // velocity (Burgers) or second input (u + scale*u2)
+    double* bufO = bufV + tile_doubles;            // accumulation target
+    const bool has_u2 = (a.u2 != nullptr);
+    const bool has_vel = (MODE == MODE_BURGERS) && (a.vel != a.u);
+    const bool has_acc = (a.accumulate != 0) && (MODE == MODE_BURGERS || MODE == MODE_P1);
+    const long long ntiles = a.nlines / L;
+
+    auto tile_base = [&](long long tile) {
+        const long long line0 = tile * L;
+        return (line0 / a.inner) * a.outer_stride + (line0 % a.inner);
+    };
+    long long tile = blockIdx.x;
+    if (tile < ntiles) {
+        const long long gb = tile_base(tile);
+        pf_issue_tile(bufU, a.u + gb, st, n, L, CS);
+        if (has_u2) pf_issue_tile(bufV, a.u2 + gb, st, n, L, CS);
+    }
+    cp_async_commit();
+    for (; tile < ntiles; tile += gridDim.x) {
+        const long long gb = tile_base(tile);
+        cp_async_wait<0>();
+        __syncthreads();
+        // ---- chunk and halos from shared memory
+        double u[CHUNK + 6];
+        {
+            const double* pc = bufU + c.t * CS + l;
+            const bool lok = PER || c.t > 0, rok = PER || c.t < c.T - 1;
+            const double* pl = bufU + ((c.t > 0) ? (c.t - 1) : (c.T - 1)) * CS + 13 * L + l;
+            const double* pr = bufU + ((c.t < c.T - 1) ? (c.t + 1) : 0) * CS + l;
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) u[j + 3] = pc[j * L];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                u[k] = lok ? pl[k * L] : 0.0;
+                u[CHUNK + 3 + k] = rok ? pr[k * L] : 0.0;
+            }
+            if (has_u2) {
+                const double* qc = bufV + c.t * CS + l;
+                const double* ql = bufV + ((c.t > 0) ? (c.t - 1) : (c.T - 1)) * CS + 13 * L + l;
+                const double* qr = bufV + ((c.t < c.T - 1) ? (c.t + 1) : 0) * CS + l;
+#pragma unroll
+                for (int j = 0; j < CHUNK; j++) u[j + 3] = u[j + 3] + qc[j * L] * a.scale;
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    if (lok) u[k] = u[k] + ql[k * L] * a.scale;
+                    if (rok) u[CHUNK + 3 + k] = u[CHUNK + 3 + k] + qr[k * L] * a.scale;
+                }
+            }
+        }
+        __syncthreads();                            // bufU / bufV free again
+        // ---- prefetch: this tile's velocity and accumulation target, then the next tile's input
+        if (has_vel) pf_issue_tile(bufV, a.vel + gb, st, n, L, CS);
+        if (has_acc) pf_issue_tile(bufO, a.out1 + gb, st, n, L, CS);
+        cp_async_commit();
+        const long long next = tile + gridDim.x;
+        if (next < ntiles) {
+            const long long gn = tile_base(next);
+            pf_issue_tile(bufU, a.u + gn, st, n, L, CS);
+        }
+        cp_async_commit();
+
+        double wb[BROW_W], wt[BROW_W];
+        if (!PER) {
+#pragma unroll
+            for (int k = 0; k < BROW_W; k++) {
+                wb[k] = (c.t == 0) ? u[3 + k] : 0.0;
+                wt[k] = (c.t == c.T - 1) ? u[3 + CHUNK - 1 - k] : 0.0;
+            }
+        }
+        double dd[2][CHUNK];
+        if (MODE == MODE_BURGERS && !has_vel) {
+            // SELF: the advecting velocity is s itself; park this thread's chunk in its own slots of bufV
+            double* vq = bufV + c.t * CS + l;
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) vq[j * L] = u[j + 3];
+        }
+        line_core<MODE, PER, NEED1, true>(u, wb, wt, c, a, l, L, sm, dd);
+        double (&d1)[CHUNK] = dd[0];
+        double (&d2)[CHUNK] = dd[1];
+
+        // ---- velocity / accumulation target have arrived (all groups but the newest one are complete)
+        if (has_vel || has_acc) {
+            cp_async_wait<1>();
+            __syncthreads();
+        }
+        double* __restrict__ o1 = a.out1 + gb + l + (long long)c.s0 * st;
+        double* __restrict__ o2 = (MODE == MODE_P2_P1) ? a.out2 + gb + l + (long long)c.s0 * st : nullptr;
+        if (MODE == MODE_BURGERS) {
+            const double* vq = bufV + c.t * CS + l;
+            const double* oq = bufO + c.t * CS + l;
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) {
+                const double v = vq[j * L];
+                double r = d2[j] - v * d1[j];
+                if (has_acc) r = (a.accumulate > 0) ? oq[j * L] + r : oq[j * L] - r;
+                d2[j] = r;
+            }
+        } else if (MODE == MODE_P1 && has_acc) {
+            const double* oq = bufO + c.t * CS + l;
+#pragma unroll
+            for (int j = 0; j < CHUNK; j++) d1[j] = (a.accumulate > 0) ? oq[j * L] + d1[j] : oq[j * L] - d1[j];
+        }
+#pragma unroll
+        for (int j = 0; j < CHUNK; j++) {
+            if (MODE == MODE_P1) __stcs(o1 + j * st, d1[j]);
+            if (MODE == MODE_P2 || MODE == MODE_BURGERS) __stcs(o1 + j * st, d2[j]);
+            if (MODE == MODE_P2_P1) { __stcs(o1 + j * st, d2[j]); __stcs(o2 + j * st, d1[j]); }
+        }
+        // the next iteration starts with wait<0> + __syncthreads, which also orders the reads of bufV / bufO
+        // above before they are overwritten
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
 // x direction: lines contiguous in memory; a tile of L lines is staged through padded shared memory
 __device__ __forceinline__ int xpos(int i) { return i + (i >> 4); }
 
@@ -606,8 +760,45 @@ __global__ void __launch_bounds__(512) line_kernel_contig(LineArgs a) {
     }
 }
 
+bool g_prefetch = false;   // experimental persistent/cp.async variant: measured slower than the direct-load kernel (profiles/), off by default
+
+template <int MODE, bool PER, bool NEED1>
+cudaError_t launch_pf(const LineArgs& a, cudaStream_t stream) {
+    const int threads = a.L * a.T;
+    const long long ntiles = a.nlines / a.L;
+    const size_t smem = (exch_doubles(a.T, a.L) + (size_t)3 * a.T * pf_chunk_stride(a.L)) * sizeof(double);
+    auto k = line_kernel_strided_pf<MODE, PER, NEED1>;
+    static int ctas_per_sm = 0;
+    static size_t smem_set = 0;
+    if (smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        smem_set = smem;
+    }
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem);
+    ctas_per_sm = occ > 0 ? occ : 1;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long long grid = std::min<long long>(ntiles, (long long)sms * ctas_per_sm);
+    k<<<(unsigned)grid, threads, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+inline bool pf_eligible(int mode, const LineArgs& a, bool contig, bool full) {
+    if (!g_prefetch || contig || !full || mode == MODE_NEUMANN) return false;
+    if (a.L < 2 || (a.L & (a.L - 1))) return false;
+    if (a.nlines % a.L || a.inner % a.L || (a.stride & 1) || (a.outer_stride & 1)) return false;
+    auto al = [](const void* p) { return (reinterpret_cast<size_t>(p) & 15) == 0; };
+    if (!al(a.u) || !al(a.u2) || !al(a.vel) || !al(a.out1)) return false;
+    const size_t smem = (exch_doubles(a.T, a.L) + (size_t)3 * a.T * pf_chunk_stride(a.L)) * sizeof(double);
+    return smem <= 200 * 1024;
+}
+
 template <int MODE, bool PER, bool NEED1, bool FULL>
 cudaError_t launch_one(const LineArgs& a, bool contig, cudaStream_t stream) {
+    if (MODE != MODE_NEUMANN && FULL && pf_eligible(MODE, a, contig, FULL)) return launch_pf<(MODE == MODE_NEUMANN ? MODE_P1 : MODE), PER, NEED1>(a, stream);
     const int threads = a.L * a.T;
     const long long blocks = (a.nlines + a.L - 1) / a.L;
     size_t smem = exch_doubles(a.T, a.L) * sizeof(double);
@@ -643,6 +834,8 @@ cudaError_t launch_mode(const LineArgs& a, bool per, bool need1, bool contig, cu
 }
 
 }  // namespace
+
+void set_prefetch(bool on) { g_prefetch = on; }
 
 int pick_lines_per_cta(int T, bool contig, int override_L) {
     if (override_L > 0) return override_L;

@@ -31,6 +31,7 @@ struct LineArgs {
 };
 
 int pick_lines_per_cta(int T, bool contig, int override_L);
+void set_prefetch(bool on);
 int xtile_stride(int n, int L);
 cudaError_t launch_lines(int mode, const LineArgs& a, bool periodic, bool need1, bool contig, cudaStream_t s);
 
