@@ -35,7 +35,7 @@ WORKLOADS = {
 ALG_BYTES_PER_PT_SUBSTEP = 995.0          # 124.4 sweeps of 8 B
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel classes from the committed
 # ncu --set full captures (profiles/), scaled to the C3 grid (bytes per point x points); None if not captured
-TRAFFIC_NCU = {}
+TRAFFIC_BYTES_PER_PT = {"burgers_y": 24.07, "burgers_z": 23.79}   # profiles/ncu_full_burgers_strided_r01.json (U_IN, 512^3)
 PHYS = dict(visc=1.0 / 5000.0, schmidt=[1.0], dtime=1.0e-3)
 
 
@@ -301,7 +301,8 @@ def run_gpu(args):
     avg_ms = ms_cls[cls_names.index(dom)] / cnt_cls[cls_names.index(dom)]
     achieved = line_classes[dom] * N / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": TRAFFIC_NCU.get(dom),
+                "frac": achieved / peak,
+                "traffic": (TRAFFIC_BYTES_PER_PT[dom] * N if dom in TRAFFIC_BYTES_PER_PT else None),
                 "algorithmic_bytes_per_launch": line_classes[dom] * N, "avg_launch_ms": avg_ms,
                 "substep": {"algorithmic_bytes_per_gpu": ALG_BYTES_PER_PT_SUBSTEP * N,
                             "achieved_per_gpu": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9,

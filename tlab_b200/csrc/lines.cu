@@ -489,10 +489,11 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 __host__ __device__ inline int pf_chunk_stride(int L) { return CHUNK * L + (L >= 16 ? 0 : L); }
 
 __device__ __forceinline__ void pf_issue_tile(double* tile, const double* __restrict__ g, long long st, int n, int L, int CS) {
-    const int ppr = L >> 1;                        // 16-byte pieces per row
+    const int ppr = L >> 1;                        // 16-byte pieces per row (L is a power of two)
+    const int sh = __ffs(ppr) - 1;
     const int total = n * ppr;
     for (int q = threadIdx.x; q < total; q += blockDim.x) {
-        const int i = q / ppr, lp = (q - i * ppr) * 2;
+        const int i = q >> sh, lp = (q & (ppr - 1)) * 2;
         cp_async16(tile + (i >> 4) * CS + (i & 15) * L + lp, g + (long long)i * st + lp);
     }
 }

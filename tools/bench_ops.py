@@ -26,10 +26,13 @@ def main():
     ap.add_argument("--poisson", action="store_true")
     ap.add_argument("--json", default="")
     ap.add_argument("--only", default="", help="regular expression selecting the operator labels to run")
+    ap.add_argument("--prefetch", type=int, default=-1, help="1/0: force the persistent cp.async variant of the y/z kernels")
     args = ap.parse_args()
     import torch
     from tlab_b200 import lib as tl, opr
     L = tl.load()
+    if args.prefetch >= 0:
+        tl.check(L.tlab_gpu_set_tuning(b"prefetch", args.prefetch))
     dev = torch.device("cuda:0")
     nx, ny, nz = [int(v) for v in args.shape.split(",")]
     N = nx * ny * nz
