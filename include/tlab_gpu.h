@@ -202,6 +202,14 @@ int tlab_time_substep(tlab_dns_t dns, double dte, double kco, int scale_h);
 int tlab_time_rungekutta_stage(tlab_dns_t dns, double dtime, int stage);
 /* TIME_RUNGEKUTTA, time.f90:185-333: hq = hs = 0, then all stages with dte = dtime*kdt(s) */
 int tlab_time_rungekutta(tlab_dns_t dns, double dtime);
+/* TIME_COURANT, time.f90:365-548 (incompressible branch): dt = min(cfla / max(|u|/dx+|v|/dy+|w|/dz),
+ * cfld / (max(1, 1/Pr, 1/min Sc) * visc * max sum 1/d^2)) with d = g%jac(:,1); *dtime is left untouched when cfla <= 0.
+ * Also returns the reference's logged CFL and diffusion numbers (dns.out columns). */
+int tlab_time_courant(tlab_dns_t dns, double cfla, double cfld, double prandtl, double* dtime, double* cfl_number,
+                      double* diffusion_number);
+/* dilatation bounds of DNS_BOUNDS_CONTROL, src/tools/dns/dns_local.f90:94-234, via FI_INVARIANT_P
+ * (src/mappings/fi_vectorcalculus.f90:111-141): minimum and maximum of div u (dns.out DilMin, DilMax) */
+int tlab_dns_bounds_control(tlab_dns_t dns, double* dil_min, double* dil_max);
 /* same, starting from and returning to HOST arrays q(N,3), s(N,nscal) (pinned memory recommended) */
 int tlab_time_rungekutta_host(tlab_dns_t dns, double dtime, double* q_host, double* s_host);
 

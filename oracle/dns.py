@@ -200,6 +200,44 @@ class Dns:
             for is_ in range(self.inb_scal):
                 self.s[is_] = np.minimum(np.maximum(self.s[is_], self.scal_min), self.scal_max)
 
+    def courant(self, cfla, cfld=None, prandtl=1.0, dtime=0.0):
+        """TIME_COURANT, time.f90:365-548 (incompressible) with the grid factors of TIME_INITIALIZE :136-178.
+        Returns (dtime, CFL number, diffusion number)."""
+        g = self.g
+        cfld = 0.25 * cfla if cfld is None else cfld
+        ods = [1.0 / gi.jac[1:, 1] for gi in g]
+        u, v, w = self.q
+        wrk = np.abs(u) * ods[0][None, None, :] + np.abs(v) * ods[1][None, :, None]
+        if g[2].size > 1:
+            wrk = wrk + np.abs(w) * ods[2][:, None, None]
+        pmax1 = wrk.max()
+        dx2i = 0.0
+        for gi, o in zip(g, ods):
+            if gi.size > 1:
+                dx2i = dx2i + (o * o).max()
+        sf = 1.0
+        sf = max(sf, 1.0 / prandtl)
+        if self.inb_scal:
+            sf = max(sf, 1.0 / min(self.schmidt))
+        pmax2 = sf * self.visc * dx2i
+        dtc = dtd = 1.0e20
+        if pmax1 > 0.0:
+            dtc = cfla / pmax1
+        if pmax2 > 0.0:
+            dtd = cfld / pmax2
+        if cfla > 0.0:
+            dtime = min(dtc, dtd)
+        return dtime, dtime * pmax1, dtime * pmax2
+
+    def bounds_control(self):
+        """DilMin, DilMax of DNS_BOUNDS_CONTROL (dns_local.f90:166-189) through FI_INVARIANT_P."""
+        bcs = [[0, 0], [0, 0]]
+        res = opr_partial(0, OPR_P1, bcs, self.g[0], self.q[0])
+        res = res + opr_partial(1, OPR_P1, bcs, self.g[1], self.q[1])
+        res = -(res + opr_partial(2, OPR_P1, bcs, self.g[2], self.q[2]))
+        amn, amx = res.min(), res.max()
+        return -amx, -amn
+
     def runge_kutta(self, dtime, hook=None):
         """TIME_RUNGEKUTTA, time.f90:185-333 (explicit low-storage branch)."""
         for a in self.hq + self.hs:

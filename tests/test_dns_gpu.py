@@ -98,3 +98,55 @@ def test_scalar_clipping(cuda):
     s = g.get("s1")
     assert s.min() >= 0.0 and s.max() <= 1.0
     assert rel_l2(s, o.s[0]) <= 1e-11
+
+
+def test_courant_and_dilatation(cuda):
+    """TIME_COURANT and the dilatation bounds of DNS_BOUNDS_CONTROL (the dns.out columns dt, CFL#, D#, DilMin, DilMax)."""
+    o, g = _pair(32, 33, 16, "tanh")
+    for cfla in (1.2, -1.0):
+        ro = o.courant(cfla, dtime=1e-3)
+        rg = g.courant(cfla, dtime=1e-3)
+        for a, b in zip(rg, ro):
+            assert abs(a - b) <= 1e-13 * max(1.0, abs(b)), (cfla, rg, ro)
+    do, dg = o.bounds_control(), g.bounds_control()
+    scale = max(abs(do[0]), abs(do[1]))
+    assert abs(dg[0] - do[0]) <= 1e-12 * scale and abs(dg[1] - do[1]) <= 1e-12 * scale
+    dt = ro[0]
+    o.runge_kutta(1e-3)
+    g.runge_kutta(1e-3)
+    do, dg = o.bounds_control(), g.bounds_control()
+    # after a step the interior is divergence free to round-off; the extrema sit at the walls
+    assert abs(dg[0] - do[0]) <= 1e-9 * max(1.0, abs(do[0])) and abs(dg[1] - do[1]) <= 1e-9 * max(1.0, abs(do[1]))
+
+
+def test_case01_shape_two_dimensional_step(cuda):
+    """BASELINE config 1: the 2-D shape of examples/Case01 (512x256x1), one RK4-5 step compared field by field.
+    (The reference's broadband initial condition needs its Fortran RNG; a deterministic shear layer is used.)"""
+    from oracle import fdm, dns as OD
+    from tlab_b200 import opr, dns as GD
+    nx, ny = 512, 256
+    x = grid_periodic(nx, 2.0)
+    y = np.linspace(0.0, 1.0, ny)
+    z = np.zeros(1)
+    go = [fdm.Plan(x, True, True, name="x"), fdm.Plan(y, False, True, name="y"), fdm.Plan(z, True, True, name="z")]
+    gg = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, True, name="y"), opr.FdmPlan(z, True, True, name="z")]
+    D, N = OD.DNS_BCS_DIRICHLET, OD.DNS_BCS_NEUMANN
+    kw = dict(visc=1.0 / 1600.0, schmidt=[1.0], bcs_flow_jmin=(N, D, N), bcs_flow_jmax=(N, D, N),
+              bcs_scal_jmin=(N,), bcs_scal_jmax=(N,))
+    o, g = OD.Dns(go, **kw), GD.Dns(gg, **kw)
+    Y, X = np.meshgrid(y, x, indexing="ij")
+    u = 0.5 * np.tanh((Y - 0.5) / 0.05) + 0.01 * np.sin(2 * np.pi * X) * np.exp(-((Y - 0.5) / 0.1) ** 2)
+    v = 0.01 * np.cos(2 * np.pi * X) * np.exp(-((Y - 0.5) / 0.1) ** 2)
+    s = 0.5 * (1.0 + np.tanh((Y - 0.5) / 0.05))
+    for i, f in enumerate((u, v, np.zeros_like(u))):
+        o.q[i][...] = f[None]
+        g.set("q%d" % (i + 1), f[None])
+    o.s[0][...] = s[None]
+    g.set("s1", s[None])
+    dt = o.courant(1.2)[0]
+    o.runge_kutta(dt)
+    g.runge_kutta(dt)
+    for i in range(2):
+        assert rel_l2(g.get("q%d" % (i + 1)), o.q[i]) <= 1e-11
+    assert np.abs(g.get("q3")).max() == 0.0
+    assert rel_l2(g.get("s1"), o.s[0]) <= 1e-11

@@ -18,6 +18,9 @@
 #include <vector>
 #include <string>
 #include <cstring>
+#include <cfloat>
+#include <cmath>
+#include <algorithm>
 
 namespace tlab {
 
@@ -103,6 +106,89 @@ void rk_tables(int mode, std::vector<double>& kdt, std::vector<double>& ktime, s
     }
 }
 
+// ---- per-step diagnostics --------------------------------------------------------------------------
+// Replaces TIME_COURANT (src/tools/dns/time.f90:365-548, incompressible branch; the grid factors of
+// TIME_INITIALIZE :136-178) and the dilatation part of DNS_BOUNDS_CONTROL (src/tools/dns/dns_local.f90:94-234)
+// with FI_INVARIANT_P (src/mappings/fi_vectorcalculus.f90:111-141) and MINMAX (src/utils/minmax.f90).
+constexpr int RED_THREADS = 256;
+
+__device__ __forceinline__ double warp_max(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v) {
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// per-block max of |u|/dx + |v|/dy + |w|/dz
+__global__ void courant_kernel(const double* __restrict__ u, const double* __restrict__ v, const double* __restrict__ w,
+                               const double* __restrict__ ox, const double* __restrict__ oy, const double* __restrict__ oz,
+                               int nx, int ny, int koff, int three_d, long long n, double* __restrict__ partial) {
+    __shared__ double sm[RED_THREADS / 32];
+    double m = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int ix = (int)(i % nx);
+        const long long r = i / nx;
+        const int iy = (int)(r % ny);
+        const int iz = (int)(r / ny);
+        double val = fabs(u[i]) * ox[ix] + fabs(v[i]) * oy[iy];
+        if (three_d) val = val + fabs(w[i]) * oz[koff + iz];
+        m = fmax(m, val);
+    }
+    m = warp_max(m);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        m = (threadIdx.x < RED_THREADS / 32) ? sm[threadIdx.x] : 0.0;
+        m = warp_max(m);
+        if (threadIdx.x == 0) partial[blockIdx.x] = m;
+    }
+}
+
+__global__ void minmax_kernel(const double* __restrict__ a, long long n, double* __restrict__ pmin, double* __restrict__ pmax) {
+    __shared__ double smin[RED_THREADS / 32], smax[RED_THREADS / 32];
+    double lo = DBL_MAX, hi = -DBL_MAX;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const double v = a[i];
+        lo = fmin(lo, v); hi = fmax(hi, v);
+    }
+    lo = warp_min(lo); hi = warp_max(hi);
+    if ((threadIdx.x & 31) == 0) { smin[threadIdx.x >> 5] = lo; smax[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        lo = (threadIdx.x < RED_THREADS / 32) ? smin[threadIdx.x] : DBL_MAX;
+        hi = (threadIdx.x < RED_THREADS / 32) ? smax[threadIdx.x] : -DBL_MAX;
+        lo = warp_min(lo); hi = warp_max(hi);
+        if (threadIdx.x == 0) { pmin[blockIdx.x] = lo; pmax[blockIdx.x] = hi; }
+    }
+}
+
+__global__ void negate_kernel(double* __restrict__ a, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] = -a[i];
+}
+
+// MPI_ALLREDUCE(MAX) of a few doubles among the z ranks
+int allreduce_max(double* host_vals, int count) {
+    Trp& t = trp();
+    if (t.P == 1) return 0;
+#ifdef TLAB_HAVE_NCCL
+    double* d = nullptr;
+    if (cudaMalloc(&d, count * sizeof(double)) != cudaSuccess) return fail(TLAB_ERR_ALLOC, "allreduce buffer");
+    cudaStream_t st = ctx().stream;
+    cudaMemcpyAsync(d, host_vals, count * sizeof(double), cudaMemcpyHostToDevice, st);
+    ncclResult_t r = ncclAllReduce(d, d, count, ncclDouble, ncclMax, t.comm, st);
+    cudaMemcpyAsync(host_vals, d, count * sizeof(double), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cudaFree(d);
+    if (r != ncclSuccess) return fail(TLAB_ERR_CUDA, std::string("ncclAllReduce: ") + ncclGetErrorString(r));
+    return 0;
+#else
+    return fail(TLAB_ERR_UNDEVELOP, "library built without NCCL");
+#endif
+}
+
+
 }  // namespace
 
 struct Dns {
@@ -117,6 +203,10 @@ struct Dns {
     // z-slab decomposition: nz is the local slab thickness, nzg the global extent, pencils hold N points each
     int P = 1, nzg = 0;
     double *zs = nullptr, *zw = nullptr, *zr = nullptr;
+    // diagnostics: 1/jac per direction, max of sum 1/jac^2, diffusivity factor, reduction partials
+    double* ods[3] = {nullptr, nullptr, nullptr};
+    double dx2i = 0.0, schmidtfactor = 0.0;
+    double* red = nullptr;
     std::vector<double> kdt, ktime, kco;
     std::vector<void*> allocs;
     double* host_stage = nullptr;        // pinned staging buffer for the *_host entry points
@@ -427,6 +517,87 @@ int tlab_time_rk_coefficients(int rkm_mode, double* kdt, double* ktime, double* 
     for (size_t i = 0; i < c.size(); i++) if (kco) kco[i] = c[i];
     return 0;
 }
+
+int tlab_time_courant(tlab_dns_t h, double cfla, double cfld, double prandtl, double* dtime, double* cfl_number,
+                      double* diffusion_number) {
+    if (!h || !dtime) return fail(TLAB_ERR_OPTION, "TIME_COURANT: null argument");
+    Dns& d = h->d;
+    cudaStream_t st = ctx().stream;
+    // grid factors (TIME_INITIALIZE): 1/jac and the maximum of sum 1/jac^2, uploaded once
+    if (!d.ods[0]) {
+        double dx2i_y = 0.0;
+        for (int ig = 0; ig < 3; ig++) {
+            const HostPlan& hp = d.g[ig]->p.h;
+            std::vector<double> o(hp.size);
+            for (int i = 0; i < hp.size; i++) o[i] = 1.0 / hp.jac(i + 1, 1);
+            if (int rc = d.alloc(&d.ods[ig], hp.size)) return rc;
+            cudaMemcpyAsync(d.ods[ig], o.data(), o.size() * sizeof(double), cudaMemcpyHostToDevice, st);
+            cudaStreamSynchronize(st);
+            double mx = 0.0;
+            for (double v : o) mx = std::max(mx, v * v);
+            if (hp.size > 1) dx2i_y += mx;   // the maximum of the sum is the sum of the maxima on a tensor-product grid
+        }
+        d.dx2i = dx2i_y;
+        double sf = 1.0;
+        sf = std::max(sf, 1.0 / prandtl);
+        double smin = 1e300;
+        for (int is = 0; is < d.ns; is++) smin = std::min(smin, d.prm.schmidt[is]);
+        if (d.ns > 0) sf = std::max(sf, 1.0 / smin);
+        d.schmidtfactor = sf * d.prm.visc;
+    }
+    const unsigned blocks = 148 * 8;
+    if (!d.red) { if (int rc = d.alloc(&d.red, 2 * blocks)) return rc; }
+    {
+        ProfScope ps(PC_ELEMENTWISE);
+        courant_kernel<<<blocks, RED_THREADS, 0, st>>>(d.q[0], d.q[1], d.q[2], d.ods[0], d.ods[1], d.ods[2], d.nx, d.ny,
+                                                        trp().rank * d.nz, d.nzg > 1 ? 1 : 0, d.N, d.red);
+    }
+    std::vector<double> part(blocks);
+    if (int rc = cuda_check(cudaMemcpyAsync(part.data(), d.red, blocks * sizeof(double), cudaMemcpyDeviceToHost, st), "courant")) return rc;
+    if (int rc = cuda_check(cudaStreamSynchronize(st), "courant")) return rc;
+    double pmax[2] = {0.0, d.schmidtfactor * d.dx2i};
+    for (double v : part) pmax[0] = std::max(pmax[0], v);
+    if (int rc = allreduce_max(pmax, 2)) return rc;
+    const double big = 1.0e+20;
+    double dtc = big, dtd = big;
+    if (pmax[0] > 0.0) dtc = cfla / pmax[0];
+    if (pmax[1] > 0.0) dtd = cfld / pmax[1];
+    if (cfla > 0.0) *dtime = std::min(std::min(dtc, dtd), big);      // explicit RK: min(dtc, dtd) (time.f90:526-538)
+    if (cfl_number) *cfl_number = *dtime * pmax[0];
+    if (diffusion_number) *diffusion_number = *dtime * pmax[1];
+    return 0;
+}
+
+int tlab_dns_bounds_control(tlab_dns_t h, double* dil_min, double* dil_max) {
+    if (!h || !dil_min || !dil_max) return fail(TLAB_ERR_OPTION, "DNS_BOUNDS_CONTROL: null argument");
+    Dns& d = h->d;
+    cudaStream_t st = ctx().stream;
+    // FI_INVARIANT_P: result = -(du/dx + dv/dy + dw/dz) in tmp1
+    int rc = run_partial(1, TLAB_OPR_P1, d.nx, d.ny, d.nz, 0, d.g[0], d.q[0], d.tmp1, nullptr);
+    if (!rc) rc = run_partial(2, TLAB_OPR_P1, d.nx, d.ny, d.nz, 0, d.g[1], d.q[1], d.tmp1, nullptr, nullptr, 0.0, +1);
+    if (!rc) rc = d.partial_z(d.q[2], nullptr, 0.0, d.tmp1, +1);
+    if (rc) return rc;
+    const unsigned blocks = 148 * 8;
+    if (!d.red) { if ((rc = d.alloc(&d.red, 2 * blocks))) return rc; }
+    {
+        ProfScope ps(PC_ELEMENTWISE);
+        negate_kernel<<<blocks, RED_THREADS, 0, st>>>(d.tmp1, d.N);
+        minmax_kernel<<<blocks, RED_THREADS, 0, st>>>(d.tmp1, d.N, d.red, d.red + blocks);
+    }
+    std::vector<double> part(2 * blocks);
+    if ((rc = cuda_check(cudaMemcpyAsync(part.data(), d.red, 2 * blocks * sizeof(double), cudaMemcpyDeviceToHost, st), "minmax"))) return rc;
+    if ((rc = cuda_check(cudaStreamSynchronize(st), "minmax"))) return rc;
+    double amn = part[0], amx = part[blocks];
+    for (unsigned b = 0; b < blocks; b++) { amn = std::min(amn, part[b]); amx = std::max(amx, part[blocks + b]); }
+    double v[2] = {-amn, amx};      // MIN over ranks as MAX of the negative
+    if ((rc = allreduce_max(v, 2))) return rc;
+    amn = -v[0]; amx = v[1];
+    // MINMAX(..., d_max_loc, d_min_loc); d_min_loc = -d_min_loc; d_max_loc = -d_max_loc  (dns_local.f90:181-182)
+    *dil_max = -amn;
+    *dil_min = -amx;
+    return 0;
+}
+
 
 int tlab_dns_launch_count(tlab_dns_t h, long long* count) {
     if (!h || !count) return fail(TLAB_ERR_OPTION, "tlab_dns_launch_count: null argument");

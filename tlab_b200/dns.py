@@ -95,6 +95,20 @@ class Dns:
         _lib.check(_lib.load().tlab_time_rungekutta_host(self.handle, float(dtime), ctypes.c_void_p(q_host),
                                                          ctypes.c_void_p(s_host)))
 
+    def courant(self, cfla, cfld=None, prandtl=1.0, dtime=0.0):
+        """TIME_COURANT (time.f90:365-548): returns (dtime, CFL number, diffusion number)."""
+        cfld = 0.25 * cfla if cfld is None else cfld          # dns_read_local.f90:72
+        dt, c1, c2 = ctypes.c_double(dtime), ctypes.c_double(), ctypes.c_double()
+        _lib.check(_lib.load().tlab_time_courant(self.handle, float(cfla), float(cfld), float(prandtl), ctypes.byref(dt),
+                                                 ctypes.byref(c1), ctypes.byref(c2)))
+        return dt.value, c1.value, c2.value
+
+    def bounds_control(self):
+        """DNS_BOUNDS_CONTROL dilatation: (DilMin, DilMax) = (min div u, max div u)."""
+        a, b = ctypes.c_double(), ctypes.c_double()
+        _lib.check(_lib.load().tlab_dns_bounds_control(self.handle, ctypes.byref(a), ctypes.byref(b)))
+        return a.value, b.value
+
     def launch_count(self):
         c = ctypes.c_longlong()
         _lib.check(_lib.load().tlab_dns_launch_count(self.handle, ctypes.byref(c)))
