@@ -84,7 +84,11 @@ int tlab_gpu_free(void* ptr);
 int tlab_gpu_upload(void* dst_device, const void* src_host, size_t bytes);
 int tlab_gpu_download(void* dst_host, const void* src_device, size_t bytes);
 int tlab_gpu_copy(void* dst_device, const void* src_device, size_t bytes);
-int tlab_gpu_set_tuning(const char* key, int value); /* "lines_x", "lines_yz": lines per CTA (0 = automatic) */
+/* "lines_x", "lines_yz": lines per CTA of the general line kernels (0 = automatic); "fast": 1/0 use the fast line
+ * kernels where the geometry allows (default 1); "pf_dist": their L2 prefetch distance in tiles (-1 automatic, 0 off) */
+int tlab_gpu_set_tuning(const char* key, int value);
+/* launch counters: "fast_launches", "general_launches" (line kernels since start-up) */
+int tlab_gpu_get_counter(const char* key, long long* value);
 
 /* the CUDA stream (cudaStream_t) every call is ordered on, for event timing by the host */
 int tlab_gpu_stream(void** stream);

@@ -25,7 +25,11 @@ def _plans(nx, ny, nz, ykind="stretched", xper=True, zper=True):
 CASES = [(64, 48, 32, "stretched", True, True),
          (50, 33, 20, "tanh", True, True),          # ragged: chunk sizes 16/17, lines not a multiple of the tile
          (32, 16, 17, "uniform", False, False),      # biased schemes in all directions, single-chunk y
-         (130, 40, 36, "stretched", True, False)]
+         (130, 40, 36, "stretched", True, False),
+         (256, 32, 16, "tanh", True, True),          # fast kernels: constant interior chunks + circulant closure in x
+         (16, 48, 256, "stretched", True, True),     # the same in z; single-chunk x
+         (32, 256, 16, "uniform", True, True),       # uniform non-periodic y: constant interior chunks
+         (64, 64, 64, "tanh", False, False)]         # biased schemes on full chunks in all directions
 
 
 @pytest.mark.parametrize("case", CASES)
@@ -131,3 +135,45 @@ def test_fdm_solve_lines_first(cuda):
     opr.FDM_Der2_Solve(nlines, gg, u, r)
     d1 = fdm.der1_solve(0, go.der1, go.der1.lu, u_np)
     assert rel_l2(r.cpu().numpy(), fdm.der2_solve(go.der2, go.der2.lu, u_np, d1)) <= TOL
+
+
+@pytest.mark.parametrize("shape", [(128, 96, 64), (1024, 32, 16), (16, 64, 1024)])
+def test_fast_and_general_kernels_agree(cuda, shape):
+    """The fast kernels (lines2.cu) and the general ones (lines.cu) are two formulations of the same solves.  On long
+    uniform lines the fast kernels replace the reference's LU factors in the interior by their converged values; the
+    factors carry round-off noise of relative size ~eps*n from the numerically differentiated Jacobian, hence 5e-13."""
+    import torch
+    from tlab_b200 import lib as tl, opr
+    nx, ny, nz = shape
+    grids, go, gg = _plans(nx, ny, nz, "tanh")
+    visc = 1.0 / 5000.0
+    opr.OPR_Burgers_Initialize(gg, visc, [1.0])
+    u = torch.from_numpy(smooth_field((nz, ny, nx), grids, seed=3)).to(cuda)
+    v = torch.from_numpy(smooth_field((nz, ny, nx), grids, seed=4)).to(cuda)
+    P = [opr.OPR_Partial_X, opr.OPR_Partial_Y, opr.OPR_Partial_Z]
+    B = [opr.OPR_Burgers_X, opr.OPR_Burgers_Y, opr.OPR_Burgers_Z]
+    bcs = [[0, 0], [0, 0]]
+    out = {}
+    import ctypes
+    cnt = {}
+    try:
+        for fast in (0, 1):
+            tl.check(tl.load().tlab_gpu_set_tuning(b"fast", fast))
+            c = ctypes.c_longlong()
+            tl.check(tl.load().tlab_gpu_get_counter(b"fast_launches", ctypes.byref(c)))
+            cnt[fast] = c.value
+            res = []
+            for d in range(3):
+                r1, r2, r3, r4 = (torch.full_like(u, float("nan")) for _ in range(4))
+                P[d](opr.OPR_P2_P1, nx, ny, nz, bcs, gg[d], u, r1, r2)
+                B[d](opr.OPR_B_U_IN, 0, nx, ny, nz, bcs, u, v, r3)
+                P[d](opr.OPR_P1, nx, ny, nz, bcs, gg[d], u, r4)
+                res += [r1, r2, r3, r4]
+            out[fast] = res
+    finally:
+        tl.check(tl.load().tlab_gpu_set_tuning(b"fast", 1))
+    c = ctypes.c_longlong()
+    tl.check(tl.load().tlab_gpu_get_counter(b"fast_launches", ctypes.byref(c)))
+    assert cnt[1] == cnt[0] and c.value == cnt[1] + 9, "the fast kernels did not run"
+    for a, b in zip(out[0], out[1]):
+        assert float(torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(a)) <= (1e-13 if max(shape) <= 128 else 5e-13)

@@ -2,6 +2,7 @@
 #include "../../include/tlab_gpu.h"
 #include "context.h"
 #include <cstring>
+#include <algorithm>
 #include <cstdio>
 #include <vector>
 
@@ -78,6 +79,43 @@ static void set_geometry(LineArgs& a, int dir, int nx, int ny, int nz, bool& con
     a.xstride = contig ? xtile_stride(a.n, a.L) : 0;
 }
 
+
+// fast path (lines2.cu): full chunks, aligned tiles, short look-back windows; otherwise the general kernels of lines.cu
+static cudaError_t launch_any(int mode, const LineArgs& a, const DevPlan& p, const Sys2& s1, const Sys2& s2, bool periodic,
+                              bool need1, bool contig, cudaStream_t st) {
+    int L = 0;
+    bool fast = ctx().tune_fast != 0 && lines2_eligible(p, s1, &s2, a.n, a.nlines, a.inner, contig,
+                                                         contig ? ctx().tune_lines_x : ctx().tune_lines_yz, &L);
+    if (fast && contig) {
+        auto al = [](const void* q) { return (reinterpret_cast<size_t>(q) & 15) == 0; };
+        fast = al(a.u) && al(a.u2) && al(a.vel) && al(a.out1) && al(a.out2);
+    }
+    if (!fast) { ctx().general_launches++; return launch_lines(mode, a, periodic, need1, contig, st); }
+    ctx().fast_launches++;
+    Line2Args b;
+    b.n = a.n; b.T = a.n / CHUNK; b.L = L;
+    b.xls = contig ? lines2_xstride(b.T, L) : 0;
+    if (!contig && ctx().tune_persist && mode != MODE_NEUMANN && !(a.u2 && mode == MODE_BURGERS)) {
+        auto al = [](const void* q) { return (reinterpret_cast<size_t>(q) & 15) == 0; };
+        b.persist = al(a.u) && al(a.u2) && al(a.vel) && (a.stride % 2 == 0) && (a.outer_stride % 2 == 0) && (L % 2 == 0) &&
+                    lines2_persist_smem(b.T, L) <= 220 * 1024;
+    }
+    b.lshift = 0;
+    while ((1 << b.lshift) < L) b.lshift++;
+    b.accumulate = a.accumulate; b.scale = a.scale;
+    // L2 prefetch of a later tile: pays for x lines and for y lines (rows a few KB apart); with rows MBs apart (z) it
+    // costs bandwidth (measured, profiles/ops_c2_r01_v9.json), so there it is on request only
+    b.pf_dist = (contig || a.stride <= 4096) ? ctx().tune_pf_dist : std::max(ctx().tune_pf_dist, 0);
+    b.stride = a.stride; b.inner = a.inner; b.outer_stride = a.outer_stride;
+    b.u = a.u; b.u2 = a.u2; b.vel = a.vel; b.out1 = a.out1; b.out2 = a.out2; b.bcs_hb = a.bcs_hb; b.bcs_ht = a.bcs_ht;
+    b.rhs_d1 = p.rhs_d1_2;
+    b.rhs1 = a.rhs1; b.rhs2 = a.rhs2; b.s1 = s1; b.s2 = s2;
+    std::memcpy(b.neu_bot, a.neu_bot, sizeof(b.neu_bot));
+    std::memcpy(b.neu_top, a.neu_top, sizeof(b.neu_top));
+    b.neu_lu_bot = a.neu_lu_bot; b.neu_lu_top = a.neu_lu_top;
+    return launch_lines2(mode, b, periodic, need1, contig, a.nlines, a.inner, st);
+}
+
 static int check_dims(int dir, int nx, int ny, int nz, const tlab_plan_s* g) {
     const int n = (dir == 1) ? nx : (dir == 2 ? ny : nz);
     if (!g) return fail(TLAB_ERR_OPTION, "null plan");
@@ -115,7 +153,7 @@ int run_partial(int dir, int type, int nx, int ny, int nz, int ibc, tlab_plan_s*
     a.lu2 = p.lu2[0];
     const int mode = (type == TLAB_OPR_P1) ? MODE_P1 : (type == TLAB_OPR_P2 ? MODE_P2 : MODE_P2_P1);
     ProfScope ps(PC_PARTIAL_X + dir - 1);
-    return cuda_check(launch_lines(mode, a, p.periodic, p.need_1der, contig, st), "line kernel");
+    return cuda_check(launch_any(mode, a, p, p.sys1[ibc], p.sys2[0], p.periodic, p.need_1der, contig, st), "line kernel");
 }
 
 int run_burgers(int dir, int is, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* s, const double* vel,
@@ -140,7 +178,7 @@ int run_burgers(int dir, int is, int nx, int ny, int nz, int ibc, tlab_plan_s* g
     a.lu1 = p.lu1[ibc];
     a.lu2 = p.lu2[g->burgers_first + is];
     ProfScope ps(PC_BURGERS_X + dir - 1);
-    return cuda_check(launch_lines(MODE_BURGERS, a, p.periodic, p.need_1der, contig, st), "burgers kernel");
+    return cuda_check(launch_any(MODE_BURGERS, a, p, p.sys1[ibc], p.sys2[g->burgers_first + is], p.periodic, p.need_1der, contig, st), "burgers kernel");
 }
 
 int run_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_s* g, const double* u, double* hb, double* ht) {
@@ -171,7 +209,7 @@ int run_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_s* g, const double*
     a.neu_lu_bot = p.neu_lu_bot[ibc];
     a.neu_lu_top = p.neu_lu_top[ibc];
     ProfScope ps(PC_NEUMANN);
-    return cuda_check(launch_lines(MODE_NEUMANN, a, false, false, false, st), "neumann kernel");
+    return cuda_check(launch_any(MODE_NEUMANN, a, p, p.sys1[ibc], p.sys2[0], false, false, false, st), "neumann kernel");
 }
 
 }  // namespace tlab
@@ -279,7 +317,18 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     if (!std::strcmp(key, "lines_x")) ctx().tune_lines_x = value;
     else if (!std::strcmp(key, "lines_yz")) ctx().tune_lines_yz = value;
     else if (!std::strcmp(key, "prefetch")) set_prefetch(value != 0);
+    else if (!std::strcmp(key, "fast")) ctx().tune_fast = value;
+    else if (!std::strcmp(key, "pf_dist")) ctx().tune_pf_dist = value;
+    else if (!std::strcmp(key, "persist")) ctx().tune_persist = value;
     else return fail(TLAB_ERR_OPTION, std::string("unknown tuning key ") + key);
+    return 0;
+}
+
+int tlab_gpu_get_counter(const char* key, long long* value) {
+    if (!key || !value) return fail(TLAB_ERR_OPTION, "null argument");
+    if (!std::strcmp(key, "fast_launches")) *value = ctx().fast_launches;
+    else if (!std::strcmp(key, "general_launches")) *value = ctx().general_launches;
+    else return fail(TLAB_ERR_OPTION, std::string("unknown counter ") + key);
     return 0;
 }
 

@@ -2,6 +2,7 @@
 #pragma once
 #include "plan.h"
 #include "lines.h"
+#include "lines2.h"
 #include <string>
 #include <vector>
 #include <cuda_runtime.h>
@@ -22,6 +23,10 @@ struct Context {
     bool async = false;
     std::string last_error;
     int tune_lines_x = 0, tune_lines_yz = 0;
+    int tune_fast = 1;        // 1: use the fast line kernels (lines2.cu) whenever the geometry allows
+    int tune_pf_dist = -1;
+    int tune_persist = 0;     // strided fast kernels: persistent CTAs with asynchronous staging
+    long long fast_launches = 0, general_launches = 0;    // L2 prefetch distance of the fast kernels in tiles (-1: automatic, 0: off)
     tlab_plan_s* burgers_plans[3] = {nullptr, nullptr, nullptr};
     bool profiling = false;
     struct ProfRec { int cls; cudaEvent_t a, b; };

@@ -1,0 +1,860 @@
+// Fast path of the batched compact-scheme line operators for sm_100a (lines whose length is a multiple of CHUNK).
+//
+// Same operator surface as lines.cu -- OPR_Partial (P1, P2, P2_P1), OPR_Burgers and BOUNDARY_BCS_NEUMANN_Y of the
+// reference (src/operators/opr_partial.f90:31-377, src/physics/opr_burgers.f90:190-521,
+// src/tools/dns/boundary_bcs.f90:368-473; banded products src/fdm/fdm_matmul.f90; Thomas sweeps
+// src/utils/linear3.f90:56-150,321-442) -- with a cheaper formulation of the factored tridiagonal solves:
+//
+//   * a line of n points is owned by T = n/16 threads, 16 consecutive points each, in registers;
+//   * each thread runs the forward and the backward substitution of its chunk ONCE, with zero inflow:
+//         y_j = f_j + a_j y_{j-1},      x^_j = d_j y_j + g_j x^_{j+1}
+//     (beta of the circulant factorisation is folded into a and d on the host);
+//   * both sweeps are linear, so the true solution of the chunk is
+//         x_j = x^_j + Q_j A + R_j B + S_j x_N
+//     with A the true forward value at the end of the previous chunk, B the (x_N-free) true solution at the start of
+//     the next chunk and x_N the rank-one closure of the circulant system; Q, R, S are precomputed per point
+//     (constants of the scheme in the interior of a uniform direction, tables elsewhere);
+//   * A and B are weighted sums of at most 6 published chunk ends (the multipliers of a chunk are < 1e-6, the
+//     dropped tail is < 2^-80): two block barriers per solve instead of four, two dependent chains instead of four,
+//     5 flops per point and system instead of 8.
+//
+// Memory: y and z lines are strided in memory and contiguous across lines, so the threads of L = 4 adjacent lines
+// load their chunks straight into registers (32-byte sectors); x lines are contiguous, a tile of L lines is staged
+// through shared memory with 16-byte accesses on both sides (chunk blocks padded to 18 doubles: conflict-free).
+// Every CTA also prefetches into L2 the tile that the CTA `pf_dist` places later will work on, so that the DRAM
+// latency of a tile is paid while earlier tiles are being solved.
+#include "lines2.h"
+#include <algorithm>
+
+namespace tlab {
+
+namespace {
+
+constexpr int C = CHUNK;
+constexpr int XB = C + 2;          // padded chunk block of the x tile (doubles)
+
+#define DMUL(a, b) __dmul_rn((a), (b))
+#define DADD(a, b) __dadd_rn((a), (b))
+#define DSUB(a, b) __dsub_rn((a), (b))
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
+
+// ------------------------------------------------------------------------------------------------
+// banded right-hand sides (explicitly rounded, reference association order; see lines.cu)
+template <bool SECOND>
+__device__ __forceinline__ void rhs_interior(const double (&u)[C + 6], double (&f)[C], const RhsTab& R) {
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        if (SECOND) {
+            // r4*u(n) + u(n+1) + u(n-1) + r6*(u(n+2) + u(n-2)) + r7*(u(n+3) + u(n-3)), fdm_matmul.f90:608-612
+            double s = DADD(DADD(DMUL(R.rc, u[j + 3]), u[j + 4]), u[j + 2]);
+            s = DADD(s, DMUL(R.r2, DADD(u[j + 5], u[j + 1])));
+            if (R.r3 != 0.0) s = DADD(s, DMUL(R.r3, DADD(u[j + 6], u[j])));
+            f[j] = s;
+        } else {
+            // u(n+1) - u(n-1) + r5*(u(n+2) - u(n-2)), fdm_matmul.f90:396-398
+            double s = DSUB(u[j + 4], u[j + 2]);
+            if (R.r2 != 0.0) s = DADD(s, DMUL(R.r2, DSUB(u[j + 5], u[j + 1])));
+            f[j] = s;
+        }
+    }
+}
+
+// special rows at the walls.  All BROW_W terms are added in the reference's column order; a zero coefficient
+// contributes an exact zero, so the sum is the one of the reference's (sparser) row.
+__device__ __forceinline__ void rhs_bottom(const double (&u)[C + 6], double (&f)[C], const RhsTab& R) {
+#pragma unroll
+    for (int i = 0; i < MAX_BROWS; i++) {
+        if (i < R.nb) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < BROW_W; k++) s = DADD(s, DMUL(R.bot[i][k], u[3 + k]));
+            f[i] = s;
+        }
+    }
+}
+__device__ __forceinline__ void rhs_top(const double (&u)[C + 6], double (&f)[C], const RhsTab& R) {
+#pragma unroll
+    for (int q = 0; q < MAX_BROWS; q++) {
+        if (q < R.nb) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = BROW_W - 1; k >= 0; k--) s = DADD(s, DMUL(R.top[q][k], u[3 + C - 1 - k]));
+            f[C - 1 - q] = s;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// solves.  Shared exchange area of one system: y[T*L] | z[T*L] | w[T*L]
+__host__ __device__ inline int exch2_per_system(int T, int L) { return 3 * T * L; }
+
+struct ChunkCtx {
+    int t, T, l, L;
+};
+
+__device__ __forceinline__ const double2* tab_ptr(const Sys2& S, int t) {
+    return S.tab + ((size_t)(t >> 3) * C * 4) * 8 + (t & 7);
+}
+
+// zero-inflow sweeps of one chunk with tabulated coefficients
+template <bool PER>
+__device__ __forceinline__ void local_tab(double (&f)[C], const double2* __restrict__ tp, double& yend, double& part) {
+    double e = 0.0, pr = 0.0;
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        const double2 ap = ldg2(tp + (j * 4 + 0) * 8);
+        e = fma(ap.x, e, f[j]);
+        f[j] = e;
+        if (PER) pr = fma(ap.y, e, pr);
+    }
+    yend = e;
+    part = pr;
+    double xb = 0.0;
+#pragma unroll
+    for (int j = C - 1; j >= 0; j--) {
+        const double2 dg = ldg2(tp + (j * 4 + 1) * 8);
+        xb = fma(dg.y, xb, dg.x * f[j]);
+        f[j] = xb;
+    }
+}
+
+__device__ __forceinline__ void local_const(double (&f)[C], const Sys2& S, double& yend) {
+    double e = 0.0;
+#pragma unroll
+    for (int j = 0; j < C; j++) { e = fma(S.ca, e, f[j]); f[j] = e; }
+    yend = e;
+    double xb = 0.0;
+#pragma unroll
+    for (int j = C - 1; j >= 0; j--) { xb = fma(S.cg, xb, S.cd * f[j]); f[j] = xb; }
+}
+
+__device__ __forceinline__ void local_const2(double (&f0)[C], double (&f1)[C], const Sys2& S0, const Sys2& S1,
+                                             double& yend0, double& yend1) {
+    double e0 = 0.0, e1 = 0.0;
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        e0 = fma(S0.ca, e0, f0[j]); f0[j] = e0;
+        e1 = fma(S1.ca, e1, f1[j]); f1[j] = e1;
+    }
+    yend0 = e0; yend1 = e1;
+    double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+    for (int j = C - 1; j >= 0; j--) {
+        x0 = fma(S0.cg, x0, S0.cd * f0[j]); f0[j] = x0;
+        x1 = fma(S1.cg, x1, S1.cd * f1[j]); f1[j] = x1;
+    }
+}
+
+// A = sum_k wf[k] y(t-k)
+__device__ __forceinline__ double look_back(const double* __restrict__ y, const double2* __restrict__ cr, const ChunkCtx& c) {
+    const double2 w01 = ldg2(cr + 0), w23 = ldg2(cr + 1), w45 = ldg2(cr + 2);
+    double A = w01.x * y[max(c.t - 1, 0) * c.L + c.l];
+    A = fma(w01.y, y[max(c.t - 2, 0) * c.L + c.l], A);
+    A = fma(w23.x, y[max(c.t - 3, 0) * c.L + c.l], A);
+    A = fma(w23.y, y[max(c.t - 4, 0) * c.L + c.l], A);
+    A = fma(w45.x, y[max(c.t - 5, 0) * c.L + c.l], A);
+    A = fma(w45.y, y[max(c.t - 6, 0) * c.L + c.l], A);
+    return A;
+}
+// B = sum_k wb[k] z(t+k)
+__device__ __forceinline__ double look_ahead(const double* __restrict__ z, const double2* __restrict__ cr, const ChunkCtx& c) {
+    const double2 w01 = ldg2(cr + 3), w23 = ldg2(cr + 4), w45 = ldg2(cr + 5);
+    const int last = c.T - 1;
+    double B = w01.x * z[min(c.t + 1, last) * c.L + c.l];
+    B = fma(w01.y, z[min(c.t + 2, last) * c.L + c.l], B);
+    B = fma(w23.x, z[min(c.t + 3, last) * c.L + c.l], B);
+    B = fma(w23.y, z[min(c.t + 4, last) * c.L + c.l], B);
+    B = fma(w45.x, z[min(c.t + 5, last) * c.L + c.l], B);
+    B = fma(w45.y, z[min(c.t + 6, last) * c.L + c.l], B);
+    return B;
+}
+__device__ __forceinline__ double closure(const double* __restrict__ w, const Sys2& S, const ChunkCtx& c) {
+    double xN = 0.0;
+    for (int k = 0; k < S.K0; k++) xN += w[k * c.L + c.l];
+    for (int k = c.T - S.K1; k < c.T; k++) xN += w[k * c.L + c.l];
+    return xN;
+}
+
+template <bool PER>
+__device__ __forceinline__ void finish_tab(double (&f)[C], const double2* __restrict__ tp, double A, double B, double xN) {
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        const double2 qr = ldg2(tp + (j * 4 + 2) * 8);
+        double v = fma(qr.x, A, fma(qr.y, B, f[j]));
+        if (PER) v = fma(__ldg(&tp[(j * 4 + 3) * 8].x), xN, v);
+        f[j] = v;
+    }
+}
+__device__ __forceinline__ void finish_const(double (&f)[C], const Sys2& S, double A, double B) {
+#pragma unroll
+    for (int j = 0; j < C; j++) f[j] = fma(S.cQ[j], A, fma(S.cR[j], B, f[j]));
+}
+
+// one system; returns B (the true solution at the start of the next chunk, up to the x_N part) for the caller
+template <bool PER>
+__device__ __forceinline__ void solve_one(double (&f)[C], const Sys2& S, const ChunkCtx& c, double* sm) {
+    const int TL = c.T * c.L;
+    double* y = sm;
+    double* z = sm + TL;
+    double* w = sm + 2 * TL;
+    const double2* cr = reinterpret_cast<const double2*>(S.crec) + c.t * 8;
+    const double2 q0pp = ldg2(cr + 6);
+    const bool isc = ldg2(cr + 7).x != 0.0;
+    const double2* tp = tab_ptr(S, c.t);
+    double yend, part = 0.0;
+    if (isc) local_const(f, S, yend);
+    else local_tab<PER>(f, tp, yend, part);
+    y[c.t * c.L + c.l] = yend;
+    __syncthreads();
+    const double A = look_back(y, cr, c);
+    z[c.t * c.L + c.l] = fma(q0pp.x, A, f[0]);
+    if (PER) w[c.t * c.L + c.l] = fma(q0pp.y, A, part);
+    __syncthreads();
+    const double B = look_ahead(z, cr, c);
+    if (isc) finish_const(f, S, A, B);
+    else {
+        const double xN = PER ? closure(w, S, c) : 0.0;
+        finish_tab<PER>(f, tp, A, B, xN);
+    }
+}
+
+// two independent systems sharing the barriers
+template <bool PER>
+__device__ __forceinline__ void solve_two(double (&f0)[C], double (&f1)[C], const Sys2& S0, const Sys2& S1,
+                                          const ChunkCtx& c, double* sm) {
+    const int TL = c.T * c.L;
+    double* y0 = sm;
+    double* z0 = sm + TL;
+    double* w0 = sm + 2 * TL;
+    double* y1 = sm + 3 * TL;
+    double* z1 = sm + 4 * TL;
+    double* w1 = sm + 5 * TL;
+    const double2* cr0 = reinterpret_cast<const double2*>(S0.crec) + c.t * 8;
+    const double2* cr1 = reinterpret_cast<const double2*>(S1.crec) + c.t * 8;
+    const double2 q0 = ldg2(cr0 + 6), q1 = ldg2(cr1 + 6);
+    const bool c0 = ldg2(cr0 + 7).x != 0.0, c1 = ldg2(cr1 + 7).x != 0.0;
+    const double2* tp0 = tab_ptr(S0, c.t);
+    const double2* tp1 = tab_ptr(S1, c.t);
+    double ye0, ye1, p0 = 0.0, p1 = 0.0;
+    if (c0 && c1) local_const2(f0, f1, S0, S1, ye0, ye1);
+    else {
+        if (c0) local_const(f0, S0, ye0); else local_tab<PER>(f0, tp0, ye0, p0);
+        if (c1) local_const(f1, S1, ye1); else local_tab<PER>(f1, tp1, ye1, p1);
+    }
+    const int me = c.t * c.L + c.l;
+    y0[me] = ye0;
+    y1[me] = ye1;
+    __syncthreads();
+    const double A0 = look_back(y0, cr0, c), A1 = look_back(y1, cr1, c);
+    z0[me] = fma(q0.x, A0, f0[0]);
+    z1[me] = fma(q1.x, A1, f1[0]);
+    if (PER) { w0[me] = fma(q0.y, A0, p0); w1[me] = fma(q1.y, A1, p1); }
+    __syncthreads();
+    const double B0 = look_ahead(z0, cr0, c), B1 = look_ahead(z1, cr1, c);
+    if (c0 && c1) {
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            f0[j] = fma(S0.cQ[j], A0, fma(S0.cR[j], B0, f0[j]));
+            f1[j] = fma(S1.cQ[j], A1, fma(S1.cR[j], B1, f1[j]));
+        }
+    } else {
+        if (c0) finish_const(f0, S0, A0, B0);
+        else finish_tab<PER>(f0, tp0, A0, B0, PER ? closure(w0, S0, c) : 0.0);
+        if (c1) finish_const(f1, S1, A1, B1);
+        else finish_tab<PER>(f1, tp1, A1, B1, PER ? closure(w1, S1, c) : 0.0);
+    }
+}
+
+// Jacobian correction of the second derivative on non-uniform grids: f2 += A2*jac2 * du (tridiagonal, extended
+// stencil in the first and last row; fdm_matmul.f90:143-145, fdm_derivative.f90:437-440).  The neighbours' end
+// values go through shared memory (one barrier).
+__device__ __forceinline__ void add_jacobian_term(double (&f2)[C], const double (&d1)[C], const Line2Args& a,
+                                                  const ChunkCtx& c, double* sm_h) {
+    sm_h[(2 * c.t) * c.L + c.l] = d1[0];
+    sm_h[(2 * c.t + 1) * c.L + c.l] = d1[C - 1];
+    __syncthreads();
+    const double left = (c.t > 0) ? sm_h[(2 * (c.t - 1) + 1) * c.L + c.l] : d1[2];              // extended stencil, first row
+    const double right = (c.t < c.T - 1) ? sm_h[(2 * (c.t + 1)) * c.L + c.l] : d1[C - 3];       // extended stencil, last row
+    const double2* rp = a.rhs_d1 + ((size_t)(c.t >> 3) * C * 2) * 8 + (c.t & 7);
+    const bool lastc = (c.t == c.T - 1);
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        const double2 r12 = ldg2(rp + (j * 2 + 0) * 8);
+        const double r3 = __ldg(&rp[(j * 2 + 1) * 8].x);
+        const double um = (j == 0) ? left : d1[j > 0 ? j - 1 : 0];
+        const double up = (j == C - 1) ? right : d1[j < C - 1 ? j + 1 : C - 1];
+        if (j == C - 1 && lastc) f2[j] = DADD(DADD(DADD(f2[j], DMUL(up, r3)), DMUL(um, r12.x)), DMUL(d1[j], r12.y));
+        else f2[j] = DADD(DADD(DADD(f2[j], DMUL(um, r12.x)), DMUL(d1[j], r12.y)), DMUL(up, r3));
+    }
+}
+
+__host__ __device__ inline size_t exch2_doubles(int T, int L) { return (size_t)6 * T * L + (size_t)2 * T * L; }
+
+// right-hand sides + solves: u (chunk + halos) -> d1, d2
+template <int MODE, bool PER, bool NEED1>
+__device__ __forceinline__ void line_core2(const double (&u)[C + 6], const Line2Args& a, const ChunkCtx& c, double* sm,
+                                           double (&d1)[C], double (&d2)[C]) {
+    constexpr bool WANT1 = (MODE == MODE_P1) || (MODE == MODE_P2_P1) || (MODE == MODE_BURGERS) || (MODE == MODE_NEUMANN) || NEED1;
+    constexpr bool WANT2 = (MODE == MODE_P2) || (MODE == MODE_P2_P1) || (MODE == MODE_BURGERS);
+    if (WANT1) {
+        rhs_interior<false>(u, d1, a.rhs1);
+        if (!PER) {
+            if (c.t == 0) rhs_bottom(u, d1, a.rhs1);
+            if (c.t == c.T - 1) rhs_top(u, d1, a.rhs1);
+        }
+    }
+    if (WANT2) {
+        rhs_interior<true>(u, d2, a.rhs2);
+        if (!PER) {
+            if (c.t == 0) rhs_bottom(u, d2, a.rhs2);
+            if (c.t == c.T - 1) rhs_top(u, d2, a.rhs2);
+        }
+    }
+    if (WANT1 && WANT2 && !NEED1) {
+        solve_two<PER>(d1, d2, a.s1, a.s2, c, sm);
+    } else {
+        if (WANT1) solve_one<PER>(d1, a.s1, c, sm);
+        if (WANT2) {
+            if (NEED1) add_jacobian_term(d2, d1, a, c, sm + 6 * c.T * c.L);
+            solve_one<PER>(d2, a.s2, c, sm + 3 * c.T * c.L);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// y / z directions: lines strided in memory, contiguous across lines.  grid = (inner / L, nlines / inner)
+template <int MODE, bool PER, bool NEED1>
+__global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__ Line2Args a) {
+    extern __shared__ double sm[];
+    ChunkCtx c;
+    c.L = a.L; c.T = a.T;
+    c.l = threadIdx.x & (a.L - 1);
+    c.t = threadIdx.x >> a.lshift;
+    const long long st = a.stride;
+    const long long tile0 = (long long)blockIdx.y * a.outer_stride + (long long)blockIdx.x * a.L;
+    const long long lbase = tile0 + c.l;
+    const int n = a.n;
+    const bool has_u2 = (a.u2 != nullptr);
+    const bool has_acc = (a.accumulate != 0) && (MODE == MODE_BURGERS || MODE == MODE_P1);
+
+    // ---- L2 prefetch of a later tile (one 32..64-byte row segment per request)
+    if (a.pf_dist > 0) {
+        const unsigned tile = blockIdx.y * gridDim.x + blockIdx.x + (unsigned)a.pf_dist;
+        if (tile < gridDim.x * gridDim.y) {
+            const unsigned ty = tile / gridDim.x, tx = tile - ty * gridDim.x;
+            const long long pb = (long long)ty * a.outer_stride + (long long)tx * a.L;
+            for (int r = threadIdx.x; r < n; r += blockDim.x) {
+                const long long o = pb + (long long)r * st;
+                prefetch_l2(a.u + o);
+                if (has_u2) prefetch_l2(a.u2 + o);
+                if (MODE == MODE_BURGERS && a.vel != a.u) prefetch_l2(a.vel + o);
+                if (has_acc) prefetch_l2(a.out1 + o);
+            }
+        }
+    }
+
+    // ---- chunk + two 3-point halos (wrapped or zero)
+    double u[C + 6];
+    const long long coff = lbase + (long long)(c.t * C) * st;
+    const bool lok = PER || c.t > 0, rok = PER || c.t < c.T - 1;
+    const long long loff = (c.t > 0) ? -3 * st : (long long)(n - 3) * st;
+    const long long roff = (c.t < c.T - 1) ? (long long)C * st : -(long long)(c.t * C) * st;
+    {
+        const double* __restrict__ pc = a.u + coff;
+#pragma unroll
+        for (int j = 0; j < C; j++) u[j + 3] = __ldcs(pc + j * st);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            u[k] = lok ? __ldcs(pc + loff + k * st) : 0.0;
+            u[C + 3 + k] = rok ? __ldcs(pc + roff + k * st) : 0.0;
+        }
+        if (has_u2) {
+            const double* __restrict__ p2 = a.u2 + coff;
+#pragma unroll
+            for (int j = 0; j < C; j++) u[j + 3] = u[j + 3] + __ldcs(p2 + j * st) * a.scale;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (lok) u[k] = u[k] + __ldcs(p2 + loff + k * st) * a.scale;
+                if (rok) u[C + 3 + k] = u[C + 3 + k] + __ldcs(p2 + roff + k * st) * a.scale;
+            }
+        }
+    }
+    double nb_sum = 0.0, nt_sum = 0.0;
+    if (MODE == MODE_NEUMANN) {
+#pragma unroll
+        for (int k = 0; k < BROW_W; k++) {
+            nb_sum = nb_sum + a.neu_bot[k] * u[3 + k];
+            nt_sum = nt_sum + a.neu_top[k] * u[3 + C - 1 - k];
+        }
+    }
+    double d1[C], d2[C];
+    line_core2<MODE, PER, NEED1>(u, a, c, sm, d1, d2);
+
+    if (MODE == MODE_NEUMANN) {
+        // boundary values such that the normal derivative vanishes (BOUNDARY_BCS_NEUMANN_Y)
+        const long long line = (long long)blockIdx.y * a.inner + (long long)blockIdx.x * a.L + c.l;
+        if (c.t == 0 && a.bcs_hb != nullptr) a.bcs_hb[line] = nb_sum + a.neu_lu_bot * d1[1];
+        if (c.t == c.T - 1 && a.bcs_ht != nullptr) a.bcs_ht[line] = nt_sum + a.neu_lu_top * d1[C - 2];
+        return;
+    }
+    double* __restrict__ o1 = a.out1 + coff;
+    if (MODE == MODE_BURGERS) {
+        const double* __restrict__ vp = a.vel + coff;
+        double vv[C];
+#pragma unroll
+        for (int j = 0; j < C; j++) vv[j] = __ldcs(vp + j * st);
+        if (has_acc) {
+            double oo[C];
+#pragma unroll
+            for (int j = 0; j < C; j++) oo[j] = __ldcs(o1 + j * st);
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                const double r = d2[j] - vv[j] * d1[j];
+                d2[j] = (a.accumulate > 0) ? oo[j] + r : oo[j] - r;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < C; j++) d2[j] = d2[j] - vv[j] * d1[j];
+        }
+    } else if (MODE == MODE_P1 && has_acc) {
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            const double o = __ldcs(o1 + j * st);
+            d1[j] = (a.accumulate > 0) ? o + d1[j] : o - d1[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < C; j++) {
+        if (MODE == MODE_P1) __stcs(o1 + j * st, d1[j]);
+        if (MODE == MODE_P2 || MODE == MODE_BURGERS) __stcs(o1 + j * st, d2[j]);
+        if (MODE == MODE_P2_P1) { __stcs(o1 + j * st, d2[j]); __stcs(a.out2 + coff + j * st, d1[j]); }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// y / z directions, persistent variant with asynchronous staging.  Each CTA loops over tiles of L lines.  The field
+// (and the velocity, or the second input) of a tile is brought into shared memory with cp.async, 16 bytes = 2 adjacent
+// lines per request; a tile is consumed into registers right after it has arrived, so the buffer is free again and
+// the copies of the NEXT tile are in flight while this one is being solved: the DRAM latency is paid behind the
+// arithmetic instead of in front of it, without a second buffer.  The accumulation target is prefetched into L2 at
+// the start of the tile and read directly at the end.
+// Tile layout: point i of line l at (i/16) * CS + (i%16) * L + l, CS = 16 L + 8: the chunk reads of a warp
+// (L lines x 32/L chunks) are conflict-free.
+__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+__host__ __device__ inline int pa_chunk_stride(int L) { return C * L + 8; }
+
+__device__ __forceinline__ void pa_issue_tile(double* tile, const double* __restrict__ g, long long st, int n, int lshift, int CS) {
+    const int sh = lshift - 1;                     // log2 of the 16-byte pieces per row
+    const int ppr = 1 << sh;
+    const int total = n << sh;
+    for (int q = threadIdx.x; q < total; q += blockDim.x) {
+        const int i = q >> sh, lp = (q & (ppr - 1)) * 2;
+        cp_async16(tile + (i >> 4) * CS + ((i & 15) << lshift) + lp, g + (long long)i * st + lp);
+    }
+}
+
+template <int MODE, bool PER, bool NEED1>
+__global__ void __launch_bounds__(512, 1) lines2_strided_pa(const __grid_constant__ Line2Args a) {
+    extern __shared__ double sm[];
+    ChunkCtx c;
+    c.L = a.L; c.T = a.T;
+    c.l = threadIdx.x & (a.L - 1);
+    c.t = threadIdx.x >> a.lshift;
+    const long long st = a.stride;
+    const int n = a.n, L = a.L, T = a.T;
+    const int CS = pa_chunk_stride(L);
+    double* bufU = sm + exch2_doubles(T, L);
+    double* bufV = bufU + (size_t)T * CS;
+    const bool has_u2 = (a.u2 != nullptr);
+    const bool has_vel = (MODE == MODE_BURGERS) && (a.vel != a.u);
+    const bool has_acc = (a.accumulate != 0) && (MODE == MODE_BURGERS || MODE == MODE_P1);
+    const double* __restrict__ vsrc = has_u2 ? a.u2 : a.vel;
+    const bool stage_v = has_u2 || has_vel;
+    const unsigned ntiles = a.ntiles, tiles_x = a.tiles_x;
+
+    auto tile_base = [&](unsigned tile) {
+        const unsigned ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        return (long long)ty * a.outer_stride + (long long)tx * L;
+    };
+    unsigned tile = blockIdx.x;
+    if (tile < ntiles) {
+        const long long gb = tile_base(tile);
+        pa_issue_tile(bufU, a.u + gb, st, n, a.lshift, CS);
+        cp_async_commit();
+        if (stage_v) pa_issue_tile(bufV, vsrc + gb, st, n, a.lshift, CS);
+        cp_async_commit();
+    }
+    for (; tile < ntiles; tile += gridDim.x) {
+        const long long gb = tile_base(tile);
+        const unsigned next = tile + gridDim.x;
+        const long long gn = (next < ntiles) ? tile_base(next) : 0;
+        const long long coff = gb + c.l + (long long)(c.t * C) * st;
+        if (has_acc) {
+            // L2 prefetch of this tile's accumulation target (read at the end of the iteration)
+            for (int r = threadIdx.x; r < n; r += blockDim.x) prefetch_l2(a.out1 + gb + (long long)r * st);
+        }
+        cp_async_wait<1>();                        // the field of this tile has arrived (the velocity may still be in flight)
+        __syncthreads();
+        double u[C + 6];
+        {
+            const bool lok = PER || c.t > 0, rok = PER || c.t < T - 1;
+            const double* pc = bufU + c.t * CS + c.l;
+            const double* pl = bufU + ((c.t > 0) ? (c.t - 1) : (T - 1)) * CS + (C - 3) * L + c.l;
+            const double* pr = bufU + ((c.t < T - 1) ? (c.t + 1) : 0) * CS + c.l;
+#pragma unroll
+            for (int j = 0; j < C; j++) u[j + 3] = pc[j * L];
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                u[k] = lok ? pl[k * L] : 0.0;
+                u[C + 3 + k] = rok ? pr[k * L] : 0.0;
+            }
+        }
+        if (has_u2) {
+            cp_async_wait<0>();
+            __syncthreads();
+            const bool lok = PER || c.t > 0, rok = PER || c.t < T - 1;
+            const double* qc = bufV + c.t * CS + c.l;
+            const double* ql = bufV + ((c.t > 0) ? (c.t - 1) : (T - 1)) * CS + (C - 3) * L + c.l;
+            const double* qr = bufV + ((c.t < T - 1) ? (c.t + 1) : 0) * CS + c.l;
+#pragma unroll
+            for (int j = 0; j < C; j++) u[j + 3] = u[j + 3] + qc[j * L] * a.scale;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (lok) u[k] = u[k] + ql[k * L] * a.scale;
+                if (rok) u[C + 3 + k] = u[C + 3 + k] + qr[k * L] * a.scale;
+            }
+        }
+        __syncthreads();                            // every thread has taken its chunk and halos: bufU (and bufV for u2) are free
+        if (next < ntiles) pa_issue_tile(bufU, a.u + gn, st, n, a.lshift, CS);
+        cp_async_commit();
+        if (has_u2) {
+            if (next < ntiles) pa_issue_tile(bufV, vsrc + gn, st, n, a.lshift, CS);
+            cp_async_commit();
+        }
+        if (MODE == MODE_BURGERS && !has_vel) {
+            // SELF: the advecting velocity is the field itself; park this thread's chunk in its own slots of bufV
+            double* vq = bufV + c.t * CS + c.l;
+#pragma unroll
+            for (int j = 0; j < C; j++) vq[j * L] = u[j + 3];
+        }
+        double d1[C], d2[C];
+        line_core2<MODE, PER, NEED1>(u, a, c, sm, d1, d2);
+
+        double* __restrict__ o1 = a.out1 + coff;
+        if (MODE == MODE_BURGERS) {
+            if (has_vel) {
+                cp_async_wait<1>();                // this tile's velocity (older than the next tile's field) has arrived
+                __syncthreads();
+            }
+            const double* vq = bufV + c.t * CS + c.l;
+#pragma unroll
+            for (int j = 0; j < C; j++) d2[j] = d2[j] - vq[j * L] * d1[j];
+            if (has_vel) {
+                __syncthreads();                    // bufV is free again
+                if (next < ntiles) pa_issue_tile(bufV, vsrc + gn, st, n, a.lshift, CS);
+                cp_async_commit();
+            }
+            if (has_acc) {
+                double oo[C];
+#pragma unroll
+                for (int j = 0; j < C; j++) oo[j] = __ldcs(o1 + j * st);
+#pragma unroll
+                for (int j = 0; j < C; j++) d2[j] = (a.accumulate > 0) ? oo[j] + d2[j] : oo[j] - d2[j];
+            }
+        } else if (MODE == MODE_P1 && has_acc) {
+            double oo[C];
+#pragma unroll
+            for (int j = 0; j < C; j++) oo[j] = __ldcs(o1 + j * st);
+#pragma unroll
+            for (int j = 0; j < C; j++) d1[j] = (a.accumulate > 0) ? oo[j] + d1[j] : oo[j] - d1[j];
+        }
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            if (MODE == MODE_P1) __stcs(o1 + j * st, d1[j]);
+            if (MODE == MODE_P2 || MODE == MODE_BURGERS) __stcs(o1 + j * st, d2[j]);
+            if (MODE == MODE_P2_P1) { __stcs(o1 + j * st, d2[j]); __stcs(a.out2 + coff + j * st, d1[j]); }
+        }
+        if (!stage_v) cp_async_commit();          // keep two groups per iteration (the wait counts above assume it)
+        // exchange areas of line_core2 are reused by the next tile: its first barrier (after cp_async_wait) orders them
+    }
+    cp_async_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// x direction: lines contiguous in memory; the tile of L lines (L*n contiguous doubles) is staged through shared
+// memory.  Tile layout: line ll at ll*T*XB, point i at (i>>4)*XB + (i&15): 16-byte accesses are conflict-free both for
+// the coalesced side (a lane owns 2 consecutive points) and for the chunk side (a lane owns 16 consecutive points).
+// Each thread moves exactly 8 double2 per array (L in {1,2,4,8}).
+template <bool ADD2>
+__device__ __forceinline__ void tile_load(double* tile, const double* __restrict__ g, const double* __restrict__ g2,
+                                          double scale, int n, int T, int L, int LS) {
+    const int nth = L * T;
+    const int per_line = (L == 8) ? 1 : (L == 4 ? 2 : (L == 2 ? 4 : 8));   // passes per line
+    const int tid = threadIdx.x;
+    double2 v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
+        v[k] = __ldcs(reinterpret_cast<const double2*>(g + (size_t)ll * n) + i2);
+    }
+    if (ADD2) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
+            const double2 w = __ldcs(reinterpret_cast<const double2*>(g2 + (size_t)ll * n) + i2);
+            v[k].x = v[k].x + w.x * scale;
+            v[k].y = v[k].y + w.y * scale;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
+        *reinterpret_cast<double2*>(tile + ll * LS + (i2 >> 3) * XB + (i2 & 7) * 2) = v[k];
+    }
+}
+
+template <int MODE, bool PER, bool NEED1>
+__global__ void __launch_bounds__(512, 1) lines2_contig(const __grid_constant__ Line2Args a) {
+    extern __shared__ double sm[];
+    ChunkCtx c;
+    c.L = a.L; c.T = a.T;
+    c.l = threadIdx.x & (a.L - 1);
+    c.t = threadIdx.x >> a.lshift;
+    const int n = a.n, T = a.T, L = a.L, LS = a.xls;
+    const size_t tile_off = (size_t)blockIdx.x * L * n;
+    double* tile = sm + exch2_doubles(T, L);
+    double* vtile = tile + (size_t)L * LS;
+    const bool two = (MODE == MODE_BURGERS) && (a.vel != a.u);
+    const bool has_acc = (a.accumulate != 0) && (MODE == MODE_BURGERS || MODE == MODE_P1);
+
+    if (a.pf_dist > 0) {
+        const unsigned tilei = blockIdx.x + (unsigned)a.pf_dist;
+        if (tilei < gridDim.x) {
+            const size_t po = (size_t)tilei * L * n;
+            for (int r = threadIdx.x * 16; r < L * n; r += blockDim.x * 16) {      // one request per 128-byte line
+                prefetch_l2(a.u + po + r);
+                if (a.u2 != nullptr) prefetch_l2(a.u2 + po + r);
+                if (two) prefetch_l2(a.vel + po + r);
+                if (has_acc) prefetch_l2(a.out1 + po + r);
+            }
+        }
+    }
+    if (a.u2 != nullptr) tile_load<true>(tile, a.u + tile_off, a.u2 + tile_off, a.scale, n, T, L, LS);
+    else tile_load<false>(tile, a.u + tile_off, nullptr, 0.0, n, T, L, LS);
+    if (two) tile_load<false>(vtile, a.vel + tile_off, nullptr, 0.0, n, T, L, LS);
+    __syncthreads();
+
+    const double* row = tile + c.l * LS;
+    double u[C + 6];
+    {
+        const double* pc = row + c.t * XB;
+#pragma unroll
+        for (int j = 0; j < C; j += 2) {
+            const double2 v = *reinterpret_cast<const double2*>(pc + j);
+            u[j + 3] = v.x; u[j + 4] = v.y;
+        }
+        const bool lok = PER || c.t > 0, rok = PER || c.t < T - 1;
+        const double* pl = row + ((c.t > 0) ? c.t - 1 : T - 1) * XB + (C - 3);
+        const double* pr = row + ((c.t < T - 1) ? c.t + 1 : 0) * XB;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            u[k] = lok ? pl[k] : 0.0;
+            u[C + 3 + k] = rok ? pr[k] : 0.0;
+        }
+    }
+    double d1[C], d2[C];
+    line_core2<MODE, PER, NEED1>(u, a, c, sm, d1, d2);
+    // all halo reads of the tile happened before the first barrier inside line_core2: results may overwrite it
+
+    {
+        double* wrow = tile + c.l * LS + c.t * XB;
+        const double* vrow = (two ? vtile : tile) + c.l * LS + c.t * XB;
+#pragma unroll
+        for (int j = 0; j < C; j += 2) {
+            double2 r;
+            if (MODE == MODE_P1) { r.x = d1[j]; r.y = d1[j + 1]; }
+            else if (MODE == MODE_P2 || MODE == MODE_P2_P1) { r.x = d2[j]; r.y = d2[j + 1]; }
+            else {
+                const double2 v = *reinterpret_cast<const double2*>(vrow + j);
+                r.x = d2[j] - v.x * d1[j];
+                r.y = d2[j + 1] - v.y * d1[j + 1];
+            }
+            *reinterpret_cast<double2*>(wrow + j) = r;
+            if (MODE == MODE_P2_P1) {
+                double2 q; q.x = d1[j]; q.y = d1[j + 1];
+                *reinterpret_cast<double2*>(vtile + c.l * LS + c.t * XB + j) = q;
+            }
+        }
+    }
+    __syncthreads();
+    const int nth = L * T;
+    const int per_line = (L == 8) ? 1 : (L == 4 ? 2 : (L == 2 ? 4 : 8));
+    const int tid = threadIdx.x;
+    {
+        double2 v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
+            v[k] = *reinterpret_cast<const double2*>(tile + ll * LS + (i2 >> 3) * XB + (i2 & 7) * 2);
+        }
+        if (has_acc) {
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
+                const double2 o = __ldcs(reinterpret_cast<const double2*>(a.out1 + tile_off + (size_t)ll * n) + i2);
+                if (a.accumulate > 0) { v[k].x = o.x + v[k].x; v[k].y = o.y + v[k].y; }
+                else { v[k].x = o.x - v[k].x; v[k].y = o.y - v[k].y; }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
+            __stcs(reinterpret_cast<double2*>(a.out1 + tile_off + (size_t)ll * n) + i2, v[k]);
+        }
+    }
+    if (MODE == MODE_P2_P1) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
+            const double2 v = *reinterpret_cast<const double2*>(vtile + ll * LS + (i2 >> 3) * XB + (i2 & 7) * 2);
+            __stcs(reinterpret_cast<double2*>(a.out2 + tile_off + (size_t)ll * n) + i2, v);
+        }
+    }
+}
+
+// prefetch distance: the number of CTAs resident on the device (the tile that far ahead starts when this one ends)
+template <class K>
+int auto_pf_dist(K k, int threads, size_t smem) {
+    int occ = 0, dev = 0, sms = 148;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem);
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return std::max(occ, 1) * sms;
+}
+
+template <int MODE, bool PER, bool NEED1>
+cudaError_t launch2(const Line2Args& a_in, bool contig, dim3 grid, cudaStream_t stream) {
+    Line2Args a = a_in;
+    const int threads = a.L * a.T;
+    size_t smem = exch2_doubles(a.T, a.L) * sizeof(double);
+    if (contig) {
+        const bool two = (MODE == MODE_P2_P1) || ((MODE == MODE_BURGERS) && (a.vel != a.u));
+        smem += (size_t)a.L * a.xls * sizeof(double) * (two ? 2 : 1);
+        auto k = lines2_contig<MODE, PER, NEED1>;
+        static size_t set = 0;
+        if (smem > set) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            set = smem;
+        }
+        static int pf = 0, pf_threads = 0;
+        static size_t pf_smem = 0;
+        if (a.pf_dist < 0) {
+            if (pf_threads != threads || pf_smem != smem) { pf = auto_pf_dist(k, threads, smem); pf_threads = threads; pf_smem = smem; }
+            a.pf_dist = pf;
+        }
+        k<<<grid, threads, smem, stream>>>(a);
+    } else if (a.persist && MODE != MODE_NEUMANN) {
+        auto k = lines2_strided_pa<(MODE == MODE_NEUMANN ? MODE_P1 : MODE), PER, NEED1>;
+        smem += (size_t)2 * a.T * pa_chunk_stride(a.L) * sizeof(double);
+        static size_t set = 48 * 1024;
+        if (smem > set) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            set = smem;
+        }
+        static int ctas = 0, c_threads = 0;
+        static size_t c_smem = 0;
+        if (c_threads != threads || c_smem != smem) { ctas = auto_pf_dist(k, threads, smem); c_threads = threads; c_smem = smem; }
+        a.tiles_x = grid.x;
+        a.ntiles = grid.x * grid.y;
+        const unsigned g = std::min<unsigned>(a.ntiles, (unsigned)ctas);
+        k<<<g, threads, smem, stream>>>(a);
+    } else {
+        auto k = lines2_strided<MODE, PER, NEED1>;
+        static size_t set = 48 * 1024;
+        if (smem > set) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            set = smem;
+        }
+        static int pf = 0, pf_threads = 0;
+        static size_t pf_smem = 0;
+        if (a.pf_dist < 0) {
+            if (pf_threads != threads || pf_smem != smem) { pf = auto_pf_dist(k, threads, smem); pf_threads = threads; pf_smem = smem; }
+            a.pf_dist = pf;
+        }
+        k<<<grid, threads, smem, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+template <int MODE>
+cudaError_t launch2_mode(const Line2Args& a, bool per, bool need1, bool contig, dim3 grid, cudaStream_t s) {
+    if (per) return launch2<MODE, true, false>(a, contig, grid, s);
+    if (need1) return launch2<MODE, false, true>(a, contig, grid, s);
+    return launch2<MODE, false, false>(a, contig, grid, s);
+}
+
+}  // namespace
+
+int lines2_xstride(int T, int L) {
+    int LS = T * XB;
+    const int want = (L >= 16) ? 0 : (16 / L) & 15;      // LS mod 16 == 16/L: the L lines of a quarter-warp hit distinct banks
+    while ((LS & 15) != want) LS += 2;
+    return LS;
+}
+
+bool lines2_eligible(const DevPlan& p, const Sys2& s1, const Sys2* s2, int n, long long nlines, long long inner, bool contig,
+                     int L_override, int* L_out) {
+    if (n < CHUNK || n % CHUNK != 0 || p.crem != 0 || p.cbase != CHUNK) return false;
+    if (!s1.ok || (s2 && !s2->ok)) return false;
+    const int T = n / CHUNK;
+    if (T > 128) return false;
+    int L;
+    if (contig) {
+        L = 4;
+        if (L_override == 1 || L_override == 2 || L_override == 4 || L_override == 8) L = L_override;
+        while (L < 8 && L * T < 64) L <<= 1;
+        while (L > 1 && (L * T > 512 || nlines % L != 0)) L >>= 1;
+        if (((size_t)L * n) % 2) return false;
+    } else {
+        L = 16;                                        // 128-byte rows when the CTA stays within 512 threads
+        if (L_override == 4 || L_override == 8 || L_override == 16 || L_override == 32) L = L_override;
+        while (L < 32 && L * T < 128 && inner % (2 * L) == 0) L <<= 1;
+        while (L > 4 && (L * T > 512 || inner % L != 0)) L >>= 1;
+        if (L * T > 512 || inner % L != 0 || nlines % inner != 0) return false;
+        if (inner / L > 0x7fffffffLL || nlines / inner > 65535) return false;
+    }
+    if (L * T < 1) return false;
+    *L_out = L;
+    return true;
+}
+
+size_t lines2_persist_smem(int T, int L) { return (exch2_doubles(T, L) + (size_t)2 * T * pa_chunk_stride(L)) * sizeof(double); }
+
+cudaError_t launch_lines2(int mode, const Line2Args& a, bool periodic, bool need1, bool contig, long long nlines,
+                          long long inner, cudaStream_t s) {
+    dim3 grid;
+    if (contig) grid = dim3((unsigned)(nlines / a.L), 1, 1);
+    else grid = dim3((unsigned)(inner / a.L), (unsigned)(nlines / inner), 1);
+    switch (mode) {
+        case MODE_P1: return launch2_mode<MODE_P1>(a, periodic, false, contig, grid, s);
+        case MODE_P2: return launch2_mode<MODE_P2>(a, periodic, need1, contig, grid, s);
+        case MODE_P2_P1: return launch2_mode<MODE_P2_P1>(a, periodic, need1, contig, grid, s);
+        case MODE_BURGERS: return launch2_mode<MODE_BURGERS>(a, periodic, need1, contig, grid, s);
+        case MODE_NEUMANN: return launch2_mode<MODE_NEUMANN>(a, periodic, false, false, grid, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace tlab

@@ -1,0 +1,40 @@
+// Fast line kernels (lines2.cu): argument block and launcher.
+#pragma once
+#include "lines.h"
+
+namespace tlab {
+
+struct Line2Args {
+    int n = 0, T = 1, L = 4, lshift = 2;
+    int accumulate = 0;               // +1: out1 += result, -1: out1 -= result, 0: out1 = result
+    int pf_dist = 0;                  // L2 prefetch distance in tiles (0: off)
+    int xls = 0;                      // shared-memory line stride of the x tile (doubles)
+    int persist = 0;                  // strided kernel: persistent CTAs with cp.async staging
+    unsigned ntiles = 0, tiles_x = 0; // persistent kernel: tile count and tiles per outer block
+    double scale = 0.0;               // input is u + scale * u2 when u2 != nullptr
+    long long stride = 1;             // distance between consecutive points of a line (strided kernel)
+    long long inner = 1;              // tile (bx, by) starts at by * outer_stride + bx * L; lines by * inner + bx * L + l
+    long long outer_stride = 0;
+    const double* u = nullptr;
+    const double* u2 = nullptr;
+    const double* vel = nullptr;
+    double* out1 = nullptr;
+    double* out2 = nullptr;
+    double* bcs_hb = nullptr;
+    double* bcs_ht = nullptr;
+    const double2* rhs_d1 = nullptr;  // Jacobian correction {r1,r2},{r3,0} per point, chunk-interleaved like Sys2::tab
+    RhsTab rhs1, rhs2;
+    Sys2 s1, s2;
+    double neu_bot[BROW_W], neu_top[BROW_W];
+    double neu_lu_bot = 0.0, neu_lu_top = 0.0;
+};
+
+// can the fast kernels run this geometry?  Returns the number of lines per CTA in *L_out.
+bool lines2_eligible(const DevPlan& p, const Sys2& s1, const Sys2* s2, int n, long long nlines, long long inner, bool contig,
+                     int L_override, int* L_out);
+int lines2_xstride(int T, int L);
+size_t lines2_persist_smem(int T, int L);
+cudaError_t launch_lines2(int mode, const Line2Args& a, bool periodic, bool need1, bool contig, long long nlines,
+                          long long inner, cudaStream_t s);
+
+}  // namespace tlab

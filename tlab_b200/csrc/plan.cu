@@ -1,6 +1,8 @@
 // Build the device tables of a plan from the host plan (see plan.h).
 #include "plan.h"
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 
@@ -99,8 +101,127 @@ void finish_solve(DevPlan& p, SolveTab& s, std::vector<double>& alpha, std::vect
     s.pd = periodic ? upload(p, pdv) : nullptr;
 }
 
+
+// ---- the same system for lines2.cu (see plan.h, Sys2) ------------------------------------------
+void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const std::vector<double>& beta,
+                const std::vector<double>& gamma, const std::vector<double>& delta, const std::vector<double>& pd,
+                const std::vector<double>& pe, double bN, bool periodic) {
+    s2 = Sys2();
+    const int n = p.n, T = p.T;
+    if (p.crem != 0 || p.cbase != CHUNK) return;            // fast kernels need full chunks
+    std::vector<double> a(n), d(n), g(n), e(n, 0.0), pp(n, 0.0);
+    for (int i = 0; i < n; i++) {
+        if (periodic) {
+            a[i] = (i > 0) ? alpha[i] * beta[i - 1] / beta[i] : 0.0;
+            d[i] = beta[i]; g[i] = gamma[i]; e[i] = pe[i];
+            pp[i] = -bN * pd[i] * beta[i];
+        } else {
+            a[i] = alpha[i]; d[i] = delta[i]; g[i] = gamma[i] * delta[i];
+        }
+    }
+    if (periodic) { d[n - 1] = 0.0; g[n - 1] = 0.0; e[n - 1] = 1.0; pp[n - 1] = bN * beta[n - 1]; a[n - 1] = alpha[n - 1] * beta[n - 2] / beta[n - 1]; }
+    // global backward sweep of the e vector: S_i = e_i + g_i S_{i+1}
+    std::vector<double> S(n + 1, 0.0);
+    for (int i = n - 1; i >= 0; i--) S[i] = e[i] + g[i] * S[i + 1];
+    std::vector<double> P(n), Q(n), R(n), Af(T), Rb(T), Q0(T), PP(T);
+    for (int t = 0; t < T; t++) {
+        const int s0 = t * CHUNK;
+        double w = 1.0, acc = 0.0;
+        for (int j = 0; j < CHUNK; j++) { w *= a[s0 + j]; P[s0 + j] = w; acc += pp[s0 + j] * w; }
+        Af[t] = w; PP[t] = acc;
+        w = 1.0;
+        double q = 0.0;
+        for (int j = CHUNK - 1; j >= 0; j--) { w *= g[s0 + j]; R[s0 + j] = w; q = d[s0 + j] * P[s0 + j] + g[s0 + j] * q; Q[s0 + j] = q; }
+        Rb[t] = w; Q0[t] = q;
+    }
+    // look-back windows must fit LB2 chunks
+    if (window(Af, true) > LB2 || window(Rb, false) > LB2) return;
+    // constant chunks: coefficients equal to the converged LU factors (interior of a uniform direction).  The reference
+    // builds the Jacobian by differentiating the node positions, which leaves round-off noise of relative size
+    // ~eps*n in its LU factors; the constants are the mean over the middle half of the line and a chunk counts as
+    // constant if it deviates by less than 2^-41 (4.5e-13) from them -- far inside the 1e-12 parity tolerance.
+    {
+        double sa = 0.0, sd = 0.0, sg = 0.0;
+        int cnt = 0;
+        for (int i = n / 4; i < n - n / 4; i++) { sa += a[i]; sd += d[i]; sg += g[i]; cnt++; }
+        s2.ca = sa / cnt; s2.cd = sd / cnt; s2.cg = sg / cnt;
+    }
+    {
+        double w = 1.0, q = 0.0;
+        std::vector<double> Pc(CHUNK);
+        for (int j = 0; j < CHUNK; j++) { w *= s2.ca; Pc[j] = w; }
+        w = 1.0;
+        for (int j = CHUNK - 1; j >= 0; j--) { w *= s2.cg; s2.cR[j] = w; q = s2.cd * Pc[j] + s2.cg * q; s2.cQ[j] = q; }
+    }
+    double pmax = 0.0, smax = 0.0;
+    for (int i = 0; i < n; i++) { pmax = std::max(pmax, std::fabs(pp[i])); smax = std::max(smax, std::fabs(S[i])); }
+    auto close = [](double v, double ref) { return std::fabs(v - ref) <= std::ldexp(std::fabs(ref), -41); };
+    std::vector<int> isc(T, 0);
+    for (int t = 0; t < T; t++) {
+        bool c = true;
+        for (int j = 0; j < CHUNK && c; j++) {
+            const int i = t * CHUNK + j;
+            c = close(a[i], s2.ca) && close(d[i], s2.cd) && close(g[i], s2.cg);
+            if (periodic && c) c = std::fabs(pp[i]) <= std::ldexp(pmax, -80) && std::fabs(S[i]) <= std::ldexp(smax, -80);
+        }
+        isc[t] = c ? 1 : 0;
+    }
+    // circulant closure: chunks [0,K0) and [T-K1,T) carry it; everything in between must be constant (p, S negligible)
+    if (periodic) {
+        int k0 = 0, k1 = 0;
+        auto carries = [&](int t) {
+            for (int j = 0; j < CHUNK; j++) {
+                const int i = t * CHUNK + j;
+                if (std::fabs(pp[i]) > std::ldexp(pmax, -80) || std::fabs(S[i]) > std::ldexp(smax, -80)) return true;
+            }
+            return false;
+        };
+        while (k0 < T && carries(k0)) k0++;
+        while (k1 < T - k0 && carries(T - 1 - k1)) k1++;
+        for (int t = k0; t < T - k1; t++) if (carries(t)) { k0 = T; k1 = 0; break; }
+        s2.K0 = k0; s2.K1 = k1;
+        for (int t = 0; t < T; t++) if (t < k0 || t >= T - k1) isc[t] = 0;
+    }
+    const int Tp = (T + 7) / 8 * 8;
+    std::vector<double2> tab((size_t)Tp * CHUNK * 4, make_double2(0.0, 0.0));
+    std::vector<double> crec((size_t)T * 16, 0.0);
+    for (int t = 0; t < T; t++) {
+        for (int j = 0; j < CHUNK; j++) {
+            const int i = t * CHUNK + j;
+            const size_t base = (((size_t)(t >> 3) * CHUNK + j) * 4) * 8 + (t & 7);
+            tab[base + 0 * 8] = make_double2(a[i], pp[i]);
+            tab[base + 1 * 8] = make_double2(d[i], g[i]);
+            tab[base + 2 * 8] = make_double2(Q[i], R[i]);
+            tab[base + 3 * 8] = make_double2(S[i], 0.0);
+        }
+        double* c = &crec[(size_t)t * 16];
+        double w = 1.0;
+        for (int k = 1; k <= LB2; k++) {            // A(t) = sum_k wf[k] yend(t-k)
+            c[k - 1] = (t - k >= 0) ? w : 0.0;
+            if (t - k >= 0) w *= Af[t - k];
+        }
+        w = 1.0;
+        for (int k = 1; k <= LB2; k++) {            // B(t) = sum_k wb[k] z(t+k)
+            c[LB2 + k - 1] = (t + k <= T - 1) ? w : 0.0;
+            if (t + k <= T - 1) w *= Rb[t + k];
+        }
+        c[12] = Q0[t]; c[13] = PP[t]; c[14] = isc[t] ? 1.0 : 0.0; c[15] = 0.0;
+    }
+    if (getenv("TLAB_DEBUG_PLAN")) {
+        for (int i : {0, 1, 2, 16, 40, 80, n / 2, n / 2 + 1, n - 80, n - 40, n - 3, n - 2, n - 1})
+            fprintf(stderr, "   i=%d a=%.17g d=%.17g g=%.17g e=%g pp=%g S=%g\n", i, a[i], d[i], g[i], e[i], pp[i], S[i]);
+        int nc = 0;
+        for (int t = 0; t < T; t++) nc += isc[t];
+        fprintf(stderr, "[sys2] n=%d T=%d periodic=%d Wf=%d Wb=%d const_chunks=%d K0=%d K1=%d ca=%g cd=%g cg=%g Af=%g Rb=%g\n", n, T,
+                (int)periodic, window(Af, true), window(Rb, false), nc, s2.K0, s2.K1, s2.ca, s2.cd, s2.cg, Af[T / 2], Rb[T / 2]);
+    }
+    s2.tab = upload_t(p, tab);
+    s2.crec = upload(p, crec);
+    s2.ok = (s2.tab && s2.crec) ? 1 : 0;
+}
+
 // lu columns c0+1..c0+3 (c0+1..c0+5 periodic); rows nmin..nmax active; scale = diffusivity (1 = none)
-void make_solve(DevPlan& p, SolveTab& s, const Mat& lu, int c0, int nmin, int nmax, bool periodic, double diff,
+void make_solve(DevPlan& p, SolveTab& s, Sys2& s2, const Mat& lu, int c0, int nmin, int nmax, bool periodic, double diff,
                 bool scaled) {
     const int n = p.n;
     std::vector<double> alpha(n, 0.0), beta(n, 1.0), gamma(n, 0.0), delta(n, 1.0), pd(n, 0.0), pe(n, 0.0);
@@ -125,6 +246,7 @@ void make_solve(DevPlan& p, SolveTab& s, const Mat& lu, int c0, int nmin, int nm
             delta[i] = b;
         }
     }
+    build_sys2(p, s2, alpha, beta, gamma, delta, pd, pe, s.bN, periodic);
     finish_solve(p, s, alpha, beta, gamma, delta, pd, pe, periodic);
 }
 
@@ -178,26 +300,40 @@ int devplan_build(DevPlan& p) {
     // first derivative
     if (h.periodic) {
         make_rhs(h.der1, false, BCS_PERIODIC, p.rhs1[0]);
-        make_solve(p, p.lu1[0], h.der1.lu, 0, 1, n, true, 1.0, false);
-        for (int b = 1; b < 4; b++) { p.rhs1[b] = p.rhs1[0]; p.lu1[b] = p.lu1[0]; }
+        make_solve(p, p.lu1[0], p.sys1[0], h.der1.lu, 0, 1, n, true, 1.0, false);
+        for (int b = 1; b < 4; b++) { p.rhs1[b] = p.rhs1[0]; p.lu1[b] = p.lu1[0]; p.sys1[b] = p.sys1[0]; }
     } else {
         for (int ibc = 0; ibc < 4; ibc++) {
             make_rhs(h.der1, false, ibc, p.rhs1[ibc]);
             int nmin = 1, nmax = n;
             if (ibc == BCS_ND || ibc == BCS_NN) nmin++;
             if (ibc == BCS_DN || ibc == BCS_NN) nmax--;
-            make_solve(p, p.lu1[ibc], h.der1.lu, ibc * 5, nmin, nmax, false, 1.0, false);
+            make_solve(p, p.lu1[ibc], p.sys1[ibc], h.der1.lu, ibc * 5, nmin, nmax, false, 1.0, false);
         }
     }
     // second derivative
     make_rhs(h.der2, true, BCS_DD, p.rhs2);
     p.lu2.clear();
     p.lu2.emplace_back();
-    make_solve(p, p.lu2[0], h.der2.lu, 0, 1, n, h.periodic, 1.0, false);
+    p.sys2.clear();
+    p.sys2.emplace_back();
+    make_solve(p, p.lu2[0], p.sys2[0], h.der2.lu, 0, 1, n, h.periodic, 1.0, false);
     if (p.need_1der) {
         std::vector<double> r(3 * (size_t)n);
         for (int i = 1; i <= n; i++) for (int j = 1; j <= 3; j++) r[3 * (size_t)(i - 1) + (j - 1)] = h.der2.rhs(i, h.der2.ndr + j);
         p.rhs_d1 = upload(p, r);
+        if (p.crem == 0 && p.cbase == CHUNK) {
+            const int Tp = (p.T + 7) / 8 * 8;
+            std::vector<double2> r2((size_t)Tp * CHUNK * 2, make_double2(0.0, 0.0));
+            for (int t = 0; t < p.T; t++)
+                for (int j = 0; j < CHUNK; j++) {
+                    const size_t i = (size_t)t * CHUNK + j;
+                    const size_t base = (((size_t)(t >> 3) * CHUNK + j) * 2) * 8 + (t & 7);
+                    r2[base] = make_double2(r[3 * i], r[3 * i + 1]);
+                    r2[base + 8] = make_double2(r[3 * i + 2], 0.0);
+                }
+            p.rhs_d1_2 = upload_t(p, r2);
+        }
     }
     {
         std::vector<double> j1(n);
@@ -233,7 +369,8 @@ int devplan_build(DevPlan& p) {
 int devplan_add_diffusion(DevPlan& p, double diff) {
     if (p.n <= 1) return 0;
     p.lu2.emplace_back();
-    make_solve(p, p.lu2.back(), p.h.der2.lu, 0, 1, p.n, p.h.periodic, diff, true);
+    p.sys2.emplace_back();
+    make_solve(p, p.lu2.back(), p.sys2.back(), p.h.der2.lu, 0, 1, p.n, p.h.periodic, diff, true);
     return (int)p.lu2.size() - 1;
 }
 

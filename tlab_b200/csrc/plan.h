@@ -40,6 +40,26 @@ struct SolveTab {
     int Wf = 0, Wb = 0;              // look-back windows (in chunks), see DESIGN.md "chunked substitution"
 };
 
+// The same system in the form used by the fast kernels (lines2.cu): per point
+//   forward : y_j = f_j + a_j y_{j-1}
+//   backward: x_j = d_j y_j + g_j x_{j+1}  [+ e_j x_N, circulant]
+// and, because both sweeps are linear, per chunk (zero-inflow sweeps x^ of the chunk alone)
+//   x_j = x^_j + Q_j A + R_j B + S_j x_N
+// with A the true y at the end of the previous chunk, B the x_N-free part of the true x at the start of the next chunk,
+// x_N = sum_i p_i y_i (circulant closure).  A and B follow from the published chunk ends through look-back /
+// look-ahead sums over at most LB2 chunks with precomputed weights (the dropped tail is < 2^-80).
+// Chunks whose coefficients are constant (interior of a uniform grid) use the scalars below instead of the tables.
+constexpr int LB2 = 6;
+struct Sys2 {
+    const double2* tab = nullptr;    // point records, 4 double2 per point: {a,p} {d,g} {Q,R} {S,0}; item (t, j, q) at
+                                     // (((t>>3)*CHUNK + j)*4 + q)*8 + (t&7)  (the 8 chunks of a warp read one 128-byte line)
+    const double* crec = nullptr;    // chunk records, 16 doubles: wf[6], wb[6], Q0, PP, isconst, 0
+    double ca = 0.0, cd = 0.0, cg = 0.0;   // constant-chunk coefficients
+    double cQ[CHUNK], cR[CHUNK];           // constant-chunk correction vectors
+    int K0 = 0, K1 = 0;              // circulant: chunks [0,K0) and [T-K1,T) contribute to x_N
+    int ok = 0;                      // 0: look-back window too long for the fast kernels
+};
+
 // banded right-hand side B u: constant interior stencil + dense special rows at the ends
 struct RhsTab {
     double rc = 0.0;                 // centre coefficient (symmetric stencils; 0 for antisymmetric)
@@ -60,7 +80,10 @@ struct DevPlan {
     RhsTab rhs2;                     // second derivative
     SolveTab lu1[4];                 // first derivative LU per ibc
     std::vector<SolveTab> lu2;       // second derivative LU: [0] plain, [1 + is] scaled by diffusivity is (Burgers)
+    Sys2 sys1[4];                    // the same systems in the form of lines2.cu
+    std::vector<Sys2> sys2;
     const double* rhs_d1 = nullptr;  // [n][3] Jacobian correction of the second derivative (need_1der)
+    const double2* rhs_d1_2 = nullptr;  // the same, chunk-interleaved for lines2.cu
     const double* d_mwn1 = nullptr;  // [n] modified wavenumbers of the first derivative (periodic)
     const double* d_jac = nullptr;   // [n] dx/ds
     // Neumann boundary-value closure (BOUNDARY_BCS_NEUMANN_Y): value = sum_k bcsrow[k] u_k + lu_coef * du_1

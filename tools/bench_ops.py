@@ -26,6 +26,9 @@ def main():
     ap.add_argument("--poisson", action="store_true")
     ap.add_argument("--json", default="")
     ap.add_argument("--only", default="", help="regular expression selecting the operator labels to run")
+    ap.add_argument("--fast", default="1", help="comma list of 0/1: general kernels (lines.cu) / fast kernels (lines2.cu)")
+    ap.add_argument("--pf-dist", default="-1", help="comma list of L2 prefetch distances of the fast kernels (-1 auto, 0 off)")
+    ap.add_argument("--persist", default="1", help="comma list of 0/1: persistent cp.async variant of the fast y/z kernels")
     ap.add_argument("--prefetch", type=int, default=-1, help="1/0: force the persistent cp.async variant of the y/z kernels")
     args = ap.parse_args()
     import torch
@@ -75,11 +78,18 @@ def main():
               (label, ms, gbs, 100 * gbs / peak, kind, peak, 100 * gbs / 8000.0), flush=True)
         tl.check(L.tlab_gpu_set_async(0))
 
-    for lx in [int(s) for s in args.lines_x.split(",")]:
-        for lyz in [int(s) for s in args.lines_yz.split(",")]:
+    combos = [(lx, lyz, fast, pf, ps) for lx in [int(s) for s in args.lines_x.split(",")]
+              for lyz in [int(s) for s in args.lines_yz.split(",")] for fast in [int(s) for s in args.fast.split(",")]
+              for pf in ([int(s) for s in args.pf_dist.split(",")] if fast else [0])
+              for ps in ([int(s) for s in args.persist.split(",")] if fast else [0])]
+    for lx, lyz, fast, pf, ps in combos:
+        if True:
             tl.check(L.tlab_gpu_set_tuning(b"lines_x", lx))
             tl.check(L.tlab_gpu_set_tuning(b"lines_yz", lyz))
-            tag = " [Lx=%d Lyz=%d]" % (lx, lyz)
+            tl.check(L.tlab_gpu_set_tuning(b"fast", fast))
+            tl.check(L.tlab_gpu_set_tuning(b"pf_dist", pf))
+            tl.check(L.tlab_gpu_set_tuning(b"persist", ps))
+            tag = " [fast=%d pf=%d ps=%d Lx=%d Lyz=%d]" % (fast, pf, ps, lx, lyz)
             for d, nm in enumerate("xyz"):
                 timeit(lambda: P[d](opr.OPR_P1, nx, ny, nz, bcs, g[d], u, r1), 16 * N, "OPR_Partial_%s P1" % nm.upper() + tag)
                 timeit(lambda: P[d](opr.OPR_P2, nx, ny, nz, bcs, g[d], u, r1), 16 * N, "OPR_Partial_%s P2" % nm.upper() + tag)
