@@ -320,6 +320,7 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "fast")) ctx().tune_fast = value;
     else if (!std::strcmp(key, "pf_dist")) ctx().tune_pf_dist = value;
     else if (!std::strcmp(key, "persist")) ctx().tune_persist = value;
+    else if (!std::strcmp(key, "poisson_minb")) ctx().tune_poisson_minb = value;
     else return fail(TLAB_ERR_OPTION, std::string("unknown tuning key ") + key);
     return 0;
 }

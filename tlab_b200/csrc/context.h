@@ -25,6 +25,7 @@ struct Context {
     int tune_lines_x = 0, tune_lines_yz = 0;
     int tune_fast = 1;        // 1: use the fast line kernels (lines2.cu) whenever the geometry allows
     int tune_pf_dist = -1;
+    int tune_poisson_minb = 3;  // resident CTAs per SM the Poisson y kernel is compiled for (register budget)
     int tune_persist = 0;     // strided fast kernels: persistent CTAs with asynchronous staging
     long long fast_launches = 0, general_launches = 0;    // L2 prefetch distance of the fast kernels in tiles (-1: automatic, 0: off)
     tlab_plan_s* burgers_plans[3] = {nullptr, nullptr, nullptr};

@@ -119,59 +119,72 @@ __device__ void int1_solve(const Int1Dev& P, double lam, const LineRef (&f)[NL],
 #pragma unroll
         for (int l = 0; l < NL; l++) bcs_far[l] = F1[l] * rb[1][2] + u0[l] * rb[1][3] + up[l] * rb[1][1];
     }
-    for (int m = 1; m <= nmax; m++) {
-        const int r = m + 1;
-        double row[6];
-        if (is_min && r == n - 1) {
+    // The forcing rows are fetched FRB rows ahead, in blocks (memory-level parallelism: the sweep is a dependent chain
+    // and would otherwise wait for one DRAM round trip every other row).
+    constexpr int FRB = 8;
+    for (int m0 = 1; m0 <= nmax; m0 += FRB) {
+        double fblk[NL][FRB];
 #pragma unroll
-            for (int k = 1; k <= 5; k++) row[k] = La[k];
-        } else if (is_min && r == n - 2) {
+        for (int j = 0; j < FRB; j++) {
+            const int rr = m0 + j + 3;              // row r + 2 of step m = m0 + j
 #pragma unroll
-            for (int k = 1; k <= 5; k++) row[k] = Lb[k];
-        } else if (!is_min && r == 2) {
-#pragma unroll
-            for (int k = 1; k <= 5; k++) row[k] = La[k];
-        } else if (!is_min && r == 3) {
-#pragma unroll
-            for (int k = 1; k <= 5; k++) row[k] = Lb[k];
-        } else {
-            Lrow(r, row);
+            for (int l = 0; l < NL; l++) fblk[l][j] = (rr <= n - 1) ? F(l, rr) : 0.0;
         }
-        double a = row[1], b = row[2], c = row[3], d = row[4], e = row[5];
-        if (m == 2) {
-            b = b / c1;
-            c = c - b * d1;
-            d = d - b * e1;
-        } else if (m >= 3) {
-            a = a / c2;
-            b = (b - a * d2) / c1;
-            c = c - b * d1 - a * e2;
-            if (m < nmax) d = d - b * e1;
-        }
-        const double nb = -b, na = -a;
-        double unext[NL];
 #pragma unroll
-        for (int l = 0; l < NL; l++) {
-            unext[l] = (r + 2 <= n - 1) ? F(l, r + 2) : 0.0;
-            double rv;
-            if (r == 2) rv = F1[l] * rb[2][1] + u0[l] * rb[2][2] + up[l] * rb[2][3];
-            else if (r == 3) rv = F1[l] * rb[3][0] + um[l] * rb[3][1] + u0[l] * rb[3][2] + up[l] * rb[3][3];
-            else if (r == n - 2) rv = um[l] * rt[0][1] + u0[l] * rt[0][2] + up[l] * rt[0][3] + FN[l] * rt[0][4];
-            else if (r == n - 1) rv = um[l] * rt[1][1] + u0[l] * rt[1][2] + FN[l] * rt[1][3];
-            else rv = um[l] * rhs(r, 1) + u0[l] * rhs(r, 2) + up[l];
-            if (is_min && r == n - 1) bcs_far[l] = um[l] * rt[2][3] + u0[l] * rt[2][1] + FN[l] * rt[2][2];
-            double y;
-            if (m == 1) y = rv;
-            else if (m == 2) y = rv + y1[l] * nb;
-            else y = rv + y1[l] * nb + y2[l] * na;
-            ysc[l].set(r, y);
-            y2[l] = y1[l]; y1[l] = y;
-            um[l] = u0[l]; u0[l] = up[l]; up[l] = unext[l];
+        for (int j = 0; j < FRB; j++) {
+            const int m = m0 + j;
+            if (m > nmax) break;
+            const int r = m + 1;
+            double row[6];
+            if (is_min && r == n - 1) {
+#pragma unroll
+                for (int k = 1; k <= 5; k++) row[k] = La[k];
+            } else if (is_min && r == n - 2) {
+#pragma unroll
+                for (int k = 1; k <= 5; k++) row[k] = Lb[k];
+            } else if (!is_min && r == 2) {
+#pragma unroll
+                for (int k = 1; k <= 5; k++) row[k] = La[k];
+            } else if (!is_min && r == 3) {
+#pragma unroll
+                for (int k = 1; k <= 5; k++) row[k] = Lb[k];
+            } else {
+                Lrow(r, row);
+            }
+            double a = row[1], b = row[2], c = row[3], d = row[4], e = row[5];
+            if (m == 2) {
+                b = b / c1;
+                c = c - b * d1;
+                d = d - b * e1;
+            } else if (m >= 3) {
+                a = a / c2;
+                b = (b - a * d2) / c1;
+                c = c - b * d1 - a * e2;
+                if (m < nmax) d = d - b * e1;
+            }
+            const double nb = -b, na = -a;
+#pragma unroll
+            for (int l = 0; l < NL; l++) {
+                const double unext = fblk[l][j];
+                double rv;
+                if (r == 2) rv = F1[l] * rb[2][1] + u0[l] * rb[2][2] + up[l] * rb[2][3];
+                else if (r == 3) rv = F1[l] * rb[3][0] + um[l] * rb[3][1] + u0[l] * rb[3][2] + up[l] * rb[3][3];
+                else if (r == n - 2) rv = um[l] * rt[0][1] + u0[l] * rt[0][2] + up[l] * rt[0][3] + FN[l] * rt[0][4];
+                else if (r == n - 1) rv = um[l] * rt[1][1] + u0[l] * rt[1][2] + FN[l] * rt[1][3];
+                else rv = um[l] * rhs(r, 1) + u0[l] * rhs(r, 2) + up[l];
+                if (is_min && r == n - 1) bcs_far[l] = um[l] * rt[2][3] + u0[l] * rt[2][1] + FN[l] * rt[2][2];
+                double y;
+                if (m == 1) y = rv;
+                else if (m == 2) y = rv + y1[l] * nb;
+                else y = rv + y1[l] * nb + y2[l] * na;
+                ysc[l].set(r, y);
+                y2[l] = y1[l]; y1[l] = y;
+                um[l] = u0[l]; u0[l] = up[l]; up[l] = unext;
+            }
+            csc.set(r, 1.0 / c);
+            dsc.set(r, -d);
+            c2 = c1; c1 = c; d2 = d1; d1 = d; e2 = e1; e1 = e;
         }
-        csc.set(r, 1.0 / c);
-        dsc.set(r, -d);
-        esc.set(r, -e);
-        c2 = c1; c1 = c; d2 = d1; d1 = d; e2 = e1; e1 = e;
     }
 
     // ---- backward sweep
@@ -179,44 +192,63 @@ __device__ void int1_solve(const Int1Dev& P, double lam, const LineRef (&f)[NL],
 #pragma unroll
     for (int l = 0; l < NL; l++) x1[l] = x2[l] = 0.0;
     double r2v[NL], r3v[NL], r4v[NL]; // results at rows 2, 3, 4 (near-end closure / derivative)
-    for (int m = nmax; m >= 1; m--) {
-        const int r = m + 1;
-        const double ci = csc.get(r), nd = dsc.get(r), ne = esc.get(r);
+    // The fifth diagonal is not touched by the elimination, so -e is rebuilt from the shared tables instead of being
+    // stored (row 2 of a BCS_MAX system is the one reduced row whose e changed).
+    constexpr int BRB = 4;
+    for (int m0 = nmax; m0 >= 1; m0 -= BRB) {
+        double cblk[BRB], dblk[BRB], yblk[NL][BRB];
 #pragma unroll
-        for (int l = 0; l < NL; l++) {
-            const double y = ysc[l].get(r);
-            double x;
-            if (m == nmax) x = y * ci;
-            else if (m == nmax - 1) x = (y + x1[l] * nd) * ci;
-            else x = (y + x1[l] * nd + x2[l] * ne) * ci;
-            res[l].set(r, x);
-            if (m == nmax - 2) {
-                // rows n-1, n-2, n-3 are known: far-end closure (BCS_MIN) or far-end derivative (BCS_MAX)
-                const double xn1 = x2[l], xn2 = x1[l], xn3 = x;
-                if (is_min) {
-                    double v = bcs_far[l];
-                    v = v + Le[2] * xn1;
-                    v = v + Le[1] * xn2;
-                    v = v + Le[5] * xn3;
-                    res[l].set(n, v);
-                } else {
-                    res[l].set(n, bc[l]);
-                    if (du) {
-                        double row[6];
-                        Lrow(n, row);
-                        double v = row[3] * bc[l];
-                        v = v + row[2] * xn1;
-                        v = v + row[1] * xn2;
-                        v = v + row[5] * xn3;
-                        v = v + rhs(n, 1) * F(l, n - 1);
-                        du[l] = v;
+        for (int j = 0; j < BRB; j++) {
+            const int r = m0 - j + 1;
+            const bool ok = (m0 - j >= 1);
+            cblk[j] = ok ? csc.get(r) : 0.0;
+            dblk[j] = ok ? dsc.get(r) : 0.0;
+#pragma unroll
+            for (int l = 0; l < NL; l++) yblk[l][j] = ok ? ysc[l].get(r) : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < BRB; j++) {
+            const int m = m0 - j;
+            if (m < 1) break;
+            const int r = m + 1;
+            const double ci = cblk[j], nd = dblk[j];
+            const double ne = (!is_min && r == 2) ? -La[5] : -(P.L0[(r - 1) * 5 + 4] + lam * P.L1[(r - 1) * 5 + 4]);
+#pragma unroll
+            for (int l = 0; l < NL; l++) {
+                const double y = yblk[l][j];
+                double x;
+                if (m == nmax) x = y * ci;
+                else if (m == nmax - 1) x = (y + x1[l] * nd) * ci;
+                else x = (y + x1[l] * nd + x2[l] * ne) * ci;
+                res[l].set(r, x);
+                if (m == nmax - 2) {
+                    // rows n-1, n-2, n-3 are known: far-end closure (BCS_MIN) or far-end derivative (BCS_MAX)
+                    const double xn1 = x2[l], xn2 = x1[l], xn3 = x;
+                    if (is_min) {
+                        double v = bcs_far[l];
+                        v = v + Le[2] * xn1;
+                        v = v + Le[1] * xn2;
+                        v = v + Le[5] * xn3;
+                        res[l].set(n, v);
+                    } else {
+                        res[l].set(n, bc[l]);
+                        if (du) {
+                            double row[6];
+                            Lrow(n, row);
+                            double v = row[3] * bc[l];
+                            v = v + row[2] * xn1;
+                            v = v + row[1] * xn2;
+                            v = v + row[5] * xn3;
+                            v = v + rhs(n, 1) * F(l, n - 1);
+                            du[l] = v;
+                        }
                     }
                 }
+                if (r == 4) r4v[l] = x;
+                if (r == 3) r3v[l] = x;
+                if (r == 2) r2v[l] = x;
+                x2[l] = x1[l]; x1[l] = x;
             }
-            if (r == 4) r4v[l] = x;
-            if (r == 3) r3v[l] = x;
-            if (r == 2) r2v[l] = x;
-            x2[l] = x1[l]; x1[l] = x;
         }
     }
 #pragma unroll
@@ -314,7 +346,8 @@ __global__ void poisson_fundamental_kernel(PoissonDev D) {
 // per call: regular modes, Neumann/Neumann (OPR_ODE2_Factorize_NN)
 __device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ cf, double* __restrict__ cv, int i, int k);
 
-__global__ void __launch_bounds__(128, POISSON_MIN_BLOCKS) poisson_modes_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv) {
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= D.nmodes) return;
     const int i = (int)(m % D.nxh), k = (int)(m / D.nxh);
@@ -356,30 +389,54 @@ __global__ void __launch_bounds__(128, POISSON_MIN_BLOCKS) poisson_modes_kernel(
     LineRef u1 = plane(D.fund + 2 * plane_sz, D.ny, m), sp = plane(D.fund + 3 * plane_sz, D.ny, m),
             ep = plane(D.fund + 4 * plane_sz, D.ny, m);
     LineRef ul[2] = {fre, fim}, vl[2] = {vre, vim};
+    double fn[2], v_1[2], u_n[2];
 #pragma unroll
     for (int l = 0; l < 2; l++) {
-        double v_1 = (bcb[l] - lam * ul[l].get(1)) / a11;
-        double u_n = (bct[l] - vl[l].get(n) - a21 * v_1) / a22;
-        const double fn = (bct[l] - du0[l] - a31 * v_1 - a32 * u_n) / a33;
-        u_n = u_n - a23 * fn;
-        v_1 = v_1 - a12 * u_n - a13 * fn;
-        // rows n, n-1 .. 2, 1
-        {
-            const double un_new = u_n;       // u(:, nx) has been replaced by the boundary value
-            const double vv = vl[l].get(n) + fn * v1.get(n) + v_1 * em.get(n) + lam * un_new;
-            ul[l].set(n, un_new);
-            vl[l].set(n, vv);
+        v_1[l] = (bcb[l] - lam * ul[l].get(1)) / a11;
+        u_n[l] = (bct[l] - vl[l].get(n) - a21 * v_1[l]) / a22;
+        fn[l] = (bct[l] - du0[l] - a31 * v_1[l] - a32 * u_n[l]) / a33;
+        u_n[l] = u_n[l] - a23 * fn[l];
+        v_1[l] = v_1[l] - a12 * u_n[l] - a13 * fn[l];
+    }
+    // rows n, n-1 .. 2, 1: the five fundamental lines are read once for both components, CRB rows per batch
+    constexpr int CRB = 4;
+    for (int r0 = n; r0 >= 1; r0 -= CRB) {
+        double fu[5][CRB], uu0[2][CRB], vv0[2][CRB];
+#pragma unroll
+        for (int j = 0; j < CRB; j++) {
+            const int r = r0 - j;
+            const bool ok = (r >= 1);
+            fu[0][j] = ok ? v1.get(r) : 0.0;
+            fu[1][j] = ok ? em.get(r) : 0.0;
+            fu[2][j] = (ok && r < n) ? u1.get(r) : 0.0;
+            fu[3][j] = (ok && r < n) ? sp.get(r) : 0.0;
+            fu[4][j] = (ok && r < n) ? ep.get(r) : 0.0;
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+                uu0[l][j] = (ok && r < n) ? ul[l].get(r) : 0.0;
+                vv0[l][j] = (ok && r > 1) ? vl[l].get(r) : 0.0;
+            }
         }
-        for (int r = n - 1; r >= 2; r--) {
-            const double uu = ul[l].get(r) + fn * u1.get(r) + v_1 * sp.get(r) + u_n * ep.get(r);
-            const double vv = vl[l].get(r) + fn * v1.get(r) + v_1 * em.get(r) + lam * uu;
-            ul[l].set(r, uu);
-            vl[l].set(r, vv);
-        }
-        {
-            const double uu = ul[l].get(1) + fn * u1.get(1) + v_1 * sp.get(1) + u_n * ep.get(1);
-            ul[l].set(1, uu);
-            vl[l].set(1, v_1 + lam * uu);
+#pragma unroll
+        for (int j = 0; j < CRB; j++) {
+            const int r = r0 - j;
+            if (r < 1) break;
+#pragma unroll
+            for (int l = 0; l < 2; l++) {
+                double uu, vv;
+                if (r == n) {
+                    uu = u_n[l];                 // u(:, nx) has been replaced by the boundary value
+                    vv = vv0[l][j] + fn[l] * fu[0][j] + v_1[l] * fu[1][j] + lam * uu;
+                } else if (r == 1) {
+                    uu = uu0[l][j] + fn[l] * fu[2][j] + v_1[l] * fu[3][j] + u_n[l] * fu[4][j];
+                    vv = v_1[l] + lam * uu;
+                } else {
+                    uu = uu0[l][j] + fn[l] * fu[2][j] + v_1[l] * fu[3][j] + u_n[l] * fu[4][j];
+                    vv = vv0[l][j] + fn[l] * fu[0][j] + v_1[l] * fu[1][j] + lam * uu;
+                }
+                ul[l].set(r, uu);
+                vl[l].set(r, vv);
+            }
         }
     }
 }
@@ -597,7 +654,10 @@ int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const do
         ProfScope ps(PC_POISSON_Y);
         const int threads = 128;
         const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
-        poisson_modes_kernel<<<blocks, threads, 0, st>>>(D, c1, c2);
+        const int minb = ctx().tune_poisson_minb;
+        if (minb == 4) poisson_modes_kernel<4><<<blocks, threads, 0, st>>>(D, c1, c2);
+        else if (minb == 2) poisson_modes_kernel<2><<<blocks, threads, 0, st>>>(D, c1, c2);
+        else poisson_modes_kernel<3><<<blocks, threads, 0, st>>>(D, c1, c2);
         if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
     }
     if (int rc = fft_z(c1, c3, CUFFT_INVERSE)) return rc;

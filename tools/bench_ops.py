@@ -103,8 +103,11 @@ def main():
         hb = torch.zeros(nx * nz, dtype=torch.float64, device=dev)
         ht = torch.zeros_like(hb)
         p = u.clone()
-        timeit(lambda: opr.OPR_Poisson(nx, ny, nz, 3, p, t1, t2, hb, ht, r1), 120 * N, "OPR_Poisson (120 B/pt model)")
-        rows[-1]["GBs_at_24B_floor"] = rows[-1]["GBs"] * 24.0 / 120.0
+        for minb in (4, 3, 2):
+            tl.check(L.tlab_gpu_set_tuning(b"poisson_minb", minb))
+            timeit(lambda: opr.OPR_Poisson(nx, ny, nz, 3, p, t1, t2, hb, ht, r1), 120 * N, "OPR_Poisson (120 B/pt model) minb=%d" % minb)
+            if rows:
+                rows[-1]["GBs_at_24B_floor"] = rows[-1]["GBs"] * 24.0 / 120.0
     if args.json:
         json.dump({"shape": [nx, ny, nz], "peak_GBs": peak, "peak_kind": kind, "rows": rows}, open(args.json, "w"), indent=1)
 
