@@ -217,6 +217,9 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=dev)
     L = tl.load()
     tl.check(L.tlab_gpu_init(local_rank))
+    for kv in [t for t in args.tune.split(",") if t]:
+        k, v = kv.split("=")
+        tl.check(L.tlab_gpu_set_tuning(k.encode(), int(v)))
 
     nx, ny, nz = WORKLOADS[args.workload]
     if args.nx:
@@ -372,6 +375,7 @@ def main():
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--nz", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--tune", default="", help="library tuning knobs, e.g. fuse=0,pf_next=1 (tlab_gpu_set_tuning)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

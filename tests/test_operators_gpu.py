@@ -96,11 +96,12 @@ def test_opr_burgers(cuda, case):
         assert rel_l2(res.cpu().numpy(), ident) <= 1e-11
 
 
-def test_boundary_bcs_neumann_y(cuda):
+@pytest.mark.parametrize("shape", [(40, 37, 24), (32, 256, 16)])     # general kernel / fast kernel (wall chunks only)
+def test_boundary_bcs_neumann_y(cuda, shape):
     import torch
     from oracle import operators as O
     from tlab_b200 import opr
-    nx, ny, nz = 40, 37, 24
+    nx, ny, nz = shape
     grids, go, gg = _plans(nx, ny, nz, "tanh")
     a = smooth_field((nz, ny, nx), grids, seed=5)
     u = torch.from_numpy(a).to(cuda)

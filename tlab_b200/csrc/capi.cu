@@ -1,6 +1,7 @@
 // C ABI: runtime, plans and the directional operators (see include/tlab_gpu.h).
 #include "../../include/tlab_gpu.h"
 #include "context.h"
+#include "trp.h"
 #include <cstring>
 #include <algorithm>
 #include <cstdio>
@@ -81,8 +82,7 @@ static void set_geometry(LineArgs& a, int dir, int nx, int ny, int nz, bool& con
 
 
 // fast path (lines2.cu): full chunks, aligned tiles, short look-back windows; otherwise the general kernels of lines.cu
-static cudaError_t launch_any(int mode, const LineArgs& a, const DevPlan& p, const Sys2& s1, const Sys2& s2, bool periodic,
-                              bool need1, bool contig, cudaStream_t st) {
+static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys2& s1, const Sys2& s2, bool contig, Line2Args& b) {
     int L = 0;
     bool fast = ctx().tune_fast != 0 && lines2_eligible(p, s1, &s2, a.n, a.nlines, a.inner, contig,
                                                          contig ? ctx().tune_lines_x : ctx().tune_lines_yz, &L);
@@ -90,9 +90,7 @@ static cudaError_t launch_any(int mode, const LineArgs& a, const DevPlan& p, con
         auto al = [](const void* q) { return (reinterpret_cast<size_t>(q) & 15) == 0; };
         fast = al(a.u) && al(a.u2) && al(a.vel) && al(a.out1) && al(a.out2);
     }
-    if (!fast) { ctx().general_launches++; return launch_lines(mode, a, periodic, need1, contig, st); }
-    ctx().fast_launches++;
-    Line2Args b;
+    if (!fast) return false;
     b.n = a.n; b.T = a.n / CHUNK; b.L = L;
     b.xls = contig ? lines2_xstride(b.T, L) : 0;
     if (!contig && ctx().tune_persist && mode != MODE_NEUMANN && !(a.u2 && mode == MODE_BURGERS)) {
@@ -113,6 +111,14 @@ static cudaError_t launch_any(int mode, const LineArgs& a, const DevPlan& p, con
     std::memcpy(b.neu_bot, a.neu_bot, sizeof(b.neu_bot));
     std::memcpy(b.neu_top, a.neu_top, sizeof(b.neu_top));
     b.neu_lu_bot = a.neu_lu_bot; b.neu_lu_top = a.neu_lu_top;
+    return true;
+}
+
+static cudaError_t launch_any(int mode, const LineArgs& a, const DevPlan& p, const Sys2& s1, const Sys2& s2, bool periodic,
+                              bool need1, bool contig, cudaStream_t st) {
+    Line2Args b;
+    if (!build_line2(mode, a, p, s1, s2, contig, b)) { ctx().general_launches++; return launch_lines(mode, a, periodic, need1, contig, st); }
+    ctx().fast_launches++;
     return launch_lines2(mode, b, periodic, need1, contig, a.nlines, a.inner, st);
 }
 
@@ -179,6 +185,51 @@ int run_burgers(int dir, int is, int nx, int ny, int nz, int ibc, tlab_plan_s* g
     a.lu2 = p.lu2[g->burgers_first + is];
     ProfScope ps(PC_BURGERS_X + dir - 1);
     return cuda_check(launch_any(MODE_BURGERS, a, p, p.sys1[ibc], p.sys2[g->burgers_first + is], p.periodic, p.need_1der, contig, st), "burgers kernel");
+}
+
+// OPR_Burgers along one direction for several fields advected by the same velocity, accumulated into out[f]
+// (the twelve calls of RHS_GLOBAL_INCOMPRESSIBLE_1, rhs_global_incompressible_1.f90:98-162, grouped by direction):
+// one fused launch when the fast kernels apply, one launch per field otherwise
+int run_burgers_multi(int dir, int nf, const int* is, const double* const* sf, const double* vel, double* const* out,
+                      int nx, int ny, int nz, tlab_plan_s* g, long long* launches) {
+    int rc = check_dims(dir, nx, ny, nz, g);
+    if (rc) return rc;
+    auto fallback = [&]() {
+        for (int f = 0; f < nf; f++) {
+            if (int r = run_burgers(dir, is[f], nx, ny, nz, 0, g, sf[f], vel, out[f], +1)) return r;
+            if (launches) (*launches)++;
+        }
+        return 0;
+    };
+    if (g->p.n == 1 || nf < 2 || nf > 4 || g->burgers_first < 0 || !ctx().tune_fuse) return fallback();
+    int is_b = -1;
+    for (int f = 0; f < nf; f++) {
+        if (is[f] < 0 || is[f] >= g->burgers_count) return fail(TLAB_ERR_OPTION, "scalar index out of range");
+        if (is[f] != is[0]) { if (is_b < 0) is_b = is[f]; else if (is[f] != is_b) return fallback(); }
+    }
+    const DevPlan& p = g->p;
+    LineArgs a;
+    fill_common(a, p);
+    bool contig;
+    set_geometry(a, dir, nx, ny, nz, contig);
+    a.u = sf[0]; a.vel = vel; a.out1 = out[0]; a.accumulate = +1;
+    a.rhs1 = p.rhs1[0];
+    a.lu1 = p.lu1[0];
+    a.lu2 = p.lu2[g->burgers_first + is[0]];
+    Line2Args b;
+    if (!build_line2(MODE_BURGERS, a, p, p.sys1[0], p.sys2[g->burgers_first + is[0]], contig, b)) return fallback();
+    if (is_b >= 0 && !p.sys2[g->burgers_first + is_b].ok) return fallback();
+    auto al = [](const void* q) { return (reinterpret_cast<size_t>(q) & 15) == 0; };
+    for (int f = 0; f < nf; f++) if (contig && !(al(sf[f]) && al(out[f]))) return fallback();
+    b.persist = 0;
+    b.nf = nf;
+    b.pf_next = ctx().tune_pf_next;
+    for (int f = 0; f < nf; f++) { b.fu[f] = sf[f]; b.fo[f] = out[f]; b.fsys[f] = (is[f] == is[0]) ? 0 : 1; }
+    if (is_b >= 0) b.s2b = p.sys2[g->burgers_first + is_b];
+    ctx().fast_launches++;
+    if (launches) (*launches)++;
+    ProfScope ps(PC_BURGERS_X + dir - 1);
+    return cuda_check(launch_lines2(MODE_BURGERS, b, p.periodic, p.need_1der, contig, a.nlines, a.inner, ctx().stream), "fused burgers kernel");
 }
 
 int run_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_s* g, const double* u, double* hb, double* ht) {
@@ -320,6 +371,9 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "fast")) ctx().tune_fast = value;
     else if (!std::strcmp(key, "pf_dist")) ctx().tune_pf_dist = value;
     else if (!std::strcmp(key, "persist")) ctx().tune_persist = value;
+    else if (!std::strcmp(key, "fuse")) ctx().tune_fuse = value;
+    else if (!std::strcmp(key, "p2p")) trp().p2p_enabled = (value != 0);
+    else if (!std::strcmp(key, "pf_next")) ctx().tune_pf_next = value;
     else if (!std::strcmp(key, "poisson_minb")) ctx().tune_poisson_minb = value;
     else return fail(TLAB_ERR_OPTION, std::string("unknown tuning key ") + key);
     return 0;
@@ -329,6 +383,8 @@ int tlab_gpu_get_counter(const char* key, long long* value) {
     if (!key || !value) return fail(TLAB_ERR_OPTION, "null argument");
     if (!std::strcmp(key, "fast_launches")) *value = ctx().fast_launches;
     else if (!std::strcmp(key, "general_launches")) *value = ctx().general_launches;
+    else if (!std::strcmp(key, "p2p_exchanges")) *value = trp().p2p_exchanges;
+    else if (!std::strcmp(key, "nccl_exchanges")) *value = trp().nccl_exchanges;
     else return fail(TLAB_ERR_OPTION, std::string("unknown counter ") + key);
     return 0;
 }

@@ -26,6 +26,8 @@ struct Context {
     int tune_fast = 1;        // 1: use the fast line kernels (lines2.cu) whenever the geometry allows
     int tune_pf_dist = -1;
     int tune_poisson_minb = 3;  // resident CTAs per SM the Poisson y kernel is compiled for (register budget)
+    int tune_pf_next = 0;     // fused Burgers launch: L2 prefetch of the tile's next field
+    int tune_fuse = 0;        // RHS: one fused Burgers launch per direction (fields sharing the advecting velocity)
     int tune_persist = 0;     // strided fast kernels: persistent CTAs with asynchronous staging
     long long fast_launches = 0, general_launches = 0;    // L2 prefetch distance of the fast kernels in tiles (-1: automatic, 0: off)
     tlab_plan_s* burgers_plans[3] = {nullptr, nullptr, nullptr};
@@ -54,6 +56,8 @@ int run_partial(int dir, int type, int nx, int ny, int nz, int ibc, tlab_plan_s*
                 double* tmp1, const double* u2 = nullptr, double scale = 0.0, int accumulate = 0);
 int run_burgers(int dir, int is, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* s, const double* vel,
                 double* result, int accumulate);
+int run_burgers_multi(int dir, int nf, const int* is, const double* const* sf, const double* vel, double* const* out,
+                      int nx, int ny, int nz, tlab_plan_s* g, long long* launches);
 int run_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_s* g, const double* u, double* hb, double* ht);
 
 }  // namespace tlab

@@ -276,13 +276,19 @@ struct Dns {
         if (P > 1 && nzg > 1) {     // transposed w is shared by the four z operators (tmp6 of the reference)
             if ((rc = trp().forward(w, nullptr, 0.0, zw, (long long)nx * ny, nz))) return rc;
         }
-        // hq1 += Bx(u,u) + By(u,v) + Bz(u,w)          (:98-111)
-        B(1, 0, u, u, hq[0]); B(2, 0, u, v, hq[0]); B(3, 0, u, w, hq[0]);
-        // hq2 += By(v,v) + Bx(v,u) + Bz(v,w)          (:99,115-123)
-        B(2, 0, v, v, hq[1]); B(1, 0, v, u, hq[1]); B(3, 0, v, w, hq[1]);
-        // hq3 += Bz(w,w) + Bx(w,u) + By(w,v)          (:100,127-135)
-        B(3, 0, w, w, hq[2]); B(1, 0, w, u, hq[2]); B(2, 0, w, v, hq[2]);
-        for (int is = 0; is < ns; is++) {              // (:149-162)
+        // hq_i += Bx(q_i,u) + By(q_i,v) + Bz(q_i,w), hs += ... (:98-162).  Grouped by direction, so that the fields that share
+        // the advecting velocity go into one fused launch (sums reordered within round-off: x, y, z for every field).
+        const int nfields = std::min(3 + ns, 4);
+        const double* sf[4] = {u, v, w, ns > 0 ? s[0] : nullptr};
+        double* outs[4] = {hq[0], hq[1], hq[2], ns > 0 ? hs[0] : nullptr};
+        const int isv[4] = {0, 0, 0, 1};
+        const bool fuse_z = (P == 1);
+        for (int dir = 1; dir <= 3 && !rc; dir++) {
+            if (dir == 3 && !fuse_z) break;
+            rc = run_burgers_multi(dir, nfields, isv, sf, q[dir - 1], outs, nx, ny, nz, g[dir - 1], &launches);
+        }
+        if (!fuse_z) { B(3, 0, u, w, hq[0]); B(3, 0, v, w, hq[1]); B(3, 0, w, w, hq[2]); if (ns > 0) B(3, 1, s[0], w, hs[0]); }
+        for (int is = 1; is < ns; is++) {              // further scalars: one launch each
             B(1, is + 1, s[is], u, hs[is]); B(2, is + 1, s[is], v, hs[is]); B(3, is + 1, s[is], w, hs[is]);
         }
         if (rc) return rc;
@@ -362,6 +368,7 @@ struct Dns {
     }
 
     void release() {
+        for (double* b : {zs, zw, zr, c2}) if (b) trp().unregister_buffer(b);
         for (void* a : allocs) cudaFree(a);
         allocs.clear();
         if (host_stage) cudaFreeHost(host_stage);
@@ -428,6 +435,9 @@ int tlab_dns_create(const tlab_dns_params* prm, tlab_plan_t gx, tlab_plan_t gy, 
         if (!rc) rc = d.alloc(&d.zs, d.N);
         if (!rc) rc = d.alloc(&d.zw, d.N);
         if (!rc) rc = d.alloc(&d.zr, d.N);
+        // peer-memory transposes: publish the pencil buffers to the other ranks (collective, same order everywhere)
+        if (!rc) rc = cuda_check(cudaStreamSynchronize(ctx().stream), "tlab_dns_create");
+        for (double* b : {d.zs, d.zw, d.zr, d.c2}) if (!rc) rc = trp().register_buffer(b);
     }
     if (!rc && bbackground_host)
         rc = cuda_check(cudaMemcpyAsync(d.bbackground, bbackground_host, d.ny * sizeof(double), cudaMemcpyHostToDevice, ctx().stream), "bbackground");

@@ -294,8 +294,8 @@ __host__ __device__ inline size_t exch2_doubles(int T, int L) { return (size_t)6
 
 // right-hand sides + solves: u (chunk + halos) -> d1, d2
 template <int MODE, bool PER, bool NEED1>
-__device__ __forceinline__ void line_core2(const double (&u)[C + 6], const Line2Args& a, const ChunkCtx& c, double* sm,
-                                           double (&d1)[C], double (&d2)[C]) {
+__device__ __forceinline__ void line_core2(const double (&u)[C + 6], const Line2Args& a, const Sys2& S2, const ChunkCtx& c,
+                                           double* sm, double (&d1)[C], double (&d2)[C]) {
     constexpr bool WANT1 = (MODE == MODE_P1) || (MODE == MODE_P2_P1) || (MODE == MODE_BURGERS) || (MODE == MODE_NEUMANN) || NEED1;
     constexpr bool WANT2 = (MODE == MODE_P2) || (MODE == MODE_P2_P1) || (MODE == MODE_BURGERS);
     if (WANT1) {
@@ -313,25 +313,23 @@ __device__ __forceinline__ void line_core2(const double (&u)[C + 6], const Line2
         }
     }
     if (WANT1 && WANT2 && !NEED1) {
-        solve_two<PER>(d1, d2, a.s1, a.s2, c, sm);
+        solve_two<PER>(d1, d2, a.s1, S2, c, sm);
     } else {
         if (WANT1) solve_one<PER>(d1, a.s1, c, sm);
         if (WANT2) {
             if (NEED1) add_jacobian_term(d2, d1, a, c, sm + 6 * c.T * c.L);
-            solve_one<PER>(d2, a.s2, c, sm + 3 * c.T * c.L);
+            solve_one<PER>(d2, S2, c, sm + 3 * c.T * c.L);
         }
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // y / z directions: lines strided in memory, contiguous across lines.  grid = (inner / L, nlines / inner)
-template <int MODE, bool PER, bool NEED1>
-__global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__ Line2Args a) {
-    extern __shared__ double sm[];
-    ChunkCtx c;
-    c.L = a.L; c.T = a.T;
-    c.l = threadIdx.x & (a.L - 1);
-    c.t = threadIdx.x >> a.lshift;
+// One field of one tile: fu = field, fo = result (out1), S2 = second-derivative system, KEEPV: the velocity is read with
+// the default cache policy (it is shared by the fields of a fused Burgers launch and should stay in L1).
+template <int MODE, bool PER, bool NEED1, bool KEEPV>
+__device__ __forceinline__ void strided_field(const Line2Args& a, const ChunkCtx& c, double* sm, const double* __restrict__ fu,
+                                              double* __restrict__ fo, const Sys2& S2) {
     const long long st = a.stride;
     const long long tile0 = (long long)blockIdx.y * a.outer_stride + (long long)blockIdx.x * a.L;
     const long long lbase = tile0 + c.l;
@@ -339,7 +337,7 @@ __global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__
     const bool has_u2 = (a.u2 != nullptr);
     const bool has_acc = (a.accumulate != 0) && (MODE == MODE_BURGERS || MODE == MODE_P1);
 
-    // ---- L2 prefetch of a later tile (one 32..64-byte row segment per request)
+    // ---- L2 prefetch of a later tile (one row segment per request)
     if (a.pf_dist > 0) {
         const unsigned tile = blockIdx.y * gridDim.x + blockIdx.x + (unsigned)a.pf_dist;
         if (tile < gridDim.x * gridDim.y) {
@@ -347,10 +345,10 @@ __global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__
             const long long pb = (long long)ty * a.outer_stride + (long long)tx * a.L;
             for (int r = threadIdx.x; r < n; r += blockDim.x) {
                 const long long o = pb + (long long)r * st;
-                prefetch_l2(a.u + o);
+                prefetch_l2(fu + o);
                 if (has_u2) prefetch_l2(a.u2 + o);
-                if (MODE == MODE_BURGERS && a.vel != a.u) prefetch_l2(a.vel + o);
-                if (has_acc) prefetch_l2(a.out1 + o);
+                if (MODE == MODE_BURGERS && a.vel != fu) prefetch_l2(a.vel + o);
+                if (has_acc) prefetch_l2(fo + o);
             }
         }
     }
@@ -361,8 +359,14 @@ __global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__
     const bool lok = PER || c.t > 0, rok = PER || c.t < c.T - 1;
     const long long loff = (c.t > 0) ? -3 * st : (long long)(n - 3) * st;
     const long long roff = (c.t < c.T - 1) ? (long long)C * st : -(long long)(c.t * C) * st;
-    {
-        const double* __restrict__ pc = a.u + coff;
+    // BOUNDARY_BCS_NEUMANN_Y needs the derivative next to the walls only, and the solution there feels the right-hand
+    // side of the first LB2 chunks only (the same 2^-80 truncation as the look-back): the rest of the line is not read
+    const bool skip = (MODE == MODE_NEUMANN) && !((a.bcs_hb != nullptr && c.t < LB2) || (a.bcs_ht != nullptr && c.t >= c.T - LB2));
+    if (skip) {
+#pragma unroll
+        for (int k = 0; k < C + 6; k++) u[k] = 0.0;
+    } else {
+        const double* __restrict__ pc = fu + coff;
 #pragma unroll
         for (int j = 0; j < C; j++) u[j + 3] = __ldcs(pc + j * st);
 #pragma unroll
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__
         }
     }
     double d1[C], d2[C];
-    line_core2<MODE, PER, NEED1>(u, a, c, sm, d1, d2);
+    line_core2<MODE, PER, NEED1>(u, a, S2, c, sm, d1, d2);
 
     if (MODE == MODE_NEUMANN) {
         // boundary values such that the normal derivative vanishes (BOUNDARY_BCS_NEUMANN_Y)
@@ -399,12 +403,12 @@ __global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__
         if (c.t == c.T - 1 && a.bcs_ht != nullptr) a.bcs_ht[line] = nt_sum + a.neu_lu_top * d1[C - 2];
         return;
     }
-    double* __restrict__ o1 = a.out1 + coff;
+    double* __restrict__ o1 = fo + coff;
     if (MODE == MODE_BURGERS) {
         const double* __restrict__ vp = a.vel + coff;
         double vv[C];
 #pragma unroll
-        for (int j = 0; j < C; j++) vv[j] = __ldcs(vp + j * st);
+        for (int j = 0; j < C; j++) vv[j] = KEEPV ? __ldg(vp + j * st) : __ldcs(vp + j * st);
         if (has_acc) {
             double oo[C];
 #pragma unroll
@@ -430,6 +434,43 @@ __global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__
         if (MODE == MODE_P1) __stcs(o1 + j * st, d1[j]);
         if (MODE == MODE_P2 || MODE == MODE_BURGERS) __stcs(o1 + j * st, d2[j]);
         if (MODE == MODE_P2_P1) { __stcs(o1 + j * st, d2[j]); __stcs(a.out2 + coff + j * st, d1[j]); }
+    }
+}
+
+template <int MODE, bool PER, bool NEED1>
+__global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__ Line2Args a) {
+    extern __shared__ double sm[];
+    ChunkCtx c;
+    c.L = a.L; c.T = a.T;
+    c.l = threadIdx.x & (a.L - 1);
+    c.t = threadIdx.x >> a.lshift;
+    strided_field<MODE, PER, NEED1, false>(a, c, sm, a.u, a.out1, a.s2);
+}
+
+// fused Burgers launch: the fields fu[0..nf) of a tile are advected by the same velocity (OPR_Burgers_X/Y/Z of u, v, w
+// and the scalars in RHS_GLOBAL_INCOMPRESSIBLE_1): the velocity comes from DRAM once per tile instead of once per field
+template <bool PER, bool NEED1>
+__global__ void __launch_bounds__(512, 1) lines2_strided_multi(const __grid_constant__ Line2Args a) {
+    extern __shared__ double sm[];
+    ChunkCtx c;
+    c.L = a.L; c.T = a.T;
+    c.l = threadIdx.x & (a.L - 1);
+    c.t = threadIdx.x >> a.lshift;
+    for (int f = 0; f < a.nf; f++) {
+        if (f > 0) __syncthreads();                 // the exchange areas of the previous field are free again
+        if (a.pf_next && f + 1 < a.nf) {
+            // the next field of this tile goes to L2 while this one is being solved
+            const long long tile0 = (long long)blockIdx.y * a.outer_stride + (long long)blockIdx.x * a.L;
+            const bool two = (a.L * 8 > 128);       // rows longer than one 128-byte line
+            for (int r = threadIdx.x; r < a.n; r += blockDim.x) {
+                const long long o = tile0 + (long long)r * a.stride;
+                prefetch_l2(a.fu[f + 1] + o);
+                prefetch_l2(a.fo[f + 1] + o);
+                if (two) { prefetch_l2(a.fu[f + 1] + o + 16); prefetch_l2(a.fo[f + 1] + o + 16); }
+            }
+        }
+        const Sys2& S2 = a.fsys[f] ? a.s2b : a.s2;
+        strided_field<MODE_BURGERS, PER, NEED1, true>(a, c, sm, a.fu[f], a.fo[f], S2);
     }
 }
 
@@ -547,7 +588,7 @@ __global__ void __launch_bounds__(512, 1) lines2_strided_pa(const __grid_constan
             for (int j = 0; j < C; j++) vq[j * L] = u[j + 3];
         }
         double d1[C], d2[C];
-        line_core2<MODE, PER, NEED1>(u, a, c, sm, d1, d2);
+        line_core2<MODE, PER, NEED1>(u, a, a.s2, c, sm, d1, d2);
 
         double* __restrict__ o1 = a.out1 + coff;
         if (MODE == MODE_BURGERS) {
@@ -622,18 +663,15 @@ __device__ __forceinline__ void tile_load(double* tile, const double* __restrict
     }
 }
 
-template <int MODE, bool PER, bool NEED1>
-__global__ void __launch_bounds__(512, 1) lines2_contig(const __grid_constant__ Line2Args a) {
-    extern __shared__ double sm[];
-    ChunkCtx c;
-    c.L = a.L; c.T = a.T;
-    c.l = threadIdx.x & (a.L - 1);
-    c.t = threadIdx.x >> a.lshift;
+// One field of one tile.  MULTI: fused Burgers launch, the velocity tile has been staged by the caller.
+template <int MODE, bool PER, bool NEED1, bool MULTI>
+__device__ __forceinline__ void contig_field(const Line2Args& a, const ChunkCtx& c, double* sm, const double* __restrict__ fu,
+                                             double* __restrict__ fo, const Sys2& S2) {
     const int n = a.n, T = a.T, L = a.L, LS = a.xls;
     const size_t tile_off = (size_t)blockIdx.x * L * n;
     double* tile = sm + exch2_doubles(T, L);
     double* vtile = tile + (size_t)L * LS;
-    const bool two = (MODE == MODE_BURGERS) && (a.vel != a.u);
+    const bool two = MULTI || ((MODE == MODE_BURGERS) && (a.vel != fu));
     const bool has_acc = (a.accumulate != 0) && (MODE == MODE_BURGERS || MODE == MODE_P1);
 
     if (a.pf_dist > 0) {
@@ -641,16 +679,16 @@ __global__ void __launch_bounds__(512, 1) lines2_contig(const __grid_constant__ 
         if (tilei < gridDim.x) {
             const size_t po = (size_t)tilei * L * n;
             for (int r = threadIdx.x * 16; r < L * n; r += blockDim.x * 16) {      // one request per 128-byte line
-                prefetch_l2(a.u + po + r);
+                prefetch_l2(fu + po + r);
                 if (a.u2 != nullptr) prefetch_l2(a.u2 + po + r);
-                if (two) prefetch_l2(a.vel + po + r);
-                if (has_acc) prefetch_l2(a.out1 + po + r);
+                if (two && !MULTI) prefetch_l2(a.vel + po + r);
+                if (has_acc) prefetch_l2(fo + po + r);
             }
         }
     }
-    if (a.u2 != nullptr) tile_load<true>(tile, a.u + tile_off, a.u2 + tile_off, a.scale, n, T, L, LS);
-    else tile_load<false>(tile, a.u + tile_off, nullptr, 0.0, n, T, L, LS);
-    if (two) tile_load<false>(vtile, a.vel + tile_off, nullptr, 0.0, n, T, L, LS);
+    if (a.u2 != nullptr) tile_load<true>(tile, fu + tile_off, a.u2 + tile_off, a.scale, n, T, L, LS);
+    else tile_load<false>(tile, fu + tile_off, nullptr, 0.0, n, T, L, LS);
+    if (two && !MULTI) tile_load<false>(vtile, a.vel + tile_off, nullptr, 0.0, n, T, L, LS);
     __syncthreads();
 
     const double* row = tile + c.l * LS;
@@ -672,7 +710,7 @@ __global__ void __launch_bounds__(512, 1) lines2_contig(const __grid_constant__ 
         }
     }
     double d1[C], d2[C];
-    line_core2<MODE, PER, NEED1>(u, a, c, sm, d1, d2);
+    line_core2<MODE, PER, NEED1>(u, a, S2, c, sm, d1, d2);
     // all halo reads of the tile happened before the first barrier inside line_core2: results may overwrite it
 
     {
@@ -710,7 +748,7 @@ __global__ void __launch_bounds__(512, 1) lines2_contig(const __grid_constant__ 
 #pragma unroll
             for (int k = 0; k < 8; k++) {
                 const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
-                const double2 o = __ldcs(reinterpret_cast<const double2*>(a.out1 + tile_off + (size_t)ll * n) + i2);
+                const double2 o = __ldcs(reinterpret_cast<const double2*>(fo + tile_off + (size_t)ll * n) + i2);
                 if (a.accumulate > 0) { v[k].x = o.x + v[k].x; v[k].y = o.y + v[k].y; }
                 else { v[k].x = o.x - v[k].x; v[k].y = o.y - v[k].y; }
             }
@@ -718,7 +756,7 @@ __global__ void __launch_bounds__(512, 1) lines2_contig(const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < 8; k++) {
             const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
-            __stcs(reinterpret_cast<double2*>(a.out1 + tile_off + (size_t)ll * n) + i2, v[k]);
+            __stcs(reinterpret_cast<double2*>(fo + tile_off + (size_t)ll * n) + i2, v[k]);
         }
     }
     if (MODE == MODE_P2_P1) {
@@ -728,6 +766,47 @@ __global__ void __launch_bounds__(512, 1) lines2_contig(const __grid_constant__ 
             const double2 v = *reinterpret_cast<const double2*>(vtile + ll * LS + (i2 >> 3) * XB + (i2 & 7) * 2);
             __stcs(reinterpret_cast<double2*>(a.out2 + tile_off + (size_t)ll * n) + i2, v);
         }
+    }
+}
+
+template <int MODE, bool PER, bool NEED1>
+__global__ void __launch_bounds__(512, 1) lines2_contig(const __grid_constant__ Line2Args a) {
+    extern __shared__ double sm[];
+    ChunkCtx c;
+    c.L = a.L; c.T = a.T;
+    c.l = threadIdx.x & (a.L - 1);
+    c.t = threadIdx.x >> a.lshift;
+    contig_field<MODE, PER, NEED1, false>(a, c, sm, a.u, a.out1, a.s2);
+}
+
+// fused Burgers launch along x (see lines2_strided_multi): the velocity tile is staged once per tile
+template <bool PER, bool NEED1>
+__global__ void __launch_bounds__(512, 1) lines2_contig_multi(const __grid_constant__ Line2Args a) {
+    extern __shared__ double sm[];
+    ChunkCtx c;
+    c.L = a.L; c.T = a.T;
+    c.l = threadIdx.x & (a.L - 1);
+    c.t = threadIdx.x >> a.lshift;
+    {
+        double* vtile = sm + exch2_doubles(a.T, a.L) + (size_t)a.L * a.xls;
+        const size_t tile_off = (size_t)blockIdx.x * a.L * a.n;
+        if (a.pf_dist > 0 && blockIdx.x + (unsigned)a.pf_dist < gridDim.x) {
+            const size_t po = (size_t)(blockIdx.x + (unsigned)a.pf_dist) * a.L * a.n;
+            for (int r = threadIdx.x * 16; r < a.L * a.n; r += blockDim.x * 16) prefetch_l2(a.vel + po + r);
+        }
+        tile_load<false>(vtile, a.vel + tile_off, nullptr, 0.0, a.n, a.T, a.L, a.xls);
+    }
+    for (int f = 0; f < a.nf; f++) {
+        if (f > 0) __syncthreads();                 // tile and exchange areas of the previous field are free again
+        if (a.pf_next && f + 1 < a.nf) {
+            const size_t to = (size_t)blockIdx.x * a.L * a.n;
+            for (int r = threadIdx.x * 16; r < a.L * a.n; r += blockDim.x * 16) {
+                prefetch_l2(a.fu[f + 1] + to + r);
+                prefetch_l2(a.fo[f + 1] + to + r);
+            }
+        }
+        const Sys2& S2 = a.fsys[f] ? a.s2b : a.s2;
+        contig_field<MODE_BURGERS, PER, NEED1, true>(a, c, sm, a.fu[f], a.fo[f], S2);
     }
 }
 
@@ -798,6 +877,46 @@ cudaError_t launch2(const Line2Args& a_in, bool contig, dim3 grid, cudaStream_t 
     return cudaGetLastError();
 }
 
+template <bool PER, bool NEED1>
+cudaError_t launch2_multi(const Line2Args& a_in, bool contig, dim3 grid, cudaStream_t stream) {
+    Line2Args a = a_in;
+    const int threads = a.L * a.T;
+    size_t smem = exch2_doubles(a.T, a.L) * sizeof(double);
+    if (contig) {
+        smem += (size_t)a.L * a.xls * sizeof(double) * 2;
+        auto k = lines2_contig_multi<PER, NEED1>;
+        static size_t set = 0;
+        if (smem > set) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            set = smem;
+        }
+        static int pf = 0, pf_threads = 0;
+        static size_t pf_smem = 0;
+        if (a.pf_dist < 0) {
+            if (pf_threads != threads || pf_smem != smem) { pf = auto_pf_dist(k, threads, smem); pf_threads = threads; pf_smem = smem; }
+            a.pf_dist = pf;
+        }
+        k<<<grid, threads, smem, stream>>>(a);
+    } else {
+        auto k = lines2_strided_multi<PER, NEED1>;
+        static size_t set = 48 * 1024;
+        if (smem > set) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            set = smem;
+        }
+        static int pf = 0, pf_threads = 0;
+        static size_t pf_smem = 0;
+        if (a.pf_dist < 0) {
+            if (pf_threads != threads || pf_smem != smem) { pf = auto_pf_dist(k, threads, smem); pf_threads = threads; pf_smem = smem; }
+            a.pf_dist = pf;
+        }
+        k<<<grid, threads, smem, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+
 template <int MODE>
 cudaError_t launch2_mode(const Line2Args& a, bool per, bool need1, bool contig, dim3 grid, cudaStream_t s) {
     if (per) return launch2<MODE, true, false>(a, contig, grid, s);
@@ -847,6 +966,11 @@ cudaError_t launch_lines2(int mode, const Line2Args& a, bool periodic, bool need
     dim3 grid;
     if (contig) grid = dim3((unsigned)(nlines / a.L), 1, 1);
     else grid = dim3((unsigned)(inner / a.L), (unsigned)(nlines / inner), 1);
+    if (mode == MODE_BURGERS && a.nf > 0) {
+        if (periodic) return launch2_multi<true, false>(a, contig, grid, s);
+        if (need1) return launch2_multi<false, true>(a, contig, grid, s);
+        return launch2_multi<false, false>(a, contig, grid, s);
+    }
     switch (mode) {
         case MODE_P1: return launch2_mode<MODE_P1>(a, periodic, false, contig, grid, s);
         case MODE_P2: return launch2_mode<MODE_P2>(a, periodic, need1, contig, grid, s);

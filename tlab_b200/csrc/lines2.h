@@ -25,6 +25,13 @@ struct Line2Args {
     const double2* rhs_d1 = nullptr;  // Jacobian correction {r1,r2},{r3,0} per point, chunk-interleaved like Sys2::tab
     RhsTab rhs1, rhs2;
     Sys2 s1, s2;
+    // fused Burgers launch (several fields advected by the same velocity): fields, results and which of s2 / s2b each uses
+    int nf = 0;
+    int pf_next = 0;                  // fused launch: prefetch the next field of the tile into L2
+    int fsys[4] = {0, 0, 0, 0};
+    const double* fu[4] = {nullptr, nullptr, nullptr, nullptr};
+    double* fo[4] = {nullptr, nullptr, nullptr, nullptr};
+    Sys2 s2b;
     double neu_bot[BROW_W], neu_top[BROW_W];
     double neu_lu_bot = 0.0, neu_lu_top = 0.0;
 };

@@ -545,6 +545,8 @@ void Poisson::release() {
     if (plan_bx) cufftDestroy(plan_bx);
     if (plan_z) cufftDestroy(plan_z);
     plan_fx = plan_bx = plan_z = 0;
+    if (c3) trp().unregister_buffer(c3);
+    c3 = nullptr;
     for (void* a : allocs) cudaFree(a);
     allocs.clear();
     ready = false;
@@ -615,6 +617,7 @@ int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz, int nz_loca
         }
         allocs.push_back(c3buf);
         c3 = c3buf;
+        if (int rc = trp().register_buffer(c3)) return rc;
     }
     const int threads = 128;
     const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);

@@ -46,6 +46,63 @@ __global__ void unpack_kernel(const double* __restrict__ recvbuf, double* __rest
     }
 }
 
+// forward transpose by peer stores: b_p[(rank*nzl + k)*nl + i] = a[k*nxy + p*nl + i] (+ scale*a2)
+// grid = (chunks of a run, nzl, P); every run of nl doubles is contiguous on both sides
+__global__ void push_forward_kernel(const double* __restrict__ a, const double* __restrict__ a2, double scale, Trp::PeerTab dst,
+                                    long long nxy, int nzl, long long nl, int rank) {
+    const int p = blockIdx.z, k = blockIdx.y;
+    const double* __restrict__ src = a + (long long)k * nxy + (long long)p * nl;
+    const double* __restrict__ src2 = a2 ? a2 + (long long)k * nxy + (long long)p * nl : nullptr;
+    double* __restrict__ d = dst.p[p] + ((long long)rank * nzl + k) * nl;
+    if ((nl & 1) == 0 && ((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(d) | reinterpret_cast<size_t>(src2)) & 15) == 0) {
+        const long long n2 = nl >> 1;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+            double2 v = __ldcs(reinterpret_cast<const double2*>(src) + i);
+            if (src2) { const double2 w = __ldcs(reinterpret_cast<const double2*>(src2) + i); v.x = v.x + w.x * scale; v.y = v.y + w.y * scale; }
+            reinterpret_cast<double2*>(d)[i] = v;
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (long long)gridDim.x * blockDim.x) {
+            double v = src[i];
+            if (src2) v = v + src2[i] * scale;
+            d[i] = v;
+        }
+    }
+}
+
+// backward transpose by peer loads: a[k*nxy + q*nl + i] (op)= b_q[(rank*nzl + k)*nl + i]
+__global__ void pull_backward_kernel(Trp::PeerTab srcs, double* __restrict__ a, long long nxy, int nzl, long long nl, int rank,
+                                     int accumulate) {
+    const int q = blockIdx.z, k = blockIdx.y;
+    const double* __restrict__ src = srcs.p[q] + ((long long)rank * nzl + k) * nl;
+    double* __restrict__ d = a + (long long)k * nxy + (long long)q * nl;
+    if ((nl & 1) == 0 && ((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(d)) & 15) == 0) {
+        const long long n2 = nl >> 1;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
+            double2 v = reinterpret_cast<const double2*>(src)[i];
+            if (accumulate != 0) {
+                const double2 o = reinterpret_cast<const double2*>(d)[i];
+                if (accumulate > 0) { v.x = o.x + v.x; v.y = o.y + v.y; } else { v.x = o.x - v.x; v.y = o.y - v.y; }
+            }
+            reinterpret_cast<double2*>(d)[i] = v;
+        }
+    } else {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (long long)gridDim.x * blockDim.x) {
+            double v = src[i];
+            if (accumulate > 0) v = d[i] + v; else if (accumulate < 0) v = d[i] - v;
+            d[i] = v;
+        }
+    }
+}
+
+inline dim3 p2p_grid(long long nl, int nzl, int P) {
+    long long per = (nl / 2 + 255) / 256;
+    const long long want = (148LL * 16 + (long long)nzl * P - 1) / ((long long)nzl * P);   // ~16 CTAs per SM in total
+    if (per > want) per = want;
+    if (per < 1) per = 1;
+    return dim3((unsigned)per, (unsigned)nzl, (unsigned)P);
+}
+
 inline unsigned blocks_for(long long n) {
     long long b = (n + 255) / 256;
     return (unsigned)(b < 148LL * 16 ? b : 148LL * 16);
@@ -64,6 +121,92 @@ static int nccl_check(ncclResult_t r, const char* what) {
     return fail(TLAB_ERR_CUDA, std::string(what) + ": " + ncclGetErrorString(r));
 }
 #endif
+
+const Trp::PeerTab* Trp::find(const double* base) const {
+    for (const auto& e : registry) if (e.first == base) return &e.second;
+    return nullptr;
+}
+
+void Trp::unregister_buffer(const double* base) {
+    for (size_t e = 0; e < registry.size(); e++) {
+        if (registry[e].first != base) continue;
+        for (int q = 0; q < 8; q++) if (q != rank && registry[e].second.p[q]) cudaIpcCloseMemHandle(registry[e].second.p[q]);
+        registry.erase(registry.begin() + e);
+        return;
+    }
+}
+
+int Trp::barrier() {
+#ifdef TLAB_HAVE_NCCL
+    if (P == 1) return 0;
+    if (!barrier_buf) {
+        if (cudaMalloc(&barrier_buf, 64) != cudaSuccess) return fail(TLAB_ERR_ALLOC, "barrier buffer");
+        cudaMemsetAsync(barrier_buf, 0, 64, ctx().stream);
+    }
+    return nccl_check(ncclAllReduce(barrier_buf, barrier_buf, 1, ncclInt, ncclSum, comm, ctx().stream), "barrier");
+#else
+    return 0;
+#endif
+}
+
+// Collective.  Publishes `base` (a cudaMalloc allocation) to the other ranks and maps theirs.
+int Trp::register_buffer(double* base) {
+    if (P == 1 || !p2p_enabled || P > 8) return 0;
+#ifdef TLAB_HAVE_NCCL
+    cudaStream_t st = ctx().stream;
+    cudaIpcMemHandle_t mine;
+    int ok = (cudaIpcGetMemHandle(&mine, base) == cudaSuccess) ? 1 : 0;
+    if (!ok) { cudaGetLastError(); std::memset(&mine, 0, sizeof(mine)); }
+    // handles (64 bytes) + ok flag, gathered through NCCL
+    const size_t rec = sizeof(cudaIpcMemHandle_t) + 64;
+    unsigned char* dbuf = nullptr;
+    if (cudaMalloc(&dbuf, rec * (P + 1)) != cudaSuccess) return fail(TLAB_ERR_ALLOC, "ipc exchange buffer");
+    std::vector<unsigned char> h(rec * (P + 1), 0);
+    std::memcpy(h.data(), &mine, sizeof(mine));
+    h[sizeof(mine)] = (unsigned char)ok;
+    cudaMemcpyAsync(dbuf, h.data(), rec, cudaMemcpyHostToDevice, st);
+    int rc = nccl_check(ncclAllGather(dbuf, dbuf + rec, rec, ncclChar, comm, st), "ncclAllGather(ipc handles)");
+    if (!rc) rc = cuda_check(cudaMemcpyAsync(h.data(), dbuf, rec * (P + 1), cudaMemcpyDeviceToHost, st), "ipc handles");
+    if (!rc) rc = cuda_check(cudaStreamSynchronize(st), "ipc handles");
+    cudaFree(dbuf);
+    if (rc) return rc;
+    bool all_ok = true;
+    for (int q = 0; q < P; q++) if (!h[rec * (q + 1) + sizeof(mine)]) all_ok = false;
+    PeerTab tab;
+    for (int q = 0; q < 8; q++) tab.p[q] = nullptr;
+    int opened = 1;
+    if (all_ok) {
+        for (int q = 0; q < P && opened; q++) {
+            if (q == rank) { tab.p[q] = base; continue; }
+            cudaIpcMemHandle_t hq;
+            std::memcpy(&hq, h.data() + rec * (q + 1), sizeof(hq));
+            void* ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); opened = 0; }
+            tab.p[q] = (double*)ptr;
+        }
+    } else opened = 0;
+    // every rank must agree, otherwise the barriers of the two paths would not match
+    int* flag = nullptr;
+    if (cudaMalloc(&flag, sizeof(int)) != cudaSuccess) return fail(TLAB_ERR_ALLOC, "ipc flag");
+    cudaMemcpyAsync(flag, &opened, sizeof(int), cudaMemcpyHostToDevice, st);
+    rc = nccl_check(ncclAllReduce(flag, flag, 1, ncclInt, ncclMin, comm, st), "ncclAllReduce(ipc)");
+    int agreed = 0;
+    if (!rc) rc = cuda_check(cudaMemcpyAsync(&agreed, flag, sizeof(int), cudaMemcpyDeviceToHost, st), "ipc flag");
+    if (!rc) rc = cuda_check(cudaStreamSynchronize(st), "ipc flag");
+    cudaFree(flag);
+    if (rc) return rc;
+    if (agreed) registry.emplace_back(base, tab);
+    else {
+        for (int q = 0; q < P; q++) if (q != rank && tab.p[q]) cudaIpcCloseMemHandle(tab.p[q]);
+        p2p_enabled = false;            // no peer mapping in this environment: stay on the NCCL path
+        registry.clear();
+    }
+    return 0;
+#else
+    (void)base;
+    return 0;
+#endif
+}
 
 int Trp::ensure(size_t doubles) {
     if (cap >= doubles) return 0;
@@ -100,6 +243,14 @@ int Trp::forward(const double* a, const double* a2, double scale, double* b, lon
     if (nxy % P) return fail(TLAB_ERR_PARPARTITION, "transpose: number of lines is not a multiple of the number of ranks");
     const long long nl = nxy / P;
     const size_t total = (size_t)nxy * nzl;
+    if (const PeerTab* tab = (P > 1 && p2p_enabled) ? find(b) : nullptr) {
+        ProfScope ps(PC_TRANSPOSE);
+        push_forward_kernel<<<p2p_grid(nl, nzl, P), 256, 0, ctx().stream>>>(a, a2, scale, *tab, nxy, nzl, nl, rank);
+        launches++;
+        p2p_exchanges++;
+        return barrier();               // every pencil is complete when the consumers start
+    }
+    nccl_exchanges++;
     if (int rc = ensure(total)) return rc;
     ProfScope ps(PC_TRANSPOSE);
     pack_kernel<<<blocks_for((long long)total), 256, 0, ctx().stream>>>(a, a2, scale, sendbuf, nxy, nzl, nl, P);
@@ -111,6 +262,15 @@ int Trp::backward(const double* b, double* a, long long nxy, int nzl, int accumu
     if (nxy % P) return fail(TLAB_ERR_PARPARTITION, "transpose: number of lines is not a multiple of the number of ranks");
     const long long nl = nxy / P;
     const size_t total = (size_t)nxy * nzl;
+    if (const PeerTab* tab = (P > 1 && p2p_enabled) ? find(b) : nullptr) {
+        ProfScope ps(PC_TRANSPOSE);
+        if (int rc = barrier()) return rc;          // every rank has finished producing its pencil
+        pull_backward_kernel<<<p2p_grid(nl, nzl, P), 256, 0, ctx().stream>>>(*tab, a, nxy, nzl, nl, rank, accumulate);
+        launches++;
+        p2p_exchanges++;
+        return barrier();                            // the pencils may be overwritten again
+    }
+    nccl_exchanges++;
     if (int rc = ensure(total)) return rc;
     ProfScope ps(PC_TRANSPOSE);
     if (int rc = alltoall(b, sendbuf, (size_t)nl * nzl)) return rc;
@@ -160,6 +320,11 @@ int tlab_mpi_finalize(void) {
 #ifdef TLAB_HAVE_NCCL
     if (t.comm) { ncclCommDestroy(t.comm); t.comm = nullptr; }
 #endif
+    for (auto& e : t.registry)
+        for (int q = 0; q < 8; q++) if (q != t.rank && e.second.p[q]) cudaIpcCloseMemHandle(e.second.p[q]);
+    t.registry.clear();
+    if (t.barrier_buf) cudaFree(t.barrier_buf);
+    t.barrier_buf = nullptr;
     if (t.sendbuf) cudaFree(t.sendbuf);
     t.sendbuf = nullptr; t.cap = 0; t.P = 1; t.rank = 0;
     return 0;

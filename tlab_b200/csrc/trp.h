@@ -1,5 +1,7 @@
 #pragma once
 #include "context.h"
+#include <vector>
+#include <utility>
 #ifdef TLAB_HAVE_NCCL
 #include <nccl.h>
 #endif
@@ -12,6 +14,18 @@ struct Trp {
 #ifdef TLAB_HAVE_NCCL
     ncclComm_t comm = nullptr;
 #endif
+    // peer-memory path: pencil buffers registered through CUDA IPC; the transposes then are one kernel that gathers
+    // from the local slab and stores straight into every peer's pencil over NVLink (forward), or loads from every
+    // peer's pencil and scatters/accumulates into the local slab (backward), bracketed by stream-ordered barriers
+    struct PeerTab { double* p[8]; };
+    std::vector<std::pair<const double*, PeerTab>> registry;
+    int* barrier_buf = nullptr;
+    bool p2p_enabled = true;
+    long long p2p_exchanges = 0, nccl_exchanges = 0;
+    int register_buffer(double* base);                  // collective: every rank calls it in the same order
+    const PeerTab* find(const double* base) const;
+    void unregister_buffer(const double* base);          // local: close the peer mappings of one buffer
+    int barrier();
     double* sendbuf = nullptr;   // pack / unpack staging
     size_t cap = 0;
     long long launches = 0;
