@@ -262,7 +262,103 @@ struct Dns {
         return trp().backward(zr, out, nxy, nz, accumulate);
     }
 
+    // ---- split domain: the z operators (transposes over NVLink + pencil kernels) run on a second, high-priority stream
+    // while the x and y operators of the same fields run on the main one; a field's z contribution is pulled into hq
+    // after its x and y kernels (events), so the accumulations never race.
+    struct StreamSwap {
+        cudaStream_t saved;
+        explicit StreamSwap(cudaStream_t s) : saved(ctx().stream) { ctx().stream = s; }
+        ~StreamSwap() { ctx().stream = saved; }
+    };
+    cudaEvent_t ev_pool[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t event(int i) {
+        if (!ev_pool[i]) cudaEventCreateWithFlags(&ev_pool[i], cudaEventDisableTiming);
+        return ev_pool[i];
+    }
+
+    int rhs_overlapped(double dte) {
+        cudaStream_t s0 = ctx().stream, s1 = trp().zstream;
+        const int b0 = 0;
+        int rc = 0;
+        const long long nxy = (long long)nx * ny;
+        const int nl = (int)(nxy / P);
+        double *u = q[0], *v = q[1], *w = q[2];
+        const int nf = 3 + ns;
+        auto field = [&](int f) { return f < 3 ? q[f] : s[f - 3]; };
+        auto target = [&](int f) { return f < 3 ? hq[f] : hs[f - 3]; };
+        // -- Burgers
+        cudaEventRecord(event(0), s0);
+        cudaStreamWaitEvent(s1, event(0), 0);
+        { StreamSwap sw(s1); rc = trp().forward(w, nullptr, 0.0, zw, nxy, nz); }
+        for (int f = 0; f < nf && !rc; f++) {
+            const int is = f < 3 ? 0 : f - 2;
+            {
+                StreamSwap sw(s1);
+                const double* zsf = zw;
+                if (f != 2) { rc = trp().forward(field(f), nullptr, 0.0, zs, nxy, nz); zsf = zs; }
+                if (!rc) rc = run_burgers(3, is, nl, 1, nzg, 0, g[2], zsf, zw, zr, 0);
+            }
+            if (!rc) rc = run_burgers(1, is, nx, ny, nz, b0, g[0], field(f), u, target(f), +1);
+            if (!rc) rc = run_burgers(2, is, nx, ny, nz, b0, g[1], field(f), v, target(f), +1);
+            cudaEventRecord(event(1 + (f & 1)), s0);
+            {
+                StreamSwap sw(s1);
+                cudaStreamWaitEvent(s1, event(1 + (f & 1)), 0);
+                if (!rc) rc = trp().backward(zr, target(f), nxy, nz, +1);
+            }
+            launches += 3;
+        }
+        if (rc) return rc;
+        // -- pressure forcing: div(hq + q/dte); the z part needs every hq complete
+        cudaEventRecord(event(3), s1);
+        cudaStreamWaitEvent(s0, event(3), 0);
+        cudaEventRecord(event(0), s0);
+        cudaStreamWaitEvent(s1, event(0), 0);
+        const double dummy = 1.0 / dte;
+        {
+            StreamSwap sw(s1);
+            rc = trp().forward(hq[2], w, dummy, zs, nxy, nz);
+            if (!rc) rc = run_partial(3, TLAB_OPR_P1, nl, 1, nzg, 0, g[2], zs, zr, nullptr);
+        }
+        if (!rc) rc = run_partial(2, TLAB_OPR_P1, nx, ny, nz, b0, g[1], hq[1], tmp1, nullptr, v, dummy, 0);
+        if (!rc) rc = run_partial(1, TLAB_OPR_P1, nx, ny, nz, b0, g[0], hq[0], tmp1, nullptr, u, dummy, +1);
+        cudaEventRecord(event(1), s0);
+        {
+            StreamSwap sw(s1);
+            cudaStreamWaitEvent(s1, event(1), 0);
+            if (!rc) rc = trp().backward(zr, tmp1, nxy, nz, +1);
+        }
+        launches += 3;
+        cudaEventRecord(event(3), s1);
+        cudaStreamWaitEvent(s0, event(3), 0);
+        if (rc) return rc;
+        const long long np = (long long)nx * nz;
+        { ProfScope ps(PC_ELEMENTWISE);
+        get_planes_kernel<<<(unsigned)((np + 255) / 256), 256, 0, s0>>>(hq[1], hb, ht, nx, ny, nz); }
+        launches++;
+        if ((rc = poisson().solve(tmp1, c1, c2, hb, ht, tmp3))) return rc;
+        launches += 2;
+        // -- hq -= grad p
+        cudaEventRecord(event(0), s0);
+        cudaStreamWaitEvent(s1, event(0), 0);
+        {
+            StreamSwap sw(s1);
+            rc = trp().forward(tmp1, nullptr, 0.0, zs, nxy, nz);
+            if (!rc) rc = run_partial(3, TLAB_OPR_P1, nl, 1, nzg, 0, g[2], zs, zr, nullptr);
+            if (!rc) rc = trp().backward(zr, hq[2], nxy, nz, -1);
+        }
+        if (!rc) rc = run_partial(1, TLAB_OPR_P1, nx, ny, nz, b0, g[0], tmp1, hq[0], nullptr, nullptr, 0.0, -1);
+        { ProfScope ps(PC_ELEMENTWISE);
+        sub_kernel<<<ew_blocks(N), EW_THREADS, 0, s0>>>(hq[1], tmp3, N); }
+        launches += 3;
+        cudaEventRecord(event(3), s1);
+        cudaStreamWaitEvent(s0, event(3), 0);
+        if (rc) return rc;
+        return rhs_bcs();
+    }
+
     int rhs(double dte) {
+        if (P > 1 && nzg > 1 && trp().zstream && ctx().tune_overlap) return rhs_overlapped(dte);
         cudaStream_t st = ctx().stream;
         const int b0 = 0;   // bcs = 0: biased, non-zero (rhs_global_incompressible_1.f90:67)
         int rc = 0;
@@ -311,7 +407,14 @@ struct Dns {
         { ProfScope ps(PC_ELEMENTWISE);
         sub_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(hq[1], tmp3, N); }
         launches += 3;
-        // boundary conditions (:356-398)
+        return rhs_bcs();
+    }
+
+    // boundary conditions (:356-398)
+    int rhs_bcs() {
+        cudaStream_t st = ctx().stream;
+        const long long np = (long long)nx * nz;
+        int rc = 0;
         for (int f = 0; f < 3 + ns; f++) {
             double* h = (f < 3) ? hq[f] : hs[f - 3];
             const int tmin = (f < 3) ? prm.bcs_flow_jmin[f] : prm.bcs_scal_jmin[f - 3];

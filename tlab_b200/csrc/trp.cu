@@ -14,6 +14,7 @@
 #include "trp.h"
 #include <cstring>
 #include <vector>
+#include <algorithm>
 
 namespace tlab {
 
@@ -46,61 +47,104 @@ __global__ void unpack_kernel(const double* __restrict__ recvbuf, double* __rest
     }
 }
 
+// a (op)= b   /   c = a + scale*a2
+__global__ void accumulate_kernel(double* __restrict__ a, const double* __restrict__ b, long long n, int accumulate) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        a[i] = (accumulate > 0) ? a[i] + b[i] : a[i] - b[i];
+}
+__global__ void combine_kernel(double* __restrict__ c, const double* __restrict__ a, const double* __restrict__ a2, double scale,
+                               long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        c[i] = a[i] + a2[i] * scale;
+}
+
 // forward transpose by peer stores: b_p[(rank*nzl + k)*nl + i] = a[k*nxy + p*nl + i] (+ scale*a2)
 // grid = (chunks of a run, nzl, P); every run of nl doubles is contiguous on both sides
 __global__ void push_forward_kernel(const double* __restrict__ a, const double* __restrict__ a2, double scale, Trp::PeerTab dst,
-                                    long long nxy, int nzl, long long nl, int rank) {
-    const int p = blockIdx.z, k = blockIdx.y;
-    const double* __restrict__ src = a + (long long)k * nxy + (long long)p * nl;
-    const double* __restrict__ src2 = a2 ? a2 + (long long)k * nxy + (long long)p * nl : nullptr;
-    double* __restrict__ d = dst.p[p] + ((long long)rank * nzl + k) * nl;
-    if ((nl & 1) == 0 && ((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(d) | reinterpret_cast<size_t>(src2)) & 15) == 0) {
-        const long long n2 = nl >> 1;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
-            double2 v = __ldcs(reinterpret_cast<const double2*>(src) + i);
-            if (src2) { const double2 w = __ldcs(reinterpret_cast<const double2*>(src2) + i); v.x = v.x + w.x * scale; v.y = v.y + w.y * scale; }
-            reinterpret_cast<double2*>(d)[i] = v;
-        }
-    } else {
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (long long)gridDim.x * blockDim.x) {
-            double v = src[i];
-            if (src2) v = v + src2[i] * scale;
-            d[i] = v;
+                                    long long nxy, int nzl, long long nl, int rank, int P) {
+    // runs (k, p) of nl contiguous doubles are dealt to the CTAs round-robin, starting with the next peer so that the
+    // ranks do not all store into the same GPU at the same time
+    const int nruns = nzl * P;
+    for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
+        const int k = run / P, p = (run % P + rank + 1) % P;
+        const double* __restrict__ src = a + (long long)k * nxy + (long long)p * nl;
+        const double* __restrict__ src2 = a2 ? a2 + (long long)k * nxy + (long long)p * nl : nullptr;
+        double* __restrict__ d = dst.p[p] + ((long long)rank * nzl + k) * nl;
+        if ((nl & 1) == 0 && ((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(d) | reinterpret_cast<size_t>(src2)) & 15) == 0) {
+            const long long n2 = nl >> 1;
+            constexpr int U = 8;                   // independent 16-byte loads in flight per thread
+            long long i = threadIdx.x;
+            for (; i + (long long)(U - 1) * blockDim.x < n2; i += (long long)U * blockDim.x) {
+                double2 v[U];
+#pragma unroll
+                for (int k = 0; k < U; k++) v[k] = __ldcs(reinterpret_cast<const double2*>(src) + i + (long long)k * blockDim.x);
+                if (src2) {
+#pragma unroll
+                    for (int k = 0; k < U; k++) {
+                        const double2 w = __ldcs(reinterpret_cast<const double2*>(src2) + i + (long long)k * blockDim.x);
+                        v[k].x = v[k].x + w.x * scale; v[k].y = v[k].y + w.y * scale;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < U; k++) reinterpret_cast<double2*>(d)[i + (long long)k * blockDim.x] = v[k];
+            }
+            for (; i < n2; i += blockDim.x) {
+                double2 v = __ldcs(reinterpret_cast<const double2*>(src) + i);
+                if (src2) { const double2 w = __ldcs(reinterpret_cast<const double2*>(src2) + i); v.x = v.x + w.x * scale; v.y = v.y + w.y * scale; }
+                reinterpret_cast<double2*>(d)[i] = v;
+            }
+        } else {
+            for (long long i = threadIdx.x; i < nl; i += blockDim.x) {
+                double v = src[i];
+                if (src2) v = v + src2[i] * scale;
+                d[i] = v;
+            }
         }
     }
 }
 
 // backward transpose by peer loads: a[k*nxy + q*nl + i] (op)= b_q[(rank*nzl + k)*nl + i]
 __global__ void pull_backward_kernel(Trp::PeerTab srcs, double* __restrict__ a, long long nxy, int nzl, long long nl, int rank,
-                                     int accumulate) {
-    const int q = blockIdx.z, k = blockIdx.y;
-    const double* __restrict__ src = srcs.p[q] + ((long long)rank * nzl + k) * nl;
-    double* __restrict__ d = a + (long long)k * nxy + (long long)q * nl;
-    if ((nl & 1) == 0 && ((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(d)) & 15) == 0) {
-        const long long n2 = nl >> 1;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) {
-            double2 v = reinterpret_cast<const double2*>(src)[i];
-            if (accumulate != 0) {
-                const double2 o = reinterpret_cast<const double2*>(d)[i];
-                if (accumulate > 0) { v.x = o.x + v.x; v.y = o.y + v.y; } else { v.x = o.x - v.x; v.y = o.y - v.y; }
+                                     int P, int accumulate) {
+    const int nruns = nzl * P;
+    for (int run = blockIdx.x; run < nruns; run += gridDim.x) {
+        const int k = run / P, q = (run % P + rank + 1) % P;
+        const double* __restrict__ src = srcs.p[q] + ((long long)rank * nzl + k) * nl;
+        double* __restrict__ d = a + (long long)k * nxy + (long long)q * nl;
+        if ((nl & 1) == 0 && ((reinterpret_cast<size_t>(src) | reinterpret_cast<size_t>(d)) & 15) == 0) {
+            const long long n2 = nl >> 1;
+            constexpr int U = 8;
+            long long i = threadIdx.x;
+            for (; i + (long long)(U - 1) * blockDim.x < n2; i += (long long)U * blockDim.x) {
+                double2 v[U];
+#pragma unroll
+                for (int k = 0; k < U; k++) v[k] = reinterpret_cast<const double2*>(src)[i + (long long)k * blockDim.x];
+                if (accumulate != 0) {
+#pragma unroll
+                    for (int k = 0; k < U; k++) {
+                        const double2 o = reinterpret_cast<const double2*>(d)[i + (long long)k * blockDim.x];
+                        if (accumulate > 0) { v[k].x = o.x + v[k].x; v[k].y = o.y + v[k].y; } else { v[k].x = o.x - v[k].x; v[k].y = o.y - v[k].y; }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < U; k++) reinterpret_cast<double2*>(d)[i + (long long)k * blockDim.x] = v[k];
             }
-            reinterpret_cast<double2*>(d)[i] = v;
-        }
-    } else {
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nl; i += (long long)gridDim.x * blockDim.x) {
-            double v = src[i];
-            if (accumulate > 0) v = d[i] + v; else if (accumulate < 0) v = d[i] - v;
-            d[i] = v;
+            for (; i < n2; i += blockDim.x) {
+                double2 v = reinterpret_cast<const double2*>(src)[i];
+                if (accumulate != 0) {
+                    const double2 o = reinterpret_cast<const double2*>(d)[i];
+                    if (accumulate > 0) { v.x = o.x + v.x; v.y = o.y + v.y; } else { v.x = o.x - v.x; v.y = o.y - v.y; }
+                }
+                reinterpret_cast<double2*>(d)[i] = v;
+            }
+        } else {
+            for (long long i = threadIdx.x; i < nl; i += blockDim.x) {
+                double v = src[i];
+                if (accumulate > 0) v = d[i] + v; else if (accumulate < 0) v = d[i] - v;
+                d[i] = v;
+            }
         }
     }
-}
-
-inline dim3 p2p_grid(long long nl, int nzl, int P) {
-    long long per = (nl / 2 + 255) / 256;
-    const long long want = (148LL * 16 + (long long)nzl * P - 1) / ((long long)nzl * P);   // ~16 CTAs per SM in total
-    if (per > want) per = want;
-    if (per < 1) per = 1;
-    return dim3((unsigned)per, (unsigned)nzl, (unsigned)P);
 }
 
 inline unsigned blocks_for(long long n) {
@@ -143,7 +187,7 @@ int Trp::barrier() {
         if (cudaMalloc(&barrier_buf, 64) != cudaSuccess) return fail(TLAB_ERR_ALLOC, "barrier buffer");
         cudaMemsetAsync(barrier_buf, 0, 64, ctx().stream);
     }
-    return nccl_check(ncclAllReduce(barrier_buf, barrier_buf, 1, ncclInt, ncclSum, comm, ctx().stream), "barrier");
+    return nccl_check(ncclAllReduce(barrier_buf, barrier_buf, 1, ncclInt, ncclMax, comm, ctx().stream), "barrier");
 #else
     return 0;
 #endif
@@ -243,9 +287,30 @@ int Trp::forward(const double* a, const double* a2, double scale, double* b, lon
     if (nxy % P) return fail(TLAB_ERR_PARPARTITION, "transpose: number of lines is not a multiple of the number of ranks");
     const long long nl = nxy / P;
     const size_t total = (size_t)nxy * nzl;
-    if (const PeerTab* tab = (P > 1 && p2p_enabled) ? find(b) : nullptr) {
+    const PeerTab* tabf = (P > 1 && p2p_enabled) ? find(b) : nullptr;
+    if (tabf && p2p_dma) {
+        // copy engines: one strided 2-D copy per peer, no SM involved (overlaps with the x/y kernels of the other stream)
         ProfScope ps(PC_TRANSPOSE);
-        push_forward_kernel<<<p2p_grid(nl, nzl, P), 256, 0, ctx().stream>>>(a, a2, scale, *tab, nxy, nzl, nl, rank);
+        cudaStream_t st = ctx().stream;
+        const double* src = a;
+        if (a2 != nullptr) {
+            if (int rc = ensure(total)) return rc;
+            combine_kernel<<<blocks_for((long long)total), 256, 0, st>>>(sendbuf, a, a2, scale, (long long)total);
+            launches++;
+            src = sendbuf;
+        }
+        for (int d = 1; d <= P; d++) {
+            const int q = (rank + d) % P;
+            if (int rc = cuda_check(cudaMemcpy2DAsync(tabf->p[q] + (long long)rank * nzl * nl, (size_t)nl * sizeof(double), src + (long long)q * nl,
+                                                      (size_t)nxy * sizeof(double), (size_t)nl * sizeof(double), (size_t)nzl,
+                                                      cudaMemcpyDefault, st), "peer copy (forward)")) return rc;
+        }
+        p2p_exchanges++;
+        return barrier();
+    }
+    if (const PeerTab* tab = tabf) {
+        ProfScope ps(PC_TRANSPOSE);
+        push_forward_kernel<<<(unsigned)std::min<long long>(p2p_ctas, (long long)nzl * P), 512, 0, ctx().stream>>>(a, a2, scale, *tab, nxy, nzl, nl, rank, P);
         launches++;
         p2p_exchanges++;
         return barrier();               // every pencil is complete when the consumers start
@@ -262,10 +327,31 @@ int Trp::backward(const double* b, double* a, long long nxy, int nzl, int accumu
     if (nxy % P) return fail(TLAB_ERR_PARPARTITION, "transpose: number of lines is not a multiple of the number of ranks");
     const long long nl = nxy / P;
     const size_t total = (size_t)nxy * nzl;
-    if (const PeerTab* tab = (P > 1 && p2p_enabled) ? find(b) : nullptr) {
+    const PeerTab* tabb = (P > 1 && p2p_enabled) ? find(b) : nullptr;
+    if (tabb && p2p_dma) {
+        ProfScope ps(PC_TRANSPOSE);
+        cudaStream_t st = ctx().stream;
+        if (accumulate != 0) { if (int rc = ensure(total)) return rc; }
+        if (int rc = barrier()) return rc;          // every rank has finished producing its pencil
+        double* dst = (accumulate != 0) ? sendbuf : a;
+        for (int d = 1; d <= P; d++) {
+            const int q = (rank + d) % P;
+            if (int rc = cuda_check(cudaMemcpy2DAsync(dst + (long long)q * nl, (size_t)nxy * sizeof(double), tabb->p[q] + (long long)rank * nzl * nl,
+                                                      (size_t)nl * sizeof(double), (size_t)nl * sizeof(double), (size_t)nzl,
+                                                      cudaMemcpyDefault, st), "peer copy (backward)")) return rc;
+        }
+        if (int rc = barrier()) return rc;          // the pencils may be overwritten again
+        if (accumulate != 0) {
+            accumulate_kernel<<<blocks_for((long long)total), 256, 0, st>>>(a, sendbuf, (long long)total, accumulate);
+            launches++;
+        }
+        p2p_exchanges++;
+        return cuda_check(cudaGetLastError(), "accumulate");
+    }
+    if (const PeerTab* tab = tabb) {
         ProfScope ps(PC_TRANSPOSE);
         if (int rc = barrier()) return rc;          // every rank has finished producing its pencil
-        pull_backward_kernel<<<p2p_grid(nl, nzl, P), 256, 0, ctx().stream>>>(*tab, a, nxy, nzl, nl, rank, accumulate);
+        pull_backward_kernel<<<(unsigned)std::min<long long>(p2p_ctas, (long long)nzl * P), 512, 0, ctx().stream>>>(*tab, a, nxy, nzl, nl, rank, P, accumulate);
         launches++;
         p2p_exchanges++;
         return barrier();                            // the pencils may be overwritten again
@@ -309,6 +395,11 @@ int tlab_mpi_init(int rank, int nranks, const void* id_128) {
     if (!id_128) return fail(TLAB_ERR_OPTION, "null unique id");
     ncclUniqueId id;
     std::memcpy(&id, id_128, 128);
+    if (!t.zstream) {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        if (cudaStreamCreateWithPriority(&t.zstream, cudaStreamNonBlocking, hi) != cudaSuccess) { cudaGetLastError(); t.zstream = nullptr; }
+    }
     return nccl_check(ncclCommInitRank(&t.comm, nranks, id, rank), "ncclCommInitRank");
 #else
     return fail(TLAB_ERR_UNDEVELOP, "library built without NCCL");
@@ -323,6 +414,7 @@ int tlab_mpi_finalize(void) {
     for (auto& e : t.registry)
         for (int q = 0; q < 8; q++) if (q != t.rank && e.second.p[q]) cudaIpcCloseMemHandle(e.second.p[q]);
     t.registry.clear();
+    if (t.zstream) { cudaStreamSynchronize(t.zstream); cudaStreamDestroy(t.zstream); t.zstream = nullptr; }
     if (t.barrier_buf) cudaFree(t.barrier_buf);
     t.barrier_buf = nullptr;
     if (t.sendbuf) cudaFree(t.sendbuf);

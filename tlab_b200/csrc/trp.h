@@ -20,7 +20,10 @@ struct Trp {
     struct PeerTab { double* p[8]; };
     std::vector<std::pair<const double*, PeerTab>> registry;
     int* barrier_buf = nullptr;
+    cudaStream_t zstream = nullptr;    // high-priority stream of the z operators of a split domain (overlap with x/y work)
     bool p2p_enabled = true;
+    bool p2p_dma = false;               // peer copies by the copy engines (cudaMemcpy2DAsync) instead of ld/st kernels
+    int p2p_ctas = 148;                 // CTAs of the peer-memory kernels: enough to fill NVLink, few enough to leave SMs to overlapped work
     long long p2p_exchanges = 0, nccl_exchanges = 0;
     int register_buffer(double* base);                  // collective: every rank calls it in the same order
     const PeerTab* find(const double* base) const;
