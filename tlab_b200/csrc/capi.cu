@@ -373,6 +373,7 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "persist")) ctx().tune_persist = value;
     else if (!std::strcmp(key, "fuse")) ctx().tune_fuse = value;
     else if (!std::strcmp(key, "overlap")) ctx().tune_overlap = value;
+    else if (!std::strcmp(key, "kxsplit")) ctx().tune_kxsplit = value;
     else if (!std::strcmp(key, "p2p")) trp().p2p_enabled = (value != 0);
     else if (!std::strcmp(key, "p2p_ctas")) trp().p2p_ctas = value > 0 ? value : 148;
     else if (!std::strcmp(key, "p2p_dma")) trp().p2p_dma = (value != 0);

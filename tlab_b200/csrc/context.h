@@ -28,6 +28,7 @@ struct Context {
     int tune_poisson_minb = 3;  // resident CTAs per SM the Poisson y kernel is compiled for (register budget)
     int tune_pf_next = 0;     // fused Burgers launch: L2 prefetch of the tile's next field
     int tune_fuse = 0;        // RHS: one fused Burgers launch per direction (fields sharing the advecting velocity)
+    int tune_kxsplit = 1;     // split domain + peer memory: kx-split spectral stage of the Poisson solver
     int tune_overlap = 1;     // split domain: z operators on a second stream, overlapped with the x/y operators
     int tune_persist = 0;     // strided fast kernels: persistent CTAs with asynchronous staging
     long long fast_launches = 0, general_launches = 0;    // L2 prefetch distance of the fast kernels in tiles (-1: automatic, 0: off)

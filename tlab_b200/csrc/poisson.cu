@@ -20,6 +20,7 @@
 #include <cufft.h>
 #include <cmath>
 #include <vector>
+#include <algorithm>
 
 #ifndef POISSON_MIN_BLOCKS
 #define POISSON_MIN_BLOCKS 4
@@ -506,6 +507,60 @@ __global__ void poisson_set_bcs_kernel(double* __restrict__ p, const double* __r
     p[i + (long long)nx * ((ny - 1) + (long long)ny * k)] = ht[idx];
 }
 
+// ---- kx-split exchanges over peer memory (complex numbers as double2) ---------------------------------------
+// slab c(kx, y, zl) of this rank  ->  pencil_p(kx - kx0[p], y, rank*nzl + zl) of every rank p   (stores into the peers)
+struct KxTab { double2* p[8]; int kx0[9]; };
+
+constexpr int KXR = 4;          // rows in flight per CTA pass (independent loads first, then the stores)
+
+__global__ void kx_push_kernel(const double2* __restrict__ c, KxTab t, int nxh, int ny, int nzl, int rank, int P, double scale) {
+    const int rows = ny * nzl;
+    for (int row0 = blockIdx.x * KXR; row0 < rows; row0 += gridDim.x * KXR) {
+        for (int j = threadIdx.x; j < nxh; j += blockDim.x) {
+            int p = 0;
+#pragma unroll
+            for (int q = 1; q < 8; q++) if (q < P && j >= t.kx0[q]) p = q;
+            const int kxl = t.kx0[p + 1] - t.kx0[p];
+            double2 v[KXR];
+#pragma unroll
+            for (int r = 0; r < KXR; r++) if (row0 + r < rows) v[r] = __ldcs(c + (size_t)nxh * (row0 + r) + j);
+#pragma unroll
+            for (int r = 0; r < KXR; r++) {
+                const int row = row0 + r;
+                if (row < rows) {
+                    const int y = row % ny, zl = row / ny;
+                    const size_t prow = (size_t)y + (size_t)ny * ((size_t)rank * nzl + zl);
+                    t.p[p][(size_t)(j - t.kx0[p]) + (size_t)kxl * prow] = v[r];
+                }
+            }
+        }
+    }
+}
+// pencil_p(kx - kx0[p], y, rank*nzl + zl) of every rank p  ->  slab c(kx, y, zl) of this rank   (loads from the peers)
+__global__ void kx_pull_kernel(double2* __restrict__ c, KxTab t, int nxh, int ny, int nzl, int rank, int P) {
+    const int rows = ny * nzl;
+    for (int row0 = blockIdx.x * KXR; row0 < rows; row0 += gridDim.x * KXR) {
+        for (int j = threadIdx.x; j < nxh; j += blockDim.x) {
+            int p = 0;
+#pragma unroll
+            for (int q = 1; q < 8; q++) if (q < P && j >= t.kx0[q]) p = q;
+            const int kxl = t.kx0[p + 1] - t.kx0[p];
+            double2 v[KXR];
+#pragma unroll
+            for (int r = 0; r < KXR; r++) {
+                const int row = row0 + r;
+                if (row < rows) {
+                    const int y = row % ny, zl = row / ny;
+                    const size_t prow = (size_t)y + (size_t)ny * ((size_t)rank * nzl + zl);
+                    v[r] = t.p[p][(size_t)(j - t.kx0[p]) + (size_t)kxl * prow];
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < KXR; r++) if (row0 + r < rows) c[(size_t)nxh * (row0 + r) + j] = v[r];
+        }
+    }
+}
+
 const double* up(std::vector<void*>& allocs, const double* h, size_t count) {
     double* d = nullptr;
     if (cudaMalloc(&d, std::max<size_t>(count, 1) * sizeof(double)) != cudaSuccess) return nullptr;
@@ -547,6 +602,10 @@ void Poisson::release() {
     plan_fx = plan_bx = plan_z = 0;
     if (c3) trp().unregister_buffer(c3);
     c3 = nullptr;
+    if (cpa) trp().unregister_buffer(cpa);
+    if (cpb) trp().unregister_buffer(cpb);
+    cpa = cpb = nullptr;
+    kxsplit = false;
     for (void* a : allocs) cudaFree(a);
     allocs.clear();
     ready = false;
@@ -565,20 +624,43 @@ int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz, int nz_loca
     const int koff = trp().rank * nz;                                        // ims_offset_k
     if (nx % 2) return fail(TLAB_ERR_DIMGRID, "OPR_Poisson needs an even number of points in x");
     nxh = nx / 2 + 1;
-    if (P > 1 && ((long long)nxh * ny) % P) return fail(TLAB_ERR_PARPARTITION, "OPR_Poisson: (nx/2+1)*ny is not a multiple of the number of ranks");
-    D.nxh = nxh; D.ny = ny; D.nz = nz; D.nmodes = (long long)nxh * nz;
+    // split domain: try the kx-split spectral stage (needs peer-mapped pencils), else the reference's y-line split
+    kxsplit = false;
+    const int rank = trp().rank;
+    if (P > 1 && nzg > 1 && P <= 8 && trp().p2p_enabled && ctx().tune_kxsplit && nxh >= P) {
+        for (int p = 0; p <= P; p++) kx0[p] = (int)(((long long)p * nxh) / P);
+        int kxl_max = 0;
+        for (int p = 0; p < P; p++) kxl_max = std::max(kxl_max, kx0[p + 1] - kx0[p]);
+        const size_t pen = (size_t)2 * kxl_max * ny * nzg;
+        double *a = nullptr, *b = nullptr;
+        if (cudaMalloc(&a, pen * sizeof(double)) != cudaSuccess || cudaMalloc(&b, pen * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(TLAB_ERR_ALLOC, "OPR_Elliptic_Initialize: out of device memory (kx pencils)");
+        }
+        allocs.push_back(a); allocs.push_back(b);
+        cpa = a; cpb = b;
+        if (int rc = trp().register_buffer(cpa)) return rc;
+        if (int rc = trp().register_buffer(cpb)) return rc;
+        kxsplit = trp().find(cpa) != nullptr && trp().find(cpb) != nullptr;
+    }
+    if (P > 1 && !kxsplit && ((long long)nxh * ny) % P) return fail(TLAB_ERR_PARPARTITION, "OPR_Poisson: (nx/2+1)*ny is not a multiple of the number of ranks");
+    const int kxo = kxsplit ? kx0[rank] : 0;                    // first wavenumber / modes in x / planes in z of the y solves
+    const int mxh = kxsplit ? kx0[rank + 1] - kx0[rank] : nxh;
+    const int mz_n = kxsplit ? nzg : nz;
+    const int mko = kxsplit ? 0 : koff;
+    D.nxh = mxh; D.ny = ny; D.nz = mz_n; D.nmodes = (long long)mxh * mz_n;
     D.norm = 1.0 / double((long long)nx * nzg);                              // opr_elliptic.f90:130
-    D.i_sing0 = 0; D.i_sing1 = nx / 2;                                       // opr_elliptic.f90:148-149 (0-based)
-    D.k_sing0 = 0 - koff; D.k_sing1 = nzg / 2 - koff;                        // task-local indices (:177-178)
+    D.i_sing0 = 0 - kxo; D.i_sing1 = nx / 2 - kxo;                           // opr_elliptic.f90:148-149 (0-based, local)
+    D.k_sing0 = 0 - mko; D.k_sing1 = nzg / 2 - mko;                          // task-local indices (:177-178)
     // lambda(k,i) = mwn_x(i)^2 + mwn_z(k)^2 from the first-derivative modified wavenumbers (:199-203)
     std::vector<double> lam((size_t)D.nmodes);
     const std::vector<double>& mx = gx->p.h.der1.mwn;
     const std::vector<double>& mz = gz->p.h.der1.mwn;
-    for (int k = 0; k < nz; k++)
-        for (int i = 0; i < nxh; i++) {
-            double l = mx[i] * mx[i];
-            if (nzg > 1) l = l + mz[koff + k] * mz[koff + k];
-            lam[(size_t)i + (size_t)nxh * k] = l;
+    for (int k = 0; k < mz_n; k++)
+        for (int i = 0; i < mxh; i++) {
+            double l = mx[kxo + i] * mx[kxo + i];
+            if (nzg > 1) l = l + mz[mko + k] * mz[mko + k];
+            lam[(size_t)i + (size_t)mxh * k] = l;
         }
     D.lambda = up(allocs, lam.data(), lam.size());
     if (int rc = make_side(gy->p.h.der1, BCS_MIN, D.smin, allocs)) return fail(rc, "integral operator (BCS_MIN) setup failed");
@@ -605,11 +687,11 @@ int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz, int nz_loca
     if (nzg > 1) {
         // slab layout (P = 1) or z-pencil layout after the K-transpose (P > 1): lines interleaved, stride = howmany
         int n3[1] = {nzg};
-        const int howmany = (int)(((long long)nxh * ny) / P);
+        const int howmany = kxsplit ? (kx0[rank + 1] - kx0[rank]) * ny : (int)(((long long)nxh * ny) / P);
         if (int rc = cufft_check(cufftPlanMany(&plan_z, 1, n3, n3, howmany, 1, n3, howmany, 1, CUFFT_Z2Z, howmany), "cufftPlanMany Z2Z")) return rc;
         cufftSetStream(plan_z, st);
     }
-    if (P > 1) {
+    if (P > 1 && !kxsplit) {
         double* c3buf = nullptr;
         if (cudaMalloc(&c3buf, (size_t)2 * nxh * ny * nz * sizeof(double)) != cudaSuccess) {
             cudaGetLastError();
@@ -651,6 +733,52 @@ int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const do
         const long long np = (long long)nx * nz;
         poisson_set_bcs_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(p, hb, ht, nx, ny, nz);
         if (int rc = cufft_check(cufftExecD2Z(plan_fx, p, (cufftDoubleComplex*)c1), "cufftExecD2Z")) return rc;
+    }
+    if (kxsplit) {
+        Trp& T = trp();
+        KxTab ta, tb;
+        const Trp::PeerTab* pa = T.find(cpa);
+        const Trp::PeerTab* pb = T.find(cpb);
+        for (int q = 0; q < 8; q++) { ta.p[q] = (double2*)pa->p[q]; tb.p[q] = (double2*)pb->p[q]; }
+        for (int q = 0; q < 9; q++) { ta.kx0[q] = kx0[q]; tb.kx0[q] = kx0[q]; }
+        const unsigned ctas = (unsigned)std::min<long long>(((long long)ny * nz + KXR - 1) / KXR, T.p2p_ctas * 4);
+        {
+            ProfScope ps(PC_TRANSPOSE);
+            kx_push_kernel<<<ctas, 256, 0, st>>>((const double2*)c1, ta, nxh, ny, nz, T.rank, P, 1.0);
+            T.launches++; T.p2p_exchanges++;
+            if (int rc = T.barrier()) return rc;
+        }
+        {
+            ProfScope ps(PC_FFT);
+            if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)cpa, (cufftDoubleComplex*)cpa, CUFFT_FORWARD), "cufftExecZ2Z")) return rc;
+        }
+        {
+            ProfScope ps(PC_POISSON_Y);
+            const int threads = 128;
+            const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
+            const int minb = ctx().tune_poisson_minb;
+            if (minb == 4) poisson_modes_kernel<4><<<blocks, threads, 0, st>>>(D, cpa, cpb);
+            else if (minb == 2) poisson_modes_kernel<2><<<blocks, threads, 0, st>>>(D, cpa, cpb);
+            else poisson_modes_kernel<3><<<blocks, threads, 0, st>>>(D, cpa, cpb);
+            if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
+        }
+        {
+            ProfScope ps(PC_FFT);
+            if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)cpa, (cufftDoubleComplex*)cpa, CUFFT_INVERSE), "cufftExecZ2Z")) return rc;
+            if (dpdy) { if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)cpb, (cufftDoubleComplex*)cpb, CUFFT_INVERSE), "cufftExecZ2Z")) return rc; }
+        }
+        {
+            ProfScope ps(PC_TRANSPOSE);
+            if (int rc = T.barrier()) return rc;
+            kx_pull_kernel<<<ctas, 256, 0, st>>>((double2*)c1, ta, nxh, ny, nz, T.rank, P);
+            if (dpdy) kx_pull_kernel<<<ctas, 256, 0, st>>>((double2*)c2, tb, nxh, ny, nz, T.rank, P);
+            T.launches += dpdy ? 2 : 1; T.p2p_exchanges += dpdy ? 2 : 1;
+            if (int rc = T.barrier()) return rc;
+        }
+        ProfScope ps(PC_FFT);
+        if (int rc = cufft_check(cufftExecZ2D(plan_bx, (cufftDoubleComplex*)c1, p), "cufftExecZ2D")) return rc;
+        if (dpdy) { if (int rc = cufft_check(cufftExecZ2D(plan_bx, (cufftDoubleComplex*)c2, dpdy), "cufftExecZ2D")) return rc; }
+        return 0;
     }
     if (int rc = fft_z(c1, P > 1 ? c2 : nullptr, CUFFT_FORWARD)) return rc;
     {

@@ -32,7 +32,12 @@ struct Poisson {
     bool ready = false;
     int nx = 0, ny = 0, nz = 0, nxh = 0;   // nz: local slab thickness
     int nzg = 0, P = 1;                     // global extent in z, ranks in z
-    double* c3 = nullptr;                   // pencil work array (P > 1)
+    double* c3 = nullptr;                   // pencil work array (P > 1, NCCL path)
+    // kx-split spectral stage (P > 1, peer memory): rank p owns the wavenumbers kx0[p] .. kx0[p+1]-1 for all y and z, so
+    // that the z transform AND the y solves run in the pencil layout: 3 complex exchanges per call instead of 6
+    bool kxsplit = false;
+    double *cpa = nullptr, *cpb = nullptr;  // complex pencils (kxl, ny, nzg)
+    int kx0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     PoissonDev D;
     cufftHandle plan_fx = 0, plan_bx = 0, plan_z = 0;
     std::vector<void*> allocs;
