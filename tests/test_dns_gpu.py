@@ -150,3 +150,25 @@ def test_case01_shape_two_dimensional_step(cuda):
         assert rel_l2(g.get("q%d" % (i + 1)), o.q[i]) <= 1e-11
     assert np.abs(g.get("q3")).max() == 0.0
     assert rel_l2(g.get("s1"), o.s[0]) <= 1e-11
+
+
+@pytest.mark.parametrize("tune", [{"fuse": 1}, {"fuse": 1, "pf_next": 1}, {"persist": 1}, {"pf_dist": 3}, {"fast": 0}])
+def test_tuning_variants_give_the_same_step(cuda, tune):
+    """The optional kernel variants (fused multi-field Burgers launch, next-field / next-tile L2 prefetch, persistent
+    cp.async staging, general kernels) are alternative schedules of the same arithmetic: one RK step on full chunks
+    (64 x 64 x 32) must agree with the oracle like the default path does."""
+    from tlab_b200 import lib as tl
+    L = tl.load()
+    defaults = {"fuse": 0, "pf_next": 0, "persist": 0, "pf_dist": -1, "fast": 1}
+    try:
+        for k, v in tune.items():
+            tl.check(L.tlab_gpu_set_tuning(k.encode(), v))
+        o, g = _pair(64, 64, 32, "tanh")
+        o.runge_kutta(1e-3)
+        g.runge_kutta(1e-3)
+        for i in range(3):
+            assert rel_l2(g.get("q%d" % (i + 1)), o.q[i]) <= 1e-11
+        assert rel_l2(g.get("s1"), o.s[0]) <= 1e-11
+    finally:
+        for k, v in defaults.items():
+            tl.check(L.tlab_gpu_set_tuning(k.encode(), v))

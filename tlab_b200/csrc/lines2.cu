@@ -337,8 +337,8 @@ __device__ __forceinline__ void strided_field(const Line2Args& a, const ChunkCtx
     const bool has_u2 = (a.u2 != nullptr);
     const bool has_acc = (a.accumulate != 0) && (MODE == MODE_BURGERS || MODE == MODE_P1);
 
-    // ---- L2 prefetch of a later tile (one row segment per request)
-    if (a.pf_dist > 0) {
+    // ---- L2 prefetch of a later tile (one row segment per request); not for the Neumann kernel, which reads a few rows only
+    if (a.pf_dist > 0 && MODE != MODE_NEUMANN) {
         const unsigned tile = blockIdx.y * gridDim.x + blockIdx.x + (unsigned)a.pf_dist;
         if (tile < gridDim.x * gridDim.y) {
             const unsigned ty = tile / gridDim.x, tx = tile - ty * gridDim.x;
