@@ -379,6 +379,7 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "p2p_dma")) trp().p2p_dma = (value != 0);
     else if (!std::strcmp(key, "pf_next")) ctx().tune_pf_next = value;
     else if (!std::strcmp(key, "poisson_minb")) ctx().tune_poisson_minb = value;
+    else if (!std::strcmp(key, "poisson_factors")) ctx().tune_poisson_factors = value;
     else return fail(TLAB_ERR_OPTION, std::string("unknown tuning key ") + key);
     return 0;
 }

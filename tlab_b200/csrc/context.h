@@ -25,6 +25,7 @@ struct Context {
     int tune_lines_x = 0, tune_lines_yz = 0;
     int tune_fast = 1;        // 1: use the fast line kernels (lines2.cu) whenever the geometry allows
     int tune_pf_dist = -1;
+    int tune_poisson_factors = 1;  // keep the per-mode LU factors of the Poisson y systems (8 more planes) instead of refactorising
     int tune_poisson_minb = 3;  // resident CTAs per SM the Poisson y kernel is compiled for (register budget)
     int tune_pf_next = 0;     // fused Burgers launch: L2 prefetch of the tile's next field
     int tune_fuse = 0;        // RHS: one fused Burgers launch per direction (fields sharing the advecting velocity)

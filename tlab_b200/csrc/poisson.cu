@@ -44,10 +44,15 @@ struct LineRef {
 //   bc     value imposed at the near end;   res: result lines (rows 1..n written)
 //   ysc, csc, dsc, esc: per-mode scratch lines (intermediate vector and the three upper factors)
 //   du     (optional) derivative at the far end, FDM_Int1_Solve's du_boundary
-template <int NL>
+//   FMODE  0: LU factors computed on the fly, upper factors through the scratch lines csc, dsc
+//          1: the same, and the four factor lines (fa, fb lower; csc, dsc upper) are kept for later calls
+//          2: factor lines read instead of recomputed (they depend on lambda only: no divisions, no table rows and a
+//             shorter dependent chain per row)
+template <int NL, int FMODE = 0>
 __device__ void int1_solve(const Int1Dev& P, double lam, const LineRef (&f)[NL], double fscale,
                            const double (&fend)[NL], const double (&bc)[NL], const LineRef (&res)[NL],
-                           const LineRef (&ysc)[NL], LineRef csc, LineRef dsc, LineRef esc, double* du) {
+                           const LineRef (&ysc)[NL], LineRef csc, LineRef dsc, LineRef esc, double* du,
+                           LineRef fa = LineRef{nullptr, 0}, LineRef fb = LineRef{nullptr, 0}) {
     const int n = P.n;
     const bool is_min = (P.bc == BCS_MIN);
     auto Lrow = [&](int r, double (&row)[6]) {
@@ -125,43 +130,55 @@ __device__ void int1_solve(const Int1Dev& P, double lam, const LineRef (&f)[NL],
     constexpr int FRB = 8;
     for (int m0 = 1; m0 <= nmax; m0 += FRB) {
         double fblk[NL][FRB];
+        double ablk[FMODE == 2 ? FRB : 1], bblk[FMODE == 2 ? FRB : 1];
 #pragma unroll
         for (int j = 0; j < FRB; j++) {
             const int rr = m0 + j + 3;              // row r + 2 of step m = m0 + j
 #pragma unroll
             for (int l = 0; l < NL; l++) fblk[l][j] = (rr <= n - 1) ? F(l, rr) : 0.0;
+            if (FMODE == 2) {
+                const bool ok = (m0 + j <= nmax);
+                ablk[j] = ok ? fa.get(m0 + j + 1) : 0.0;
+                bblk[j] = ok ? fb.get(m0 + j + 1) : 0.0;
+            }
         }
 #pragma unroll
         for (int j = 0; j < FRB; j++) {
             const int m = m0 + j;
             if (m > nmax) break;
             const int r = m + 1;
-            double row[6];
-            if (is_min && r == n - 1) {
-#pragma unroll
-                for (int k = 1; k <= 5; k++) row[k] = La[k];
-            } else if (is_min && r == n - 2) {
-#pragma unroll
-                for (int k = 1; k <= 5; k++) row[k] = Lb[k];
-            } else if (!is_min && r == 2) {
-#pragma unroll
-                for (int k = 1; k <= 5; k++) row[k] = La[k];
-            } else if (!is_min && r == 3) {
-#pragma unroll
-                for (int k = 1; k <= 5; k++) row[k] = Lb[k];
+            double a = 0.0, b = 0.0, c = 1.0, d = 0.0, e = 0.0;
+            if (FMODE == 2) {
+                a = ablk[j]; b = bblk[j];
             } else {
-                Lrow(r, row);
-            }
-            double a = row[1], b = row[2], c = row[3], d = row[4], e = row[5];
-            if (m == 2) {
-                b = b / c1;
-                c = c - b * d1;
-                d = d - b * e1;
-            } else if (m >= 3) {
-                a = a / c2;
-                b = (b - a * d2) / c1;
-                c = c - b * d1 - a * e2;
-                if (m < nmax) d = d - b * e1;
+                double row[6];
+                if (is_min && r == n - 1) {
+#pragma unroll
+                    for (int k = 1; k <= 5; k++) row[k] = La[k];
+                } else if (is_min && r == n - 2) {
+#pragma unroll
+                    for (int k = 1; k <= 5; k++) row[k] = Lb[k];
+                } else if (!is_min && r == 2) {
+#pragma unroll
+                    for (int k = 1; k <= 5; k++) row[k] = La[k];
+                } else if (!is_min && r == 3) {
+#pragma unroll
+                    for (int k = 1; k <= 5; k++) row[k] = Lb[k];
+                } else {
+                    Lrow(r, row);
+                }
+                a = row[1]; b = row[2]; c = row[3]; d = row[4]; e = row[5];
+                if (m == 2) {
+                    b = b / c1;
+                    c = c - b * d1;
+                    d = d - b * e1;
+                } else if (m >= 3) {
+                    a = a / c2;
+                    b = (b - a * d2) / c1;
+                    c = c - b * d1 - a * e2;
+                    if (m < nmax) d = d - b * e1;
+                }
+                if (FMODE == 1) { fa.set(r, m >= 3 ? a : 0.0); fb.set(r, m >= 2 ? b : 0.0); }
             }
             const double nb = -b, na = -a;
 #pragma unroll
@@ -177,14 +194,16 @@ __device__ void int1_solve(const Int1Dev& P, double lam, const LineRef (&f)[NL],
                 double y;
                 if (m == 1) y = rv;
                 else if (m == 2) y = rv + y1[l] * nb;
-                else y = rv + y1[l] * nb + y2[l] * na;
+                else y = rv + y1[l] * nb + y2[l] * na;      // (FMODE 2 reads a = 0 at m <= 2 and b = 0 at m = 1)
                 ysc[l].set(r, y);
                 y2[l] = y1[l]; y1[l] = y;
                 um[l] = u0[l]; u0[l] = up[l]; up[l] = unext;
             }
-            csc.set(r, 1.0 / c);
-            dsc.set(r, -d);
-            c2 = c1; c1 = c; d2 = d1; d1 = d; e2 = e1; e1 = e;
+            if (FMODE != 2) {
+                csc.set(r, 1.0 / c);
+                dsc.set(r, -d);
+                c2 = c1; c1 = c; d2 = d1; d1 = d; e2 = e1; e1 = e;
+            }
         }
     }
 
@@ -276,6 +295,9 @@ __device__ void int1_solve(const Int1Dev& P, double lam, const LineRef (&f)[NL],
     }
 }
 
+template <int MINB, bool FAC>
+__global__ void poisson_modes_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv);
+
 struct ModeGeom {
     int nxh, ny, nz;          // half-spectrum extent in x, lines in y, modes in z (local)
     long long nmodes;         // nxh * nz
@@ -308,8 +330,13 @@ __global__ void poisson_fundamental_kernel(PoissonDev D) {
         double fend[2] = {1.0, 0.0}, bc[2] = {0.0, 1.0};
         LineRef res[2] = {plane(D.fund + 0 * plane_sz, D.ny, m), plane(D.fund + 1 * plane_sz, D.ny, m)};
         LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, D.ny, m), plane(D.scr + 1 * plane_sz, D.ny, m)};
-        int1_solve<2>(D.smin, lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, D.ny, m),
-                      plane(D.scr + 4 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), nullptr);
+        if (D.fac)
+            int1_solve<2, 1>(D.smin, lam, f, 1.0, fend, bc, res, ysc, plane(D.fac + 2 * plane_sz, D.ny, m),
+                             plane(D.fac + 3 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), nullptr,
+                             plane(D.fac + 0 * plane_sz, D.ny, m), plane(D.fac + 1 * plane_sz, D.ny, m));
+        else
+            int1_solve<2>(D.smin, lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, D.ny, m),
+                          plane(D.scr + 4 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), nullptr);
     }
     // stage 2: u1, s+, e+ from (v1, e-, 0) with values (0, 0, 1) at row n
     double der[3];
@@ -321,8 +348,13 @@ __global__ void poisson_fundamental_kernel(PoissonDev D) {
                           plane(D.fund + 4 * plane_sz, D.ny, m)};
         LineRef ysc[3] = {plane(D.scr + 0 * plane_sz, D.ny, m), plane(D.scr + 1 * plane_sz, D.ny, m),
                           plane(D.scr + 2 * plane_sz, D.ny, m)};
-        int1_solve<3>(D.smax, -lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, D.ny, m),
-                      plane(D.scr + 4 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), der);
+        if (D.fac)
+            int1_solve<3, 1>(D.smax, -lam, f, 1.0, fend, bc, res, ysc, plane(D.fac + 6 * plane_sz, D.ny, m),
+                             plane(D.fac + 7 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), der,
+                             plane(D.fac + 4 * plane_sz, D.ny, m), plane(D.fac + 5 * plane_sz, D.ny, m));
+        else
+            int1_solve<3>(D.smax, -lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, D.ny, m),
+                          plane(D.scr + 4 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), der);
     }
     // boundary system (opr_odes.f90:329-348), stored LU-decomposed
     const double v1n = plane(D.fund + 0 * plane_sz, D.ny, m).get(n), emn = plane(D.fund + 1 * plane_sz, D.ny, m).get(n);
@@ -347,7 +379,7 @@ __global__ void poisson_fundamental_kernel(PoissonDev D) {
 // per call: regular modes, Neumann/Neumann (OPR_ODE2_Factorize_NN)
 __device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ cf, double* __restrict__ cv, int i, int k);
 
-template <int MINB>
+template <int MINB, bool FAC>
 __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv) {
     const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= D.nmodes) return;
@@ -372,14 +404,24 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
     // v^(0): v' + lam v = f, f(n) = 0, v(1) = 0
     {
         LineRef f[2] = {fre, fim}, res[2] = {vre, vim};
-        int1_solve<2>(D.smin, lam, f, norm, zero2, zero2, res, ysc, csc, dsc, esc, nullptr);
+        if (FAC)
+            int1_solve<2, 2>(D.smin, lam, f, norm, zero2, zero2, res, ysc, plane(D.fac + 2 * plane_sz, D.ny, m),
+                             plane(D.fac + 3 * plane_sz, D.ny, m), esc, nullptr, plane(D.fac + 0 * plane_sz, D.ny, m),
+                             plane(D.fac + 1 * plane_sz, D.ny, m));
+        else
+            int1_solve<2>(D.smin, lam, f, norm, zero2, zero2, res, ysc, csc, dsc, esc, nullptr);
     }
     // u^(0): u' - lam u = v, u(n) = 0  (written over the forcing, which is no longer needed)
     double du0[2];
     {
         LineRef f[2] = {vre, vim}, res[2] = {fre, fim};
         const double fend[2] = {vre.get(1), vim.get(1)};
-        int1_solve<2>(D.smax, -lam, f, 1.0, fend, zero2, res, ysc, csc, dsc, esc, du0);
+        if (FAC)
+            int1_solve<2, 2>(D.smax, -lam, f, 1.0, fend, zero2, res, ysc, plane(D.fac + 6 * plane_sz, D.ny, m),
+                             plane(D.fac + 7 * plane_sz, D.ny, m), esc, du0, plane(D.fac + 4 * plane_sz, D.ny, m),
+                             plane(D.fac + 5 * plane_sz, D.ny, m));
+        else
+            int1_solve<2>(D.smax, -lam, f, 1.0, fend, zero2, res, ysc, csc, dsc, esc, du0);
     }
     // constraint and boundary conditions (opr_odes.f90:350-367)
     const double* A = D.amat;
@@ -590,6 +632,19 @@ int make_side(const HostDer& der1, int bc, Int1Dev& S, std::vector<void*>& alloc
 
 }  // namespace
 
+static void launch_modes(const PoissonDev& D, double* cf, double* cv, unsigned blocks, int threads, cudaStream_t st) {
+    const int minb = ctx().tune_poisson_minb;
+    if (D.fac) {
+        if (minb == 4) poisson_modes_kernel<4, true><<<blocks, threads, 0, st>>>(D, cf, cv);
+        else if (minb == 2) poisson_modes_kernel<2, true><<<blocks, threads, 0, st>>>(D, cf, cv);
+        else poisson_modes_kernel<3, true><<<blocks, threads, 0, st>>>(D, cf, cv);
+    } else {
+        if (minb == 4) poisson_modes_kernel<4, false><<<blocks, threads, 0, st>>>(D, cf, cv);
+        else if (minb == 2) poisson_modes_kernel<2, false><<<blocks, threads, 0, st>>>(D, cf, cv);
+        else poisson_modes_kernel<3, false><<<blocks, threads, 0, st>>>(D, cf, cv);
+    }
+}
+
 static int cufft_check(cufftResult r, const char* what) {
     if (r == CUFFT_SUCCESS) return 0;
     return fail(TLAB_ERR_CUDA, std::string(what) + ": cuFFT error " + std::to_string((int)r));
@@ -676,6 +731,16 @@ int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz, int nz_loca
     }
     allocs.push_back(fund); allocs.push_back(scr); allocs.push_back(amat);
     D.fund = fund; D.scr = scr; D.amat = amat;
+    D.fac = nullptr;
+    if (ctx().tune_poisson_factors) {
+        // LU factors of every mode kept (like the reference does, opr_elliptic.f90:140,205-209) when memory allows
+        size_t free_b = 0, total_b = 0;
+        cudaMemGetInfo(&free_b, &total_b);
+        const size_t need = 8 * plane_sz * sizeof(double);
+        double* fac = nullptr;
+        if (free_b > need + (size_t)60 * plane_sz * sizeof(double) / 2 && cudaMalloc(&fac, need) == cudaSuccess) { allocs.push_back(fac); D.fac = fac; }
+        else cudaGetLastError();
+    }
     cudaMemset(fund, 0, 5 * plane_sz * sizeof(double));
     // cuFFT plans (Appendix B of SURVEY.md: same geometry as the FFTW plans, opr_fourier.f90:101-171)
     cudaStream_t st = ctx().stream;
@@ -756,10 +821,7 @@ int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const do
             ProfScope ps(PC_POISSON_Y);
             const int threads = 128;
             const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
-            const int minb = ctx().tune_poisson_minb;
-            if (minb == 4) poisson_modes_kernel<4><<<blocks, threads, 0, st>>>(D, cpa, cpb);
-            else if (minb == 2) poisson_modes_kernel<2><<<blocks, threads, 0, st>>>(D, cpa, cpb);
-            else poisson_modes_kernel<3><<<blocks, threads, 0, st>>>(D, cpa, cpb);
+            launch_modes(D, cpa, cpb, blocks, threads, st);
             if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
         }
         {
@@ -785,10 +847,7 @@ int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const do
         ProfScope ps(PC_POISSON_Y);
         const int threads = 128;
         const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
-        const int minb = ctx().tune_poisson_minb;
-        if (minb == 4) poisson_modes_kernel<4><<<blocks, threads, 0, st>>>(D, c1, c2);
-        else if (minb == 2) poisson_modes_kernel<2><<<blocks, threads, 0, st>>>(D, c1, c2);
-        else poisson_modes_kernel<3><<<blocks, threads, 0, st>>>(D, c1, c2);
+        launch_modes(D, c1, c2, blocks, threads, st);
         if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
     }
     if (int rc = fft_z(c1, c3, CUFFT_INVERSE)) return rc;

@@ -26,6 +26,8 @@ struct PoissonDev {
     double* fund = nullptr;           // 5 planes [ny][nmodes]: v1, e-, u1, s+, e+
     double* scr = nullptr;            // 6 planes [ny][nmodes] of per-mode scratch
     double* amat = nullptr;           // 9 x [nmodes]: LU-decomposed 3x3 boundary system
+    double* fac = nullptr;            // optional, 8 planes [ny][nmodes]: LU factors (la, lb, 1/c, -d) of the BCS_MIN(+lam) and
+                                      // BCS_MAX(-lam) systems of every regular mode, computed once (they depend on lambda only)
 };
 
 struct Poisson {
