@@ -36,6 +36,17 @@ ALG_BYTES_PER_PT_SUBSTEP = 995.0          # 124.4 sweeps of 8 B
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel classes from the committed
 # ncu --set full captures (profiles/), scaled to the C3 grid (bytes per point x points); None if not captured
 TRAFFIC_BYTES_PER_PT = {"burgers_y": 24.07, "burgers_z": 23.79}   # profiles/ncu_full_burgers_strided_r01.json (U_IN, 512^3)
+
+
+def load_traffic():
+    """Measured DRAM bytes per point and launch of the line-kernel classes in the RHS of this bench (they include the
+    read-modify-write of hq that the launches fuse): profiles/ncu_dram_bench_r01.json, written by tools/ncu_dram_summary.py
+    from an `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` pass over one substep."""
+    path = os.path.join(ROOT, "profiles", "ncu_dram_bench_r01.json")
+    try:
+        return {k: float(v) for k, v in json.load(open(path))["bytes_per_point_per_launch"].items()}
+    except Exception:
+        return dict(TRAFFIC_BYTES_PER_PT)
 PHYS = dict(visc=1.0 / 5000.0, schmidt=[1.0], dtime=1.0e-3)
 
 
@@ -305,7 +316,7 @@ def run_gpu(args):
     achieved = line_classes[dom] * N / (avg_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": (TRAFFIC_BYTES_PER_PT[dom] * N if dom in TRAFFIC_BYTES_PER_PT else None),
+                "traffic": (load_traffic()[dom] * N if dom in load_traffic() else None),
                 "algorithmic_bytes_per_launch": line_classes[dom] * N, "avg_launch_ms": avg_ms,
                 "substep": {"algorithmic_bytes_per_gpu": ALG_BYTES_PER_PT_SUBSTEP * N,
                             "achieved_per_gpu": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9,

@@ -664,6 +664,28 @@ __device__ __forceinline__ void tile_load(double* tile, const double* __restrict
 }
 
 // One field of one tile.  MULTI: fused Burgers launch, the velocity tile has been staged by the caller.
+// two tiles at once: all 16 loads are in flight before the first shared-memory store
+__device__ __forceinline__ void tile_load_pair(double* tile, double* tile2, const double* __restrict__ g, const double* __restrict__ g2,
+                                               int n, int T, int L, int LS) {
+    const int nth = L * T;
+    const int per_line = (L == 8) ? 1 : (L == 4 ? 2 : (L == 2 ? 4 : 8));
+    const int tid = threadIdx.x;
+    double2 v[8], w[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
+        v[k] = __ldcs(reinterpret_cast<const double2*>(g + (size_t)ll * n) + i2);
+        w[k] = __ldcs(reinterpret_cast<const double2*>(g2 + (size_t)ll * n) + i2);
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
+        const int o = ll * LS + (i2 >> 3) * XB + (i2 & 7) * 2;
+        *reinterpret_cast<double2*>(tile + o) = v[k];
+        *reinterpret_cast<double2*>(tile2 + o) = w[k];
+    }
+}
+
 template <int MODE, bool PER, bool NEED1, bool MULTI>
 __device__ __forceinline__ void contig_field(const Line2Args& a, const ChunkCtx& c, double* sm, const double* __restrict__ fu,
                                              double* __restrict__ fo, const Sys2& S2) {
@@ -687,8 +709,9 @@ __device__ __forceinline__ void contig_field(const Line2Args& a, const ChunkCtx&
         }
     }
     if (a.u2 != nullptr) tile_load<true>(tile, fu + tile_off, a.u2 + tile_off, a.scale, n, T, L, LS);
+    else if (two && !MULTI) tile_load_pair(tile, vtile, fu + tile_off, a.vel + tile_off, n, T, L, LS);
     else tile_load<false>(tile, fu + tile_off, nullptr, 0.0, n, T, L, LS);
-    if (two && !MULTI) tile_load<false>(vtile, a.vel + tile_off, nullptr, 0.0, n, T, L, LS);
+    if (two && !MULTI && a.u2 != nullptr) tile_load<false>(vtile, a.vel + tile_off, nullptr, 0.0, n, T, L, LS);
     __syncthreads();
 
     const double* row = tile + c.l * LS;
@@ -713,6 +736,18 @@ __device__ __forceinline__ void contig_field(const Line2Args& a, const ChunkCtx&
     line_core2<MODE, PER, NEED1>(u, a, S2, c, sm, d1, d2);
     // all halo reads of the tile happened before the first barrier inside line_core2: results may overwrite it
 
+    const int nth = L * T;
+    const int per_line = (L == 8) ? 1 : (L == 4 ? 2 : (L == 2 ? 4 : 8));
+    const int tid = threadIdx.x;
+    double2 acc[8];
+    if (has_acc) {
+        // in flight while the results are staged and the barrier is crossed
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
+            acc[k] = __ldcs(reinterpret_cast<const double2*>(fo + tile_off + (size_t)ll * n) + i2);
+        }
+    }
     {
         double* wrow = tile + c.l * LS + c.t * XB;
         const double* vrow = (two ? vtile : tile) + c.l * LS + c.t * XB;
@@ -734,9 +769,6 @@ __device__ __forceinline__ void contig_field(const Line2Args& a, const ChunkCtx&
         }
     }
     __syncthreads();
-    const int nth = L * T;
-    const int per_line = (L == 8) ? 1 : (L == 4 ? 2 : (L == 2 ? 4 : 8));
-    const int tid = threadIdx.x;
     {
         double2 v[8];
 #pragma unroll
@@ -747,8 +779,7 @@ __device__ __forceinline__ void contig_field(const Line2Args& a, const ChunkCtx&
         if (has_acc) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const int ll = (k * L) >> 3, i2 = tid + (k & (per_line - 1)) * nth;
-                const double2 o = __ldcs(reinterpret_cast<const double2*>(fo + tile_off + (size_t)ll * n) + i2);
+                const double2 o = acc[k];
                 if (a.accumulate > 0) { v[k].x = o.x + v[k].x; v[k].y = o.y + v[k].y; }
                 else { v[k].x = o.x - v[k].x; v[k].y = o.y - v[k].y; }
             }
