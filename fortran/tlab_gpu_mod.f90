@@ -121,6 +121,52 @@ module TLab_GPU
             type(c_ptr), value :: dns
             real(c_double), value :: dtime
         end function
+        ! TIME_SUBSTEP_INCOMPRESSIBLE_EXPLICIT + update of one stage (time.f90:559-670, 277-297)
+        integer(c_int) function tlab_time_rungekutta_stage(dns, dtime, stage) bind(C, name='tlab_time_rungekutta_stage')
+            import :: c_int, c_double, c_ptr
+            type(c_ptr), value :: dns
+            real(c_double), value :: dtime
+            integer(c_int), value :: stage
+        end function
+        ! same step from and to host arrays q(isize_field,3), s(isize_field,inb_scal)
+        integer(c_int) function tlab_time_rungekutta_host(dns, dtime, q, s) bind(C, name='tlab_time_rungekutta_host')
+            import :: c_int, c_double, c_ptr
+            type(c_ptr), value :: dns
+            real(c_double), value :: dtime
+            real(c_double) :: q(*), s(*)
+        end function
+        ! TIME_COURANT (time.f90:365-548): new dtime and the logged CFL / diffusion numbers
+        integer(c_int) function tlab_time_courant(dns, cfla, cfld, prandtl, dtime, cfl_number, diffusion_number) &
+            bind(C, name='tlab_time_courant')
+            import :: c_int, c_double, c_ptr
+            type(c_ptr), value :: dns
+            real(c_double), value :: cfla, cfld, prandtl
+            real(c_double) :: dtime, cfl_number, diffusion_number
+        end function
+        ! DNS_BOUNDS_CONTROL (dns_local.f90:94-234): extrema of the dilatation
+        integer(c_int) function tlab_dns_bounds_control(dns, dil_min, dil_max) bind(C, name='tlab_dns_bounds_control')
+            import :: c_int, c_double, c_ptr
+            type(c_ptr), value :: dns
+            real(c_double) :: dil_min, dil_max
+        end function
+        integer(c_int) function tlab_boundary_bcs_neumann_y(ibc, nx, ny, nz, g, u, bcs_hb, bcs_ht) &
+            bind(C, name='tlab_boundary_bcs_neumann_y')
+            import :: c_int, c_ptr
+            integer(c_int), value :: ibc, nx, ny, nz
+            type(c_ptr), value :: g, u, bcs_hb, bcs_ht
+        end function
+        integer(c_int) function tlab_gpu_set_tuning(key, value) bind(C, name='tlab_gpu_set_tuning')
+            import :: c_int, c_char
+            character(kind=c_char), intent(in) :: key(*)
+            integer(c_int), value :: value
+        end function
+        integer(c_int) function tlab_mpi_finalize() bind(C, name='tlab_mpi_finalize')
+            import :: c_int
+        end function
+        integer(c_int) function tlab_dns_destroy(dns) bind(C, name='tlab_dns_destroy')
+            import :: c_int, c_ptr
+            type(c_ptr), value :: dns
+        end function
         function tlab_gpu_last_error() bind(C, name='tlab_gpu_last_error') result(msg)
             import :: c_ptr
             type(c_ptr) :: msg
@@ -134,6 +180,8 @@ module TLab_GPU
     public :: tlab_fdm_plan_create, tlab_opr_partial, tlab_opr_burgers_init, tlab_opr_burgers
     public :: tlab_opr_elliptic_init, tlab_opr_poisson, tlab_mpi_get_unique_id, tlab_mpi_init
     public :: tlab_dns_create, tlab_dns_upload_host, tlab_dns_download_host, tlab_time_rungekutta
+    public :: tlab_time_rungekutta_stage, tlab_time_rungekutta_host, tlab_time_courant, tlab_dns_bounds_control
+    public :: tlab_boundary_bcs_neumann_y, tlab_gpu_set_tuning, tlab_mpi_finalize, tlab_dns_destroy
     public :: OPR_Partial_GPU, OPR_Burgers_GPU, OPR_Poisson_GPU, TLab_GPU_Check
 
 contains

@@ -20,6 +20,9 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     from tlab_b200 import lib as tl, opr, dns as GD, mpi
     tl.check(tl.load().tlab_gpu_init(local))
+    for kv in [t for t in os.environ.get("TLAB_TUNE", "").split(",") if t]:
+        k, v = kv.split("=")
+        tl.check(tl.load().tlab_gpu_set_tuning(k.encode(), int(v)))
     mpi.init_from_torch_distributed()
     nx, ny, nz = 32, 32, 32
     kmax, koff = mpi.slab(nz, rank, world)
@@ -58,6 +61,13 @@ def main():
         gathered.append(torch.cat(out, dim=0).cpu().numpy())
     if rank == 0:
         errs = [rel_l2(a, b) for a, b in zip(gathered, ref)]
+        import ctypes
+        cnt = {}
+        for key in ("p2p_exchanges", "nccl_exchanges"):
+            c = ctypes.c_longlong()
+            tl.check(tl.load().tlab_gpu_get_counter(key.encode(), ctypes.byref(c)))
+            cnt[key] = c.value
+        print("DIST_PATH p2p=%d nccl=%d" % (cnt["p2p_exchanges"], cnt["nccl_exchanges"]), flush=True)
         print("DIST_ERRS", " ".join("%.3e" % e for e in errs), flush=True)
         assert max(errs) <= 1e-11, errs
     g.close()

@@ -9,15 +9,27 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_gpu_rk_steps(cuda):
+@pytest.mark.parametrize("tune", ["", "p2p=0", "overlap=0,kxsplit=0", "p2p_dma=1"])
+def test_two_gpu_rk_steps(cuda, tune):
+    """Two RK steps on 2 z slabs against the single-domain oracle: peer-memory transposes with overlapped z operators
+    and the kx-split Poisson stage (default), the NCCL send/recv fallback, the plain schedule, the copy-engine variant."""
+    import re
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    env = dict(os.environ, TLAB_TUNE=tune)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "DIST_ERRS" in r.stdout
+    m = re.search(r"DIST_PATH p2p=(\d+) nccl=(\d+)", r.stdout)
+    assert m, r.stdout[-2000:]
+    p2p, nccl = int(m.group(1)), int(m.group(2))
+    if tune == "p2p=0":
+        assert p2p == 0 and nccl > 0
+    # (where peer mapping is unavailable the library falls back to NCCL by itself: either count may be the non-zero one)
+    assert p2p + nccl > 0
 
 
 def test_single_rank_transposes_are_copies(cuda):

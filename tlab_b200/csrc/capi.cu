@@ -98,6 +98,7 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
         b.persist = al(a.u) && al(a.u2) && al(a.vel) && (a.stride % 2 == 0) && (a.outer_stride % 2 == 0) && (L % 2 == 0) &&
                     lines2_persist_smem(b.T, L) <= 220 * 1024;
     }
+    b.pf_l1 = contig ? 0 : ctx().tune_pf_l1;
     b.lshift = 0;
     while ((1 << b.lshift) < L) b.lshift++;
     b.accumulate = a.accumulate; b.scale = a.scale;
@@ -371,6 +372,7 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "fast")) ctx().tune_fast = value;
     else if (!std::strcmp(key, "pf_dist")) ctx().tune_pf_dist = value;
     else if (!std::strcmp(key, "persist")) ctx().tune_persist = value;
+    else if (!std::strcmp(key, "pf_l1")) ctx().tune_pf_l1 = value;
     else if (!std::strcmp(key, "fuse")) ctx().tune_fuse = value;
     else if (!std::strcmp(key, "overlap")) ctx().tune_overlap = value;
     else if (!std::strcmp(key, "kxsplit")) ctx().tune_kxsplit = value;

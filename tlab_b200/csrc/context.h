@@ -31,6 +31,7 @@ struct Context {
     int tune_fuse = 0;        // RHS: one fused Burgers launch per direction (fields sharing the advecting velocity)
     int tune_kxsplit = 1;     // split domain + peer memory: kx-split spectral stage of the Poisson solver
     int tune_overlap = 1;     // split domain: z operators on a second stream, overlapped with the x/y operators
+    int tune_pf_l1 = 0;       // strided fast kernels: early L1 prefetch of the operands needed after the solve
     int tune_persist = 0;     // strided fast kernels: persistent CTAs with asynchronous staging
     long long fast_launches = 0, general_launches = 0;    // L2 prefetch distance of the fast kernels in tiles (-1: automatic, 0: off)
     tlab_plan_s* burgers_plans[3] = {nullptr, nullptr, nullptr};

@@ -38,6 +38,7 @@ constexpr int XB = C + 2;          // padded chunk block of the x tile (doubles)
 #define DSUB(a, b) __dsub_rn((a), (b))
 
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ double2 ldg2(const double2* p) { return __ldg(p); }
 
 // ------------------------------------------------------------------------------------------------
@@ -356,6 +357,14 @@ __device__ __forceinline__ void strided_field(const Line2Args& a, const ChunkCtx
     // ---- chunk + two 3-point halos (wrapped or zero)
     double u[C + 6];
     const long long coff = lbase + (long long)(c.t * C) * st;
+    if (a.pf_l1 && (MODE == MODE_BURGERS || (MODE == MODE_P1 && has_acc))) {
+        // the velocity and the accumulation target are needed after the solve: ask for them now (L1, no registers)
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            if (MODE == MODE_BURGERS && a.vel != fu) prefetch_l1(a.vel + coff + j * st);
+            if (has_acc) prefetch_l1(fo + coff + j * st);
+        }
+    }
     const bool lok = PER || c.t > 0, rok = PER || c.t < c.T - 1;
     const long long loff = (c.t > 0) ? -3 * st : (long long)(n - 3) * st;
     const long long roff = (c.t < c.T - 1) ? (long long)C * st : -(long long)(c.t * C) * st;

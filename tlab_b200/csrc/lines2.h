@@ -9,6 +9,7 @@ struct Line2Args {
     int accumulate = 0;               // +1: out1 += result, -1: out1 -= result, 0: out1 = result
     int pf_dist = 0;                  // L2 prefetch distance in tiles (0: off)
     int xls = 0;                      // shared-memory line stride of the x tile (doubles)
+    int pf_l1 = 0;                    // strided kernel: L1 prefetch of the velocity / accumulation target at kernel start
     int persist = 0;                  // strided kernel: persistent CTAs with cp.async staging
     unsigned ntiles = 0, tiles_x = 0; // persistent kernel: tile count and tiles per outer block
     double scale = 0.0;               // input is u + scale * u2 when u2 != nullptr
