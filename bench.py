@@ -309,15 +309,28 @@ def run_gpu(args):
 
     # roofline of the dominant kernel class (by device time inside the timed region)
     peak, peak_kind = load_peaks()
-    line_classes = {"burgers_x": 22.0, "burgers_y": 22.0, "burgers_z": 22.0,      # (16 + 3*24)/4 B/pt per launch
-                    "partial_x": 16.0, "partial_y": 16.0, "partial_z": 16.0}
+    # Algorithmic bytes per point of one launch = compulsory traffic at the reference's operator surface:
+    # OPR_Burgers SELF 16 / U_IN 24 B/pt, mean over the 1 + 3 launches of a direction = 22; every launch of the RHS also
+    # performs the reference's separate `hq = hq + tmp` sweep (24 B/pt there), which fused costs one more read of hq: +8.
+    # OPR_Partial P1 in the RHS: 16 B/pt + 8 for the second input (hq + q/dte) and/or + 8 for the accumulation target:
+    # y: 24 (one launch); x and z: (32 + 24)/2 = 28 (divergence term and pressure gradient).
+    line_classes = {"burgers_x": 30.0, "burgers_y": 30.0, "burgers_z": 30.0,
+                    "partial_x": 28.0, "partial_y": 24.0, "partial_z": 28.0}
+    surface_only = {"burgers_x": 22.0, "burgers_y": 22.0, "burgers_z": 22.0, "partial_x": 16.0, "partial_y": 16.0, "partial_z": 16.0}
     dom = max((k for k in breakdown if k in line_classes), key=lambda k: breakdown[k]["ms_per_step"])
     avg_ms = ms_cls[cls_names.index(dom)] / cnt_cls[cls_names.index(dom)]
     achieved = line_classes[dom] * N / (avg_ms * 1e-3) / 1e9
+    traffic = load_traffic()
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": achieved / peak,
-                "traffic": (load_traffic()[dom] * N if dom in load_traffic() else None),
+                "traffic": (traffic[dom] * N if dom in traffic else None),
                 "algorithmic_bytes_per_launch": line_classes[dom] * N, "avg_launch_ms": avg_ms,
+                "algorithmic_bytes_note": "operator surface (%g B/pt) + the extra operand(s) of the reference's separate "
+                                          "accumulation / pressure-forcing sweeps that the launch fuses" % surface_only[dom],
+                "achieved_operator_surface_only": surface_only[dom] * N / (avg_ms * 1e-3) / 1e9,
+                "per_class": {k: {"achieved": line_classes[k] * N / (ms_cls[cls_names.index(k)] / cnt_cls[cls_names.index(k)] * 1e-3) / 1e9,
+                                  "frac": line_classes[k] * N / (ms_cls[cls_names.index(k)] / cnt_cls[cls_names.index(k)] * 1e-3) / 1e9 / peak}
+                              for k in breakdown if k in line_classes},
                 "substep": {"algorithmic_bytes_per_gpu": ALG_BYTES_PER_PT_SUBSTEP * N,
                             "achieved_per_gpu": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9,
                             "frac": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9 / peak}}
