@@ -87,7 +87,9 @@ int tlab_gpu_copy(void* dst_device, const void* src_device, size_t bytes);
 /* "lines_x", "lines_yz": lines per CTA of the general line kernels (0 = automatic); "fast": 1/0 use the fast line
  * kernels where the geometry allows (default 1); "pf_dist": their L2 prefetch distance in tiles (-1 automatic, 0 off) */
 int tlab_gpu_set_tuning(const char* key, int value);
-/* launch counters: "fast_launches", "general_launches" (line kernels since start-up) */
+/* "tma": 1/0 run the y/z line operators as persistent CTAs fed and drained by the TMA unit (default 0: measured slower on rows
+ * of 32-128 bytes; falls back to the LSU kernels when a geometry is not eligible).
+ * launch counters: "fast_launches", "general_launches", "tma_launches" (line kernels since start-up) */
 int tlab_gpu_get_counter(const char* key, long long* value);
 
 /* the CUDA stream (cudaStream_t) every call is ordered on, for event timing by the host */

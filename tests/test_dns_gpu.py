@@ -152,14 +152,15 @@ def test_case01_shape_two_dimensional_step(cuda):
     assert rel_l2(g.get("s1"), o.s[0]) <= 1e-11
 
 
-@pytest.mark.parametrize("tune", [{"fuse": 1}, {"fuse": 1, "pf_next": 1}, {"persist": 1}, {"pf_dist": 3}, {"fast": 0}])
+@pytest.mark.parametrize("tune", [{"fuse": 1}, {"fuse": 1, "pf_next": 1}, {"persist": 1}, {"pf_dist": 3}, {"fast": 0},
+                                  {"tma": 1}])
 def test_tuning_variants_give_the_same_step(cuda, tune):
     """The optional kernel variants (fused multi-field Burgers launch, next-field / next-tile L2 prefetch, persistent
     cp.async staging, general kernels) are alternative schedules of the same arithmetic: one RK step on full chunks
     (64 x 64 x 32) must agree with the oracle like the default path does."""
     from tlab_b200 import lib as tl
     L = tl.load()
-    defaults = {"fuse": 0, "pf_next": 0, "persist": 0, "pf_dist": -1, "fast": 1}
+    defaults = {"fuse": 0, "pf_next": 0, "persist": 0, "pf_dist": -1, "fast": 1, "tma": 0}
     try:
         for k, v in tune.items():
             tl.check(L.tlab_gpu_set_tuning(k.encode(), v))
@@ -172,3 +173,31 @@ def test_tuning_variants_give_the_same_step(cuda, tune):
     finally:
         for k, v in defaults.items():
             tl.check(L.tlab_gpu_set_tuning(k.encode(), v))
+
+
+@pytest.mark.parametrize("shape,lines", [((16, 64, 128), 0), ((16, 32, 1024), 0), ((16, 32, 1024), 4), ((16, 512, 16), 4),
+                                         ((16, 512, 16), 8)])
+def test_step_through_the_tma_kernels(cuda, shape, lines):
+    """y and z operators as persistent CTAs fed by the TMA unit (tensor-map loads, reduce-add stores into hq/hs):
+    32/16/8/4 lines per CTA (row-order permutations in shared memory), 3-D (y) and 2-D (z) tensor maps, second input
+    and accumulation.  The step must agree with the oracle and the TMA kernels must actually have run."""
+    import ctypes
+    from tlab_b200 import lib as tl
+    L = tl.load()
+    before = ctypes.c_longlong(0)
+    tl.check(L.tlab_gpu_get_counter(b"tma_launches", ctypes.byref(before)))
+    try:
+        tl.check(L.tlab_gpu_set_tuning(b"tma", 1))
+        tl.check(L.tlab_gpu_set_tuning(b"lines_yz", lines))
+        o, g = _pair(*shape, "tanh")
+        o.runge_kutta(1e-3)
+        g.runge_kutta(1e-3)
+    finally:
+        tl.check(L.tlab_gpu_set_tuning(b"lines_yz", 0))
+        tl.check(L.tlab_gpu_set_tuning(b"tma", 0))
+    after = ctypes.c_longlong(0)
+    tl.check(L.tlab_gpu_get_counter(b"tma_launches", ctypes.byref(after)))
+    assert after.value - before.value >= 5 * 10, "the TMA line kernels did not run"
+    for i in range(3):
+        assert rel_l2(g.get("q%d" % (i + 1)), o.q[i]) <= 1e-11
+    assert rel_l2(g.get("s1"), o.s[0]) <= 1e-11

@@ -29,7 +29,8 @@ CASES = [(64, 48, 32, "stretched", True, True),
          (256, 32, 16, "tanh", True, True),          # fast kernels: constant interior chunks + circulant closure in x
          (16, 48, 256, "stretched", True, True),     # the same in z; single-chunk x
          (32, 256, 16, "uniform", True, True),       # uniform non-periodic y: constant interior chunks
-         (64, 64, 64, "tanh", False, False)]         # biased schemes on full chunks in all directions
+         (64, 64, 64, "tanh", False, False),         # biased schemes on full chunks in all directions
+         (16, 32, 1024, "tanh", True, True)]         # z lines of 64 chunks: TMA kernel with 8 lines per CTA (64-byte rows)
 
 
 @pytest.mark.parametrize("case", CASES)

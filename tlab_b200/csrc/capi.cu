@@ -112,6 +112,10 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
     std::memcpy(b.neu_bot, a.neu_bot, sizeof(b.neu_bot));
     std::memcpy(b.neu_top, a.neu_top, sizeof(b.neu_top));
     b.neu_lu_bot = a.neu_lu_bot; b.neu_lu_top = a.neu_lu_top;
+    b.tma_rb = 16;
+    while (b.tma_rb < 256 && b.n % (b.tma_rb * 2) == 0) b.tma_rb *= 2;
+    b.tma_l2 = ctx().tune_tma_l2;
+    b.tma = (!contig && ctx().tune_tma && lines2_tma_eligible(mode, b)) ? 1 : 0;
     return true;
 }
 
@@ -223,6 +227,7 @@ int run_burgers_multi(int dir, int nf, const int* is, const double* const* sf, c
     auto al = [](const void* q) { return (reinterpret_cast<size_t>(q) & 15) == 0; };
     for (int f = 0; f < nf; f++) if (contig && !(al(sf[f]) && al(out[f]))) return fallback();
     b.persist = 0;
+    b.tma = 0;
     b.nf = nf;
     b.pf_next = ctx().tune_pf_next;
     for (int f = 0; f < nf; f++) { b.fu[f] = sf[f]; b.fo[f] = out[f]; b.fsys[f] = (is[f] == is[0]) ? 0 : 1; }
@@ -372,6 +377,8 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "fast")) ctx().tune_fast = value;
     else if (!std::strcmp(key, "pf_dist")) ctx().tune_pf_dist = value;
     else if (!std::strcmp(key, "persist")) ctx().tune_persist = value;
+    else if (!std::strcmp(key, "tma")) ctx().tune_tma = value;
+    else if (!std::strcmp(key, "tma_l2")) ctx().tune_tma_l2 = value;
     else if (!std::strcmp(key, "pf_l1")) ctx().tune_pf_l1 = value;
     else if (!std::strcmp(key, "fuse")) ctx().tune_fuse = value;
     else if (!std::strcmp(key, "overlap")) ctx().tune_overlap = value;
@@ -390,6 +397,7 @@ int tlab_gpu_get_counter(const char* key, long long* value) {
     if (!key || !value) return fail(TLAB_ERR_OPTION, "null argument");
     if (!std::strcmp(key, "fast_launches")) *value = ctx().fast_launches;
     else if (!std::strcmp(key, "general_launches")) *value = ctx().general_launches;
+    else if (!std::strcmp(key, "tma_launches")) *value = lines2_tma_launches();
     else if (!std::strcmp(key, "p2p_exchanges")) *value = trp().p2p_exchanges;
     else if (!std::strcmp(key, "nccl_exchanges")) *value = trp().nccl_exchanges;
     else return fail(TLAB_ERR_OPTION, std::string("unknown counter ") + key);

@@ -33,6 +33,10 @@ struct Context {
     int tune_overlap = 1;     // split domain: z operators on a second stream, overlapped with the x/y operators
     int tune_pf_l1 = 0;       // strided fast kernels: early L1 prefetch of the operands needed after the solve
     int tune_persist = 0;     // strided fast kernels: persistent CTAs with asynchronous staging
+    int tune_tma_l2 = 0;      // L2 promotion of the tensor maps of the TMA kernels
+    int tune_tma = 0;         // strided fast kernels: persistent CTAs fed and drained by the TMA unit (tensor maps, reduce-add
+                              // stores).  Off: measured slower than the LSU kernels, the TMA unit sustains ~20 GB/s per SM on
+                              // rows of 32-128 bytes (profiles/ncu_full_tma_r01.json)
     long long fast_launches = 0, general_launches = 0;    // L2 prefetch distance of the fast kernels in tiles (-1: automatic, 0: off)
     tlab_plan_s* burgers_plans[3] = {nullptr, nullptr, nullptr};
     bool profiling = false;

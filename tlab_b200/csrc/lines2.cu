@@ -24,7 +24,11 @@
 // Every CTA also prefetches into L2 the tile that the CTA `pf_dist` places later will work on, so that the DRAM
 // latency of a tile is paid while earlier tiles are being solved.
 #include "lines2.h"
+#include <cuda.h>
 #include <algorithm>
+#include <cstring>
+#include <map>
+#include <tuple>
 
 namespace tlab {
 
@@ -640,6 +644,223 @@ __global__ void __launch_bounds__(512, 1) lines2_strided_pa(const __grid_constan
 }
 
 // ------------------------------------------------------------------------------------------------
+// y / z directions, persistent CTAs fed by the TMA unit.  Nothing of the field traffic goes through the LSU: a tile of
+// L lines (n rows of L*8 bytes, rows `stride` apart) is brought into shared memory by cp.async.bulk.tensor (boxes of
+// L x RB points, completion on an mbarrier), the result tile is staged in shared memory and leaves through a bulk
+// tensor store -- a reduce-add store when the operator accumulates (hq += ..., hq -= dp/dx), so the accumulation target
+// is never loaded by the SM: the read-modify-write happens in L2.  Buffers: U (field), V (velocity or second input, or
+// the parked field of a SELF call), R (result).  Per tile:
+//     wait U [and V: second input] -> registers | barrier S1 | TMA U(next) [V(next)] | solve | wait V: velocity |
+//     combine -> R | fence.proxy.async, barrier S2 | TMA store R, TMA V(next)
+// so the loads of the next tile are in flight while this one is solved and stored.  Tile layout in shared memory is
+// dense, point i of line l at i*L + l (what a box copy produces).  With L = 8 a row is 64 bytes = half of the banks and
+// the four chunks of a warp start 16 rows apart: odd chunks visit the rows of a pair in swapped order, so that every
+// access of a warp covers all banks once per 128 bytes.
+struct TmaMaps {
+    CUtensorMap u, v, o;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+template <bool THREE>
+__device__ __forceinline__ void tma_load_box(unsigned dst, const CUtensorMap* m, unsigned bar, int c0, int c1, int c2) {
+    if (THREE)
+        asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                     ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    else
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                     ::"r"(dst), "l"(m), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+template <bool THREE, bool ADD>
+__device__ __forceinline__ void tma_store_box(const CUtensorMap* m, unsigned src, int c0, int c1, int c2) {
+    if (THREE) {
+        if (ADD) asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];"
+                              ::"l"(m), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+        else asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                          ::"l"(m), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    } else {
+        if (ADD) asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.bulk_group [%0, {%2, %3}], [%1];"
+                              ::"l"(m), "r"(src), "r"(c0), "r"(c1) : "memory");
+        else asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                          ::"l"(m), "r"(src), "r"(c0), "r"(c1) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// warp 0: one tile of one array -> shared memory (n / RB boxes, one per lane), completion on `bar`
+template <bool THREE>
+__device__ __forceinline__ void tma_tile_in(const CUtensorMap* m, double* buf, unsigned bar, int x0, int outer, int n, int L, int RB) {
+    const int lane = threadIdx.x & 31;
+    if (lane == 0) mbar_expect_tx(bar, (unsigned)(n * L) * 8u);
+    __syncwarp();
+    for (int r = lane * RB; r < n; r += 32 * RB) tma_load_box<THREE>(smem_u32(buf + (size_t)r * L), m, bar, x0, r, outer);
+}
+template <bool THREE>
+__device__ __forceinline__ void tma_tile_out(const CUtensorMap* m, const double* buf, bool add, int x0, int outer, int n, int L, int RB) {
+    const int lane = threadIdx.x & 31;
+    for (int r = lane * RB; r < n; r += 32 * RB) {
+        if (add) tma_store_box<THREE, true>(m, smem_u32(buf + (size_t)r * L), x0, r, outer);
+        else tma_store_box<THREE, false>(m, smem_u32(buf + (size_t)r * L), x0, r, outer);
+    }
+    bulk_commit();
+}
+
+// the 16 points of a chunk <-> registers.  A row of the tile is L*8 bytes; with L = 8 (4) it covers a half (a quarter) of
+// the banks and the chunks of a warp start 16 rows apart, i.e. in the same banks: chunk t visits the rows of each aligned
+// pair (quad) in the order j ^ (t & 1) (j ^ (t & 3)), so that a warp access covers all banks once per 128 bytes; the values
+// are put back in order with conditional swaps.
+template <int LL>
+__device__ __forceinline__ void xor_permute(double* v, int s) {
+    if (LL <= 8) {
+#pragma unroll
+        for (int k = 0; k < C; k += 2) {
+            const double a = v[k], b = v[k + 1];
+            v[k] = (s & 1) ? b : a;
+            v[k + 1] = (s & 1) ? a : b;
+        }
+    }
+    if (LL == 4) {
+#pragma unroll
+        for (int k = 0; k < C; k += 4) {
+            const double a = v[k], b = v[k + 1], c = v[k + 2], d = v[k + 3];
+            v[k] = (s & 2) ? c : a;
+            v[k + 1] = (s & 2) ? d : b;
+            v[k + 2] = (s & 2) ? a : c;
+            v[k + 3] = (s & 2) ? b : d;
+        }
+    }
+}
+template <int LL>
+__device__ __forceinline__ void chunk_get(const double* buf, int t, int l, double* v) {
+    const int s = (LL == 8) ? (t & 1) : ((LL == 4) ? (t & 3) : 0);
+    const double* pc = buf + (size_t)(t * C) * LL + l;
+#pragma unroll
+    for (int k = 0; k < C; k++) v[k] = pc[(k ^ s) * LL];
+    xor_permute<LL>(v, s);
+}
+template <int LL>
+__device__ __forceinline__ void chunk_put(double* buf, int t, int l, const double* v) {
+    const int s = (LL == 8) ? (t & 1) : ((LL == 4) ? (t & 3) : 0);
+    double* pc = buf + (size_t)(t * C) * LL + l;
+    double w[C];
+#pragma unroll
+    for (int k = 0; k < C; k++) w[k] = v[k];
+    xor_permute<LL>(w, s);
+#pragma unroll
+    for (int k = 0; k < C; k++) pc[(k ^ s) * LL] = w[k];
+}
+
+template <int MODE, bool PER, bool NEED1, int LL, bool THREE>
+__global__ void __launch_bounds__(512, 1) lines2_strided_tma(const __grid_constant__ Line2Args a, const __grid_constant__ TmaMaps maps) {
+    extern __shared__ __align__(128) double smt[];
+    ChunkCtx c;
+    c.L = LL; c.T = a.T;
+    c.l = threadIdx.x & (LL - 1);
+    c.t = threadIdx.x / LL;
+    const int n = a.n, T = a.T, RB = a.tma_rb;
+    double* bufU = smt + exch2_doubles(T, LL);
+    double* bufV = bufU + (size_t)n * LL;
+    double* bufR = bufV + (size_t)n * LL;
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(bufR + (size_t)n * LL);
+    const unsigned barU = smem_u32(bars), barV = smem_u32(bars + 1);
+    const bool has_u2 = (a.u2 != nullptr);
+    const bool has_vel = (MODE == MODE_BURGERS) && (a.vel != a.u);
+    const bool has_acc = (a.accumulate != 0) && (MODE == MODE_BURGERS || MODE == MODE_P1);
+    const bool warp0 = threadIdx.x < 32;
+    const unsigned ntiles = a.ntiles, tiles_x = a.tiles_x;
+
+    if (threadIdx.x == 0) {
+        mbar_init(barU, 1);
+        mbar_init(barV, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    unsigned tile = blockIdx.x;
+    if (warp0 && tile < ntiles) {
+        const unsigned ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        tma_tile_in<THREE>(&maps.u, bufU, barU, (int)tx * LL, (int)ty, n, LL, RB);
+        if (has_u2 || has_vel) tma_tile_in<THREE>(&maps.v, bufV, barV, (int)tx * LL, (int)ty, n, LL, RB);
+    }
+    unsigned parity = 0;
+    for (; tile < ntiles; tile += gridDim.x, parity ^= 1u) {
+        const unsigned ty = tile / tiles_x, tx = tile - ty * tiles_x;
+        const unsigned next = tile + gridDim.x;
+        const bool more = next < ntiles;
+        const unsigned nty = more ? next / tiles_x : 0, ntx = more ? next - nty * tiles_x : 0;
+
+        // ---- this tile's chunk + halos: shared memory -> registers
+        double u[C + 6];
+        const bool lok = PER || c.t > 0, rok = PER || c.t < T - 1;
+        const int rl = ((c.t > 0) ? c.t * C : n) - 3;             // first row of the left halo
+        const int rr = (c.t < T - 1) ? (c.t + 1) * C : 0;         // first row of the right halo
+        mbar_wait(barU, parity);
+        chunk_get<LL>(bufU, c.t, c.l, u + 3);
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            u[k] = lok ? bufU[(size_t)(rl + k) * LL + c.l] : 0.0;
+            u[C + 3 + k] = rok ? bufU[(size_t)(rr + k) * LL + c.l] : 0.0;
+        }
+        if (has_u2) {
+            mbar_wait(barV, parity);
+            double w[C];
+            chunk_get<LL>(bufV, c.t, c.l, w);
+#pragma unroll
+            for (int j = 0; j < C; j++) u[j + 3] = u[j + 3] + w[j] * a.scale;
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (lok) u[k] = u[k] + bufV[(size_t)(rl + k) * LL + c.l] * a.scale;
+                if (rok) u[C + 3 + k] = u[C + 3 + k] + bufV[(size_t)(rr + k) * LL + c.l] * a.scale;
+            }
+        }
+        if (warp0) bulk_wait_read0();              // the store of the previous tile has left R
+        __syncthreads();                            // S1: U (and V with a second input) consumed, R free
+        if (warp0 && more) {
+            tma_tile_in<THREE>(&maps.u, bufU, barU, (int)ntx * LL, (int)nty, n, LL, RB);
+            if (has_u2) tma_tile_in<THREE>(&maps.v, bufV, barV, (int)ntx * LL, (int)nty, n, LL, RB);
+        }
+        if (MODE == MODE_BURGERS && !has_vel) chunk_put<LL>(bufV, c.t, c.l, u + 3);   // SELF: park the advecting field
+
+        double d1[C], d2[C];
+        line_core2<MODE, PER, NEED1>(u, a, a.s2, c, smt, d1, d2);
+
+        if (MODE == MODE_BURGERS) {
+            if (has_vel) mbar_wait(barV, parity);
+            double vv[C];
+            chunk_get<LL>(bufV, c.t, c.l, vv);
+#pragma unroll
+            for (int j = 0; j < C; j++) d2[j] = d2[j] - vv[j] * d1[j];
+        }
+        if (has_acc && a.accumulate < 0) {
+#pragma unroll
+            for (int j = 0; j < C; j++) { d1[j] = -d1[j]; d2[j] = -d2[j]; }
+        }
+        chunk_put<LL>(bufR, c.t, c.l, (MODE == MODE_P1) ? d1 : d2);
+        fence_async_smem();
+        __syncthreads();                            // S2: R complete, V consumed
+        if (warp0) {
+            tma_tile_out<THREE>(&maps.o, bufR, has_acc, (int)tx * LL, (int)ty, n, LL, RB);
+            if (has_vel && more) tma_tile_in<THREE>(&maps.v, bufV, barV, (int)ntx * LL, (int)nty, n, LL, RB);
+        }
+    }
+    if (warp0) bulk_wait0();
+}
+
+// ------------------------------------------------------------------------------------------------
 // x direction: lines contiguous in memory; the tile of L lines (L*n contiguous doubles) is staged through shared
 // memory.  Tile layout: line ll at ll*T*XB, point i at (i>>4)*XB + (i&15): 16-byte accesses are conflict-free both for
 // the coalesced side (a lane owns 2 consecutive points) and for the chunk side (a lane owns 16 consecutive points).
@@ -860,10 +1081,116 @@ int auto_pf_dist(K k, int threads, size_t smem) {
     return std::max(occ, 1) * sms;
 }
 
+long long g_tma_launches = 0;
+
+// ---- tensor maps of the TMA kernel: one per (array, geometry), cached (the fields of a run live at fixed addresses)
+using EncodeFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn tensor_map_encoder() {
+    static EncodeFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeFn>(p);
+        cudaGetLastError();
+    }
+    return fn;
+}
+
+size_t tma_smem_bytes(int T, int L, int n) { return (exch2_doubles(T, L) + (size_t)3 * n * L) * sizeof(double) + 64; }
+
+// field viewed as (inner, n, nouter) with strides (1, stride, outer_stride); box = L lines x rb rows
+bool tensor_map_for(const double* base, const Line2Args& a, long long nouter, CUtensorMap* out) {
+    if (!base) { std::memset(out, 0, sizeof(*out)); return true; }
+    using Key = std::tuple<const void*, long long, int, long long, long long, long long, int, int, int>;
+    static std::map<Key, CUtensorMap> cache;
+    const Key key{base, a.inner, a.n, nouter, a.stride, a.outer_stride, a.L, a.tma_rb, a.tma_l2};
+    auto it = cache.find(key);
+    if (it != cache.end()) { *out = it->second; return true; }
+    EncodeFn enc = tensor_map_encoder();
+    if (!enc) return false;
+    const bool three = nouter > 1;
+    cuuint64_t gdim[3] = {(cuuint64_t)a.inner, (cuuint64_t)a.n, (cuuint64_t)nouter};
+    cuuint64_t gstr[2] = {(cuuint64_t)a.stride * 8, (cuuint64_t)a.outer_stride * 8};
+    cuuint32_t box[3] = {(cuuint32_t)a.L, (cuuint32_t)a.tma_rb, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUtensorMap m;
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, three ? 3 : 2, const_cast<double*>(base), gdim, gstr, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                           a.tma_l2 == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B : (a.tma_l2 == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B :
+                           (a.tma_l2 == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE)),
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return false;
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = m;
+    *out = m;
+    return true;
+}
+
+template <int MODE, bool PER, bool NEED1, int LL, bool THREE>
+cudaError_t launch2_tma_k(const Line2Args& a, const TmaMaps& maps, cudaStream_t stream) {
+    auto k = lines2_strided_tma<MODE, PER, NEED1, LL, THREE>;
+    const size_t smem = tma_smem_bytes(a.T, LL, a.n);
+    static size_t set = 0;
+    if (smem > set) {
+        cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        set = smem;
+    }
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    // CTAs per SM: as many as the shared memory of this geometry allows (1 for 512-thread tiles)
+    static int occ = 0, occ_threads = 0;
+    static size_t occ_smem = 0;
+    const int threads = LL * a.T;
+    if (occ_threads != threads || occ_smem != smem) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem);
+        occ = std::max(occ, 1);
+        occ_threads = threads; occ_smem = smem;
+    }
+    const unsigned g = std::min<unsigned>(a.ntiles, (unsigned)(occ * sms));
+    k<<<g, threads, smem, stream>>>(a, maps);
+    return cudaGetLastError();
+}
+
+// returns cudaErrorNotSupported when the tensor maps cannot be built (the caller then uses the LSU kernels)
+template <int MODE, bool PER, bool NEED1>
+cudaError_t launch2_tma(const Line2Args& a_in, dim3 grid, cudaStream_t stream) {
+    Line2Args a = a_in;
+    a.tiles_x = grid.x;
+    a.ntiles = grid.x * grid.y;
+    const long long nouter = grid.y;
+    TmaMaps maps;
+    const double* second = a.u2 ? a.u2 : ((MODE == MODE_BURGERS && a.vel != a.u) ? a.vel : nullptr);
+    if (!tensor_map_for(a.u, a, nouter, &maps.u) || !tensor_map_for(second, a, nouter, &maps.v) ||
+        !tensor_map_for(a.out1, a, nouter, &maps.o))
+        return cudaErrorNotSupported;
+    const bool three = nouter > 1;
+    g_tma_launches++;
+    if (a.L == 4) return three ? launch2_tma_k<MODE, PER, NEED1, 4, true>(a, maps, stream) : launch2_tma_k<MODE, PER, NEED1, 4, false>(a, maps, stream);
+    if (a.L == 32) return three ? launch2_tma_k<MODE, PER, NEED1, 32, true>(a, maps, stream) : launch2_tma_k<MODE, PER, NEED1, 32, false>(a, maps, stream);
+    if (a.L == 8) return three ? launch2_tma_k<MODE, PER, NEED1, 8, true>(a, maps, stream) : launch2_tma_k<MODE, PER, NEED1, 8, false>(a, maps, stream);
+    return three ? launch2_tma_k<MODE, PER, NEED1, 16, true>(a, maps, stream) : launch2_tma_k<MODE, PER, NEED1, 16, false>(a, maps, stream);
+}
+
 template <int MODE, bool PER, bool NEED1>
 cudaError_t launch2(const Line2Args& a_in, bool contig, dim3 grid, cudaStream_t stream) {
     Line2Args a = a_in;
     const int threads = a.L * a.T;
+    if (!contig && a.tma && (MODE == MODE_P1 || MODE == MODE_P2 || MODE == MODE_BURGERS)) {
+        constexpr int M = (MODE == MODE_P1 || MODE == MODE_P2 || MODE == MODE_BURGERS) ? MODE : MODE_P1;
+        const cudaError_t e = launch2_tma<M, PER, NEED1>(a, grid, stream);
+        if (e != cudaErrorNotSupported) return e;
+    }
     size_t smem = exch2_doubles(a.T, a.L) * sizeof(double);
     if (contig) {
         const bool two = (MODE == MODE_P2_P1) || ((MODE == MODE_BURGERS) && (a.vel != a.u));
@@ -998,6 +1325,21 @@ bool lines2_eligible(const DevPlan& p, const Sys2& s1, const Sys2* s2, int n, lo
     *L_out = L;
     return true;
 }
+
+bool lines2_tma_eligible(int mode, const Line2Args& a) {
+    if (mode != MODE_P1 && mode != MODE_P2 && mode != MODE_BURGERS) return false;
+    if (a.L != 4 && a.L != 8 && a.L != 16 && a.L != 32) return false;
+    if (a.u2 && mode == MODE_BURGERS) return false;
+    if (a.L * a.T > 512 || a.n % CHUNK != 0) return false;
+    auto al = [](const void* q) { return (reinterpret_cast<size_t>(q) & 15) == 0; };
+    if (!(al(a.u) && al(a.u2) && al(a.vel) && al(a.out1))) return false;
+    if (a.stride % 2 != 0 || a.outer_stride % 2 != 0 || a.inner % a.L != 0) return false;
+    if (a.inner >= (1LL << 31) || (a.stride * 8) >= (1LL << 40) || (a.outer_stride * 8) >= (1LL << 40)) return false;
+    if (tma_smem_bytes(a.T, a.L, a.n) > 227 * 1024) return false;
+    return tensor_map_encoder() != nullptr;
+}
+
+long long lines2_tma_launches() { return g_tma_launches; }
 
 size_t lines2_persist_smem(int T, int L) { return (exch2_doubles(T, L) + (size_t)2 * T * pa_chunk_stride(L)) * sizeof(double); }
 

@@ -12,6 +12,9 @@ struct Line2Args {
     int pf_l1 = 0;                    // strided kernel: L1 prefetch of the velocity / accumulation target at kernel start
     int persist = 0;                  // strided kernel: persistent CTAs with cp.async staging
     unsigned ntiles = 0, tiles_x = 0; // persistent kernel: tile count and tiles per outer block
+    int tma = 0;                      // strided kernel: persistent CTAs fed and drained by the TMA unit (lines2_strided_tma)
+    int tma_rb = 0;                   // rows per TMA box
+    int tma_l2 = 0;                   // L2 promotion of the tensor maps (0 none, 1/2/3: 64/128/256 bytes)
     double scale = 0.0;               // input is u + scale * u2 when u2 != nullptr
     long long stride = 1;             // distance between consecutive points of a line (strided kernel)
     long long inner = 1;              // tile (bx, by) starts at by * outer_stride + bx * L; lines by * inner + bx * L + l
@@ -42,6 +45,8 @@ bool lines2_eligible(const DevPlan& p, const Sys2& s1, const Sys2* s2, int n, lo
                      int L_override, int* L_out);
 int lines2_xstride(int T, int L);
 size_t lines2_persist_smem(int T, int L);
+long long lines2_tma_launches();
+bool lines2_tma_eligible(int mode, const Line2Args& a);   // geometry, alignment and shared-memory budget of the TMA kernel
 cudaError_t launch_lines2(int mode, const Line2Args& a, bool periodic, bool need1, bool contig, long long nlines,
                           long long inner, cudaStream_t s);
 
