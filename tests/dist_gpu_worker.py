@@ -24,7 +24,7 @@ def main():
         k, v = kv.split("=")
         tl.check(tl.load().tlab_gpu_set_tuning(k.encode(), int(v)))
     mpi.init_from_torch_distributed()
-    nx, ny, nz = 32, 32, 32
+    nx, ny, nz = [int(v) for v in os.environ.get("TLAB_SHAPE", "32,32,32").split(",")]
     kmax, koff = mpi.slab(nz, rank, world)
     x, y, z = grid_periodic(nx), grid_tanh(ny), grid_periodic(nz)
     gg = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, False, name="y"), opr.FdmPlan(z, True, True, name="z")]
@@ -63,11 +63,11 @@ def main():
         errs = [rel_l2(a, b) for a, b in zip(gathered, ref)]
         import ctypes
         cnt = {}
-        for key in ("p2p_exchanges", "nccl_exchanges"):
+        for key in ("p2p_exchanges", "nccl_exchanges", "splitz_ops"):
             c = ctypes.c_longlong()
             tl.check(tl.load().tlab_gpu_get_counter(key.encode(), ctypes.byref(c)))
             cnt[key] = c.value
-        print("DIST_PATH p2p=%d nccl=%d" % (cnt["p2p_exchanges"], cnt["nccl_exchanges"]), flush=True)
+        print("DIST_PATH p2p=%d nccl=%d splitz=%d" % (cnt["p2p_exchanges"], cnt["nccl_exchanges"], cnt["splitz_ops"]), flush=True)
         print("DIST_ERRS", " ".join("%.3e" % e for e in errs), flush=True)
         assert max(errs) <= 1e-11, errs
     g.close()

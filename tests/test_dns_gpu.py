@@ -153,14 +153,14 @@ def test_case01_shape_two_dimensional_step(cuda):
 
 
 @pytest.mark.parametrize("tune", [{"fuse": 1}, {"fuse": 1, "pf_next": 1}, {"persist": 1}, {"pf_dist": 3}, {"fast": 0},
-                                  {"tma": 1}])
+                                  {"tma": 1}, {"poisson_split": 0}, {"poisson_split": 1}])
 def test_tuning_variants_give_the_same_step(cuda, tune):
     """The optional kernel variants (fused multi-field Burgers launch, next-field / next-tile L2 prefetch, persistent
     cp.async staging, general kernels) are alternative schedules of the same arithmetic: one RK step on full chunks
     (64 x 64 x 32) must agree with the oracle like the default path does."""
     from tlab_b200 import lib as tl
     L = tl.load()
-    defaults = {"fuse": 0, "pf_next": 0, "persist": 0, "pf_dist": -1, "fast": 1, "tma": 0}
+    defaults = {"fuse": 0, "pf_next": 0, "persist": 0, "pf_dist": -1, "fast": 1, "tma": 0, "poisson_split": -1}
     try:
         for k, v in tune.items():
             tl.check(L.tlab_gpu_set_tuning(k.encode(), v))
@@ -201,3 +201,33 @@ def test_step_through_the_tma_kernels(cuda, shape, lines):
     for i in range(3):
         assert rel_l2(g.get("q%d" % (i + 1)), o.q[i]) <= 1e-11
     assert rel_l2(g.get("s1"), o.s[0]) <= 1e-11
+
+
+@pytest.mark.parametrize("shape,pv", [((32, 32, 256), 2), ((16, 32, 192), 2), ((16, 32, 512), 4), ((64, 16, 384), 3)])
+def test_split_z_operators_on_virtual_slabs(cuda, shape, pv):
+    """The split-z kernels of splitz.cu (z operators of a z-split domain without transposes: halo planes and chunk ends
+    exchanged between neighbouring slabs) run over pv virtual slabs of one field on one GPU: the RK step must agree with
+    the oracle, and with the whole-line kernels to round-off.  Slab thicknesses 128 / 96 (the minimum: 6 chunks) planes."""
+    import ctypes
+    from tlab_b200 import lib as tl
+    L = tl.load()
+    o, g = _pair(*shape, "tanh")
+    o.runge_kutta(1e-3)
+    g.runge_kutta(1e-3)
+    whole = [g.get("q%d" % (i + 1)) for i in range(3)] + [g.get("s1")]
+    before = ctypes.c_longlong(0)
+    tl.check(L.tlab_gpu_get_counter(b"splitz_ops", ctypes.byref(before)))
+    try:
+        tl.check(L.tlab_gpu_set_tuning(b"split_emulate", pv))
+        _, g2 = _pair(*shape, "tanh")
+        g2.runge_kutta(1e-3)
+    finally:
+        tl.check(L.tlab_gpu_set_tuning(b"split_emulate", 0))
+    after = ctypes.c_longlong(0)
+    tl.check(L.tlab_gpu_get_counter(b"splitz_ops", ctypes.byref(after)))
+    assert after.value - before.value == 5 * 6, "the split-z kernels did not run"
+    split = [g2.get("q%d" % (i + 1)) for i in range(3)] + [g2.get("s1")]
+    ref = o.q + o.s
+    for a, b, c in zip(split, whole, ref):
+        assert rel_l2(a, c) <= 1e-11
+        assert rel_l2(a, b) <= 1e-13

@@ -2,6 +2,7 @@
 #include "../../include/tlab_gpu.h"
 #include "context.h"
 #include "trp.h"
+#include "splitz.h"
 #include <cstring>
 #include <algorithm>
 #include <cstdio>
@@ -379,6 +380,8 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "persist")) ctx().tune_persist = value;
     else if (!std::strcmp(key, "tma")) ctx().tune_tma = value;
     else if (!std::strcmp(key, "tma_l2")) ctx().tune_tma_l2 = value;
+    else if (!std::strcmp(key, "splitz")) ctx().tune_splitz = value;
+    else if (!std::strcmp(key, "split_emulate")) ctx().tune_split_emulate = value;
     else if (!std::strcmp(key, "pf_l1")) ctx().tune_pf_l1 = value;
     else if (!std::strcmp(key, "fuse")) ctx().tune_fuse = value;
     else if (!std::strcmp(key, "overlap")) ctx().tune_overlap = value;
@@ -388,6 +391,7 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "p2p_dma")) trp().p2p_dma = (value != 0);
     else if (!std::strcmp(key, "pf_next")) ctx().tune_pf_next = value;
     else if (!std::strcmp(key, "poisson_minb")) ctx().tune_poisson_minb = value;
+    else if (!std::strcmp(key, "poisson_split")) ctx().tune_poisson_split = value;
     else if (!std::strcmp(key, "poisson_factors")) ctx().tune_poisson_factors = value;
     else return fail(TLAB_ERR_OPTION, std::string("unknown tuning key ") + key);
     return 0;
@@ -398,6 +402,7 @@ int tlab_gpu_get_counter(const char* key, long long* value) {
     if (!std::strcmp(key, "fast_launches")) *value = ctx().fast_launches;
     else if (!std::strcmp(key, "general_launches")) *value = ctx().general_launches;
     else if (!std::strcmp(key, "tma_launches")) *value = lines2_tma_launches();
+    else if (!std::strcmp(key, "splitz_ops")) *value = splitz().ops;
     else if (!std::strcmp(key, "p2p_exchanges")) *value = trp().p2p_exchanges;
     else if (!std::strcmp(key, "nccl_exchanges")) *value = trp().nccl_exchanges;
     else return fail(TLAB_ERR_OPTION, std::string("unknown counter ") + key);

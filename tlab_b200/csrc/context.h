@@ -26,6 +26,7 @@ struct Context {
     int tune_fast = 1;        // 1: use the fast line kernels (lines2.cu) whenever the geometry allows
     int tune_pf_dist = -1;
     int tune_poisson_factors = 1;  // keep the per-mode LU factors of the Poisson y systems (8 more planes) instead of refactorising
+    int tune_poisson_split = -1;  // Poisson y solves: one thread per component instead of per mode (-1: when there are few modes)
     int tune_poisson_minb = 3;  // resident CTAs per SM the Poisson y kernel is compiled for (register budget)
     int tune_pf_next = 0;     // fused Burgers launch: L2 prefetch of the tile's next field
     int tune_fuse = 0;        // RHS: one fused Burgers launch per direction (fields sharing the advecting velocity)
@@ -33,6 +34,8 @@ struct Context {
     int tune_overlap = 1;     // split domain: z operators on a second stream, overlapped with the x/y operators
     int tune_pf_l1 = 0;       // strided fast kernels: early L1 prefetch of the operands needed after the solve
     int tune_persist = 0;     // strided fast kernels: persistent CTAs with asynchronous staging
+    int tune_splitz = 1;      // split domain: z operators on the slabs with halo / chunk-end exchange (splitz.cu) instead of transposes
+    int tune_split_emulate = 0;  // P = 1: run the split-z kernels over this many virtual slabs of the field (tests)
     int tune_tma_l2 = 0;      // L2 promotion of the tensor maps of the TMA kernels
     int tune_tma = 0;         // strided fast kernels: persistent CTAs fed and drained by the TMA unit (tensor maps, reduce-add
                               // stores).  Off: measured slower than the LSU kernels, the TMA unit sustains ~20 GB/s per SM on

@@ -15,6 +15,7 @@
 #include "context.h"
 #include "poisson.h"
 #include "trp.h"
+#include "splitz.h"
 #include <vector>
 #include <string>
 #include <cstring>
@@ -237,7 +238,20 @@ struct Dns {
     }
 
     // Burgers operator along z, accumulated into out; with a split domain through the z pencils
+    // split-z path (splitz.cu): the slabs stay where they are, neighbours exchange halo planes and chunk ends.
+    // P == 1 with the tuning key split_emulate = Pv > 1 runs the same kernels over Pv virtual slabs of the field (tests).
+    bool use_split(int is) {
+        if (nzg <= 1 || !ctx().tune_splitz) return false;
+        if (P == 1) {
+            const int pv = ctx().tune_split_emulate;
+            if (pv < 2 || nz % pv) return false;
+            if (splitz().init((long long)nx * ny, nz / pv, nz, pv, 0, pv)) return false;
+        } else if (!splitz().ready || splitz().emulate > 1) return false;
+        return splitz().eligible(g[2], is);
+    }
+
     int burgers_z(int is, const double* sf, const double* w, double* out, bool self) {
+        if (use_split(is)) return splitz().burgers(g[2], is, sf, w, out, +1);
         if (P == 1) return run_burgers(3, is, nx, ny, nz, 0, g[2], sf, w, out, +1);
         const long long nxy = (long long)nx * ny;
         const int nl = (int)(nxy / P);
@@ -253,6 +267,7 @@ struct Dns {
 
     // out (+|-)= d/dz (a + scale*a2)
     int partial_z(const double* a, const double* a2, double scale, double* out, int accumulate) {
+        if (use_split(-1)) return splitz().partial(g[2], a, a2, scale, out, accumulate);
         if (P == 1) return run_partial(3, TLAB_OPR_P1, nx, ny, nz, 0, g[2], a, out, nullptr, a2, scale, accumulate);
         const long long nxy = (long long)nx * ny;
         const int nl = (int)(nxy / P);
@@ -358,7 +373,9 @@ struct Dns {
     }
 
     int rhs(double dte) {
-        if (P > 1 && nzg > 1 && trp().zstream && ctx().tune_overlap) return rhs_overlapped(dte);
+        bool split = true;
+        for (int is = 0; is <= ns && split; is++) split = use_split(is);
+        if (P > 1 && nzg > 1 && trp().zstream && ctx().tune_overlap && !split) return rhs_overlapped(dte);
         cudaStream_t st = ctx().stream;
         const int b0 = 0;   // bcs = 0: biased, non-zero (rhs_global_incompressible_1.f90:67)
         int rc = 0;
@@ -369,7 +386,7 @@ struct Dns {
             launches++;
         };
         double *u = q[0], *v = q[1], *w = q[2];
-        if (P > 1 && nzg > 1) {     // transposed w is shared by the four z operators (tmp6 of the reference)
+        if (P > 1 && nzg > 1 && !split) {     // transposed w is shared by the four z operators (tmp6 of the reference)
             if ((rc = trp().forward(w, nullptr, 0.0, zw, (long long)nx * ny, nz))) return rc;
         }
         // hq_i += Bx(q_i,u) + By(q_i,v) + Bz(q_i,w), hs += ... (:98-162).  Grouped by direction, so that the fields that share
@@ -378,7 +395,7 @@ struct Dns {
         const double* sf[4] = {u, v, w, ns > 0 ? s[0] : nullptr};
         double* outs[4] = {hq[0], hq[1], hq[2], ns > 0 ? hs[0] : nullptr};
         const int isv[4] = {0, 0, 0, 1};
-        const bool fuse_z = (P == 1);
+        const bool fuse_z = (P == 1) && !split;
         for (int dir = 1; dir <= 3 && !rc; dir++) {
             if (dir == 3 && !fuse_z) break;
             rc = run_burgers_multi(dir, nfields, isv, sf, q[dir - 1], outs, nx, ny, nz, g[dir - 1], &launches);
@@ -541,6 +558,9 @@ int tlab_dns_create(const tlab_dns_params* prm, tlab_plan_t gx, tlab_plan_t gy, 
         // peer-memory transposes: publish the pencil buffers to the other ranks (collective, same order everywhere)
         if (!rc) rc = cuda_check(cudaStreamSynchronize(ctx().stream), "tlab_dns_create");
         for (double* b : {d.zs, d.zw, d.zr, d.c2}) if (!rc) rc = trp().register_buffer(b);
+        // split-z operators: exchange blocks for halo planes and chunk ends (collective; not eligible -> transposes stay)
+        if (!rc && ctx().tune_splitz && d.nzg > 1)
+            rc = splitz().init((long long)d.nx * d.ny, d.nz, d.nzg, P, trp().rank, 0);
     }
     if (!rc && bbackground_host)
         rc = cuda_check(cudaMemcpyAsync(d.bbackground, bbackground_host, d.ny * sizeof(double), cudaMemcpyHostToDevice, ctx().stream), "bbackground");

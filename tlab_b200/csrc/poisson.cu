@@ -295,7 +295,7 @@ __device__ void int1_solve(const Int1Dev& P, double lam, const LineRef (&f)[NL],
     }
 }
 
-template <int MINB, bool FAC>
+template <int MINB, bool FAC, int NL>
 __global__ void poisson_modes_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv);
 
 struct ModeGeom {
@@ -379,12 +379,18 @@ __global__ void poisson_fundamental_kernel(PoissonDev D) {
 // per call: regular modes, Neumann/Neumann (OPR_ODE2_Factorize_NN)
 __device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ cf, double* __restrict__ cv, int i, int k);
 
-template <int MINB, bool FAC>
+// NL = 2: one thread per mode, both components (real, imaginary) of the mode in the same thread, which shares the factor
+// and fundamental-solution loads.  NL = 1: one thread per component (adjacent lanes = re, im of a mode: unit-stride
+// accesses of the complex lines and twice the threads) -- for few modes per GPU (kx-split stage of a split domain),
+// where the per-mode marches along y are latency-bound and there are not enough of them to fill the SMs.
+template <int MINB, bool FAC, int NL>
 __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv) {
-    const long long m = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long h = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long m = (NL == 1) ? (h >> 1) : h;
+    const int l0 = (NL == 1) ? (int)(h & 1) : 0;
     if (m >= D.nmodes) return;
     const int i = (int)(m % D.nxh), k = (int)(m / D.nxh);
-    if (mode_is_singular(D, i, k)) { poisson_singular_mode(D, cf, cv, i, k); return; }
+    if (mode_is_singular(D, i, k)) { if (l0 == 0) poisson_singular_mode(D, cf, cv, i, k); return; }
     const double lam = sqrt(D.lambda[m]);
     const long long NM = D.nmodes;
     const long long plane_sz = D.plane_sz;
@@ -392,36 +398,41 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
     // complex lines of this mode inside c(kx, y, kz): re/im interleaved
     const long long off = 2 * ((long long)i + (long long)D.nxh * D.ny * k);
     const long long js = 2LL * D.nxh;
-    LineRef fre = {cf + off, js}, fim = {cf + off + 1, js};
-    LineRef vre = {cv + off, js}, vim = {cv + off + 1, js};
+    LineRef fl[NL], vl[NL], ysc[NL];
+    double bcb[NL], bct[NL], zero[NL];
     const double norm = D.norm;
-    const double bcb[2] = {fre.get(1) * norm, fim.get(1) * norm};      // bcs(1:2,1) = f(1:2)
-    const double bct[2] = {fre.get(n) * norm, fim.get(n) * norm};      // bcs(1:2,2) = f(2ny-1:2ny)
-    LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, D.ny, m), plane(D.scr + 1 * plane_sz, D.ny, m)};
+#pragma unroll
+    for (int l = 0; l < NL; l++) {
+        fl[l] = LineRef{cf + off + l0 + l, js};
+        vl[l] = LineRef{cv + off + l0 + l, js};
+        ysc[l] = plane(D.scr + (l0 + l) * plane_sz, D.ny, m);
+        bcb[l] = fl[l].get(1) * norm;      // bcs(1:2,1) = f(1:2)
+        bct[l] = fl[l].get(n) * norm;      // bcs(1:2,2) = f(2ny-1:2ny)
+        zero[l] = 0.0;
+    }
     LineRef csc = plane(D.scr + 2 * plane_sz, D.ny, m), dsc = plane(D.scr + 3 * plane_sz, D.ny, m),
             esc = plane(D.scr + 4 * plane_sz, D.ny, m);
-    const double zero2[2] = {0.0, 0.0};
     // v^(0): v' + lam v = f, f(n) = 0, v(1) = 0
     {
-        LineRef f[2] = {fre, fim}, res[2] = {vre, vim};
         if (FAC)
-            int1_solve<2, 2>(D.smin, lam, f, norm, zero2, zero2, res, ysc, plane(D.fac + 2 * plane_sz, D.ny, m),
-                             plane(D.fac + 3 * plane_sz, D.ny, m), esc, nullptr, plane(D.fac + 0 * plane_sz, D.ny, m),
-                             plane(D.fac + 1 * plane_sz, D.ny, m));
+            int1_solve<NL, 2>(D.smin, lam, fl, norm, zero, zero, vl, ysc, plane(D.fac + 2 * plane_sz, D.ny, m),
+                              plane(D.fac + 3 * plane_sz, D.ny, m), esc, nullptr, plane(D.fac + 0 * plane_sz, D.ny, m),
+                              plane(D.fac + 1 * plane_sz, D.ny, m));
         else
-            int1_solve<2>(D.smin, lam, f, norm, zero2, zero2, res, ysc, csc, dsc, esc, nullptr);
+            int1_solve<NL>(D.smin, lam, fl, norm, zero, zero, vl, ysc, csc, dsc, esc, nullptr);
     }
     // u^(0): u' - lam u = v, u(n) = 0  (written over the forcing, which is no longer needed)
-    double du0[2];
+    double du0[NL];
     {
-        LineRef f[2] = {vre, vim}, res[2] = {fre, fim};
-        const double fend[2] = {vre.get(1), vim.get(1)};
+        double fend[NL];
+#pragma unroll
+        for (int l = 0; l < NL; l++) fend[l] = vl[l].get(1);
         if (FAC)
-            int1_solve<2, 2>(D.smax, -lam, f, 1.0, fend, zero2, res, ysc, plane(D.fac + 6 * plane_sz, D.ny, m),
-                             plane(D.fac + 7 * plane_sz, D.ny, m), esc, du0, plane(D.fac + 4 * plane_sz, D.ny, m),
-                             plane(D.fac + 5 * plane_sz, D.ny, m));
+            int1_solve<NL, 2>(D.smax, -lam, vl, 1.0, fend, zero, fl, ysc, plane(D.fac + 6 * plane_sz, D.ny, m),
+                              plane(D.fac + 7 * plane_sz, D.ny, m), esc, du0, plane(D.fac + 4 * plane_sz, D.ny, m),
+                              plane(D.fac + 5 * plane_sz, D.ny, m));
         else
-            int1_solve<2>(D.smax, -lam, f, 1.0, fend, zero2, res, ysc, csc, dsc, esc, du0);
+            int1_solve<NL>(D.smax, -lam, vl, 1.0, fend, zero, fl, ysc, csc, dsc, esc, du0);
     }
     // constraint and boundary conditions (opr_odes.f90:350-367)
     const double* A = D.amat;
@@ -431,10 +442,10 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
     LineRef v1 = plane(D.fund + 0 * plane_sz, D.ny, m), em = plane(D.fund + 1 * plane_sz, D.ny, m);
     LineRef u1 = plane(D.fund + 2 * plane_sz, D.ny, m), sp = plane(D.fund + 3 * plane_sz, D.ny, m),
             ep = plane(D.fund + 4 * plane_sz, D.ny, m);
-    LineRef ul[2] = {fre, fim}, vl[2] = {vre, vim};
-    double fn[2], v_1[2], u_n[2];
+    const LineRef (&ul)[NL] = fl;
+    double fn[NL], v_1[NL], u_n[NL];
 #pragma unroll
-    for (int l = 0; l < 2; l++) {
+    for (int l = 0; l < NL; l++) {
         v_1[l] = (bcb[l] - lam * ul[l].get(1)) / a11;
         u_n[l] = (bct[l] - vl[l].get(n) - a21 * v_1[l]) / a22;
         fn[l] = (bct[l] - du0[l] - a31 * v_1[l] - a32 * u_n[l]) / a33;
@@ -444,7 +455,7 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
     // rows n, n-1 .. 2, 1: the five fundamental lines are read once for both components, CRB rows per batch
     constexpr int CRB = 4;
     for (int r0 = n; r0 >= 1; r0 -= CRB) {
-        double fu[5][CRB], uu0[2][CRB], vv0[2][CRB];
+        double fu[5][CRB], uu0[NL][CRB], vv0[NL][CRB];
 #pragma unroll
         for (int j = 0; j < CRB; j++) {
             const int r = r0 - j;
@@ -455,7 +466,7 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
             fu[3][j] = (ok && r < n) ? sp.get(r) : 0.0;
             fu[4][j] = (ok && r < n) ? ep.get(r) : 0.0;
 #pragma unroll
-            for (int l = 0; l < 2; l++) {
+            for (int l = 0; l < NL; l++) {
                 uu0[l][j] = (ok && r < n) ? ul[l].get(r) : 0.0;
                 vv0[l][j] = (ok && r > 1) ? vl[l].get(r) : 0.0;
             }
@@ -465,7 +476,7 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
             const int r = r0 - j;
             if (r < 1) break;
 #pragma unroll
-            for (int l = 0; l < 2; l++) {
+            for (int l = 0; l < NL; l++) {
                 double uu, vv;
                 if (r == n) {
                     uu = u_n[l];                 // u(:, nx) has been replaced by the boundary value
@@ -632,16 +643,28 @@ int make_side(const HostDer& der1, int bc, Int1Dev& S, std::vector<void*>& alloc
 
 }  // namespace
 
-static void launch_modes(const PoissonDev& D, double* cf, double* cv, unsigned blocks, int threads, cudaStream_t st) {
+// One thread per mode, or (tuning key poisson_split: 1 always, 0 never, -1 when the modes of this GPU would fill less than
+// four waves of CTAs) one thread per component; the latter needs the stored factor lines.
+static void launch_modes(const PoissonDev& D, double* cf, double* cv, cudaStream_t st) {
     const int minb = ctx().tune_poisson_minb;
-    if (D.fac) {
-        if (minb == 4) poisson_modes_kernel<4, true><<<blocks, threads, 0, st>>>(D, cf, cv);
-        else if (minb == 2) poisson_modes_kernel<2, true><<<blocks, threads, 0, st>>>(D, cf, cv);
-        else poisson_modes_kernel<3, true><<<blocks, threads, 0, st>>>(D, cf, cv);
+    const int threads = 128;
+    int split = ctx().tune_poisson_split;
+    if (split < 0) split = (D.nmodes < 4LL * 148 * 4 * threads) ? 1 : 0;
+    if (!D.fac) split = 0;
+    const long long work = split ? 2 * D.nmodes : D.nmodes;
+    const unsigned blocks = (unsigned)((work + threads - 1) / threads);
+    if (split) {
+        if (minb == 4) poisson_modes_kernel<4, true, 1><<<blocks, threads, 0, st>>>(D, cf, cv);
+        else if (minb == 2) poisson_modes_kernel<2, true, 1><<<blocks, threads, 0, st>>>(D, cf, cv);
+        else poisson_modes_kernel<3, true, 1><<<blocks, threads, 0, st>>>(D, cf, cv);
+    } else if (D.fac) {
+        if (minb == 4) poisson_modes_kernel<4, true, 2><<<blocks, threads, 0, st>>>(D, cf, cv);
+        else if (minb == 2) poisson_modes_kernel<2, true, 2><<<blocks, threads, 0, st>>>(D, cf, cv);
+        else poisson_modes_kernel<3, true, 2><<<blocks, threads, 0, st>>>(D, cf, cv);
     } else {
-        if (minb == 4) poisson_modes_kernel<4, false><<<blocks, threads, 0, st>>>(D, cf, cv);
-        else if (minb == 2) poisson_modes_kernel<2, false><<<blocks, threads, 0, st>>>(D, cf, cv);
-        else poisson_modes_kernel<3, false><<<blocks, threads, 0, st>>>(D, cf, cv);
+        if (minb == 4) poisson_modes_kernel<4, false, 2><<<blocks, threads, 0, st>>>(D, cf, cv);
+        else if (minb == 2) poisson_modes_kernel<2, false, 2><<<blocks, threads, 0, st>>>(D, cf, cv);
+        else poisson_modes_kernel<3, false, 2><<<blocks, threads, 0, st>>>(D, cf, cv);
     }
 }
 
@@ -819,9 +842,7 @@ int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const do
         }
         {
             ProfScope ps(PC_POISSON_Y);
-            const int threads = 128;
-            const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
-            launch_modes(D, cpa, cpb, blocks, threads, st);
+            launch_modes(D, cpa, cpb, st);
             if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
         }
         {
@@ -845,9 +866,7 @@ int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const do
     if (int rc = fft_z(c1, P > 1 ? c2 : nullptr, CUFFT_FORWARD)) return rc;
     {
         ProfScope ps(PC_POISSON_Y);
-        const int threads = 128;
-        const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
-        launch_modes(D, c1, c2, blocks, threads, st);
+        launch_modes(D, c1, c2, st);
         if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
     }
     if (int rc = fft_z(c1, c3, CUFFT_INVERSE)) return rc;

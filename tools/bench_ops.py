@@ -29,6 +29,8 @@ def main():
     ap.add_argument("--fast", default="1", help="comma list of 0/1: general kernels (lines.cu) / fast kernels (lines2.cu)")
     ap.add_argument("--pf-dist", default="-1", help="comma list of L2 prefetch distances of the fast kernels (-1 auto, 0 off)")
     ap.add_argument("--persist", default="1", help="comma list of 0/1: persistent cp.async variant of the fast y/z kernels")
+    ap.add_argument("--tune", default="", help="further tuning keys, e.g. poisson_split=1,tma=1")
+    ap.add_argument("--no-lines", action="store_true", help="skip the line operators (Poisson only)")
     ap.add_argument("--prefetch", type=int, default=-1, help="1/0: force the persistent cp.async variant of the y/z kernels")
     args = ap.parse_args()
     import torch
@@ -36,6 +38,9 @@ def main():
     L = tl.load()
     if args.prefetch >= 0:
         tl.check(L.tlab_gpu_set_tuning(b"prefetch", args.prefetch))
+    for kv in [t for t in args.tune.split(",") if t]:
+        k, v = kv.split("=")
+        tl.check(L.tlab_gpu_set_tuning(k.encode(), int(v)))
     dev = torch.device("cuda:0")
     nx, ny, nz = [int(v) for v in args.shape.split(",")]
     N = nx * ny * nz
@@ -83,7 +88,7 @@ def main():
               for pf in ([int(s) for s in args.pf_dist.split(",")] if fast else [0])
               for ps in ([int(s) for s in args.persist.split(",")] if fast else [0])]
     for lx, lyz, fast, pf, ps in combos:
-        if True:
+        if not args.no_lines:
             tl.check(L.tlab_gpu_set_tuning(b"lines_x", lx))
             tl.check(L.tlab_gpu_set_tuning(b"lines_yz", lyz))
             tl.check(L.tlab_gpu_set_tuning(b"fast", fast))
@@ -103,9 +108,19 @@ def main():
         hb = torch.zeros(nx * nz, dtype=torch.float64, device=dev)
         ht = torch.zeros_like(hb)
         p = u.clone()
-        for minb in (4, 3, 2):
+        for minb, split in ((3, 0), (3, 1), (4, 1), (2, 1)):
             tl.check(L.tlab_gpu_set_tuning(b"poisson_minb", minb))
-            timeit(lambda: opr.OPR_Poisson(nx, ny, nz, 3, p, t1, t2, hb, ht, r1), 120 * N, "OPR_Poisson (120 B/pt model) minb=%d" % minb)
+            tl.check(L.tlab_gpu_set_tuning(b"poisson_split", split))
+            tl.check(L.tlab_gpu_profile(1))
+            timeit(lambda: opr.OPR_Poisson(nx, ny, nz, 3, p, t1, t2, hb, ht, r1), 120 * N,
+                   "OPR_Poisson (120 B/pt model) minb=%d split=%d" % (minb, split))
+            ms = (ctypes.c_double * 16)()
+            cn = (ctypes.c_int * 16)()
+            tl.check(L.tlab_gpu_profile_report(ms, cn, 16))
+            tl.check(L.tlab_gpu_profile(0))
+            if rows and cn[8]:
+                rows[-1]["poisson_y_ms"] = ms[8] / cn[8]
+                print("      y solves %.3f ms per call" % (ms[8] / cn[8]), flush=True)
             if rows:
                 rows[-1]["GBs_at_24B_floor"] = rows[-1]["GBs"] * 24.0 / 120.0
     if args.json:
