@@ -26,6 +26,7 @@ struct Context {
     int tune_fast = 1;        // 1: use the fast line kernels (lines2.cu) whenever the geometry allows
     int tune_pf_dist = -1;
     int tune_poisson_factors = 1;  // keep the per-mode LU factors of the Poisson y systems (8 more planes) instead of refactorising
+    int tune_poisson_il = 0;      // Poisson: per-mode planes that are read together interleaved row by row (set before OPR_Elliptic_Initialize)
     int tune_poisson_split = -1;  // Poisson y solves: one thread per component instead of per mode (-1: when there are few modes)
     int tune_poisson_minb = 3;  // resident CTAs per SM the Poisson y kernel is compiled for (register budget)
     int tune_pf_next = 0;     // fused Burgers launch: L2 prefetch of the tile's next field

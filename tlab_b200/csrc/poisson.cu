@@ -307,10 +307,24 @@ __device__ __forceinline__ bool mode_is_singular(const PoissonDev& D, int i, int
     return (i == D.i_sing0 || i == D.i_sing1) && (k == D.k_sing0 || k == D.k_sing1);
 }
 
-// scratch planes, blocked by 32 modes: element (row, m) at ((m / 32) * ny + row) * 32 + m % 32, so that a warp
-// marching along y streams through one contiguous region per array (DRAM page and TLB friendly)
-__device__ __forceinline__ LineRef plane(double* base, int ny, long long m) {
-    LineRef r; r.p = base + (m >> 5) * ((long long)ny * 32) + (m & 31); r.js = 32; return r;
+// per-mode planes (fundamental solutions, scratch, LU factors), blocked by 32 modes so that a warp marching along y
+// streams through contiguous memory.  Planes that are read together are interleaved row by row inside a block (D.il):
+// the five fundamental lines, the factor lines in the pairs a sweep reads, the two scratch lines of the components --
+// element (row, k, m) of a group of g planes at (((m / 32) * ny + row) * g + k) * 32 + m % 32.  A warp then follows three
+// address streams per sweep instead of five to seven (fewer pages and DRAM rows open at a time).
+enum { P_FUND = 0, P_SCR = 1, P_FAC = 2 };
+__device__ __forceinline__ LineRef plane(const PoissonDev& D, int which, int k, long long m) {
+    double* base = (which == P_FUND) ? D.fund : (which == P_SCR ? D.scr : D.fac);
+    int g0, gn;
+    if (!D.il) { g0 = k; gn = 1; }
+    else if (which == P_FUND) { g0 = 0; gn = 5; }
+    else if (which == P_FAC) { g0 = k & ~1; gn = 2; }
+    else if (k < 2) { g0 = 0; gn = 2; }
+    else { g0 = k; gn = 1; }
+    LineRef r;
+    r.p = base + (long long)g0 * D.plane_sz + ((m >> 5) * ((long long)D.ny * gn) + (k - g0)) * 32 + (m & 31);
+    r.js = 32LL * gn;
+    return r;
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -328,38 +342,38 @@ __global__ void poisson_fundamental_kernel(PoissonDev D) {
     {
         LineRef f[2] = {{nullptr, 0}, {nullptr, 0}};
         double fend[2] = {1.0, 0.0}, bc[2] = {0.0, 1.0};
-        LineRef res[2] = {plane(D.fund + 0 * plane_sz, D.ny, m), plane(D.fund + 1 * plane_sz, D.ny, m)};
-        LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, D.ny, m), plane(D.scr + 1 * plane_sz, D.ny, m)};
+        LineRef res[2] = {plane(D, P_FUND, 0, m), plane(D, P_FUND, 1, m)};
+        LineRef ysc[2] = {plane(D, P_SCR, 0, m), plane(D, P_SCR, 1, m)};
         if (D.fac)
-            int1_solve<2, 1>(D.smin, lam, f, 1.0, fend, bc, res, ysc, plane(D.fac + 2 * plane_sz, D.ny, m),
-                             plane(D.fac + 3 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), nullptr,
-                             plane(D.fac + 0 * plane_sz, D.ny, m), plane(D.fac + 1 * plane_sz, D.ny, m));
+            int1_solve<2, 1>(D.smin, lam, f, 1.0, fend, bc, res, ysc, plane(D, P_FAC, 2, m),
+                             plane(D, P_FAC, 3, m), plane(D, P_SCR, 5, m), nullptr,
+                             plane(D, P_FAC, 0, m), plane(D, P_FAC, 1, m));
         else
-            int1_solve<2>(D.smin, lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, D.ny, m),
-                          plane(D.scr + 4 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), nullptr);
+            int1_solve<2>(D.smin, lam, f, 1.0, fend, bc, res, ysc, plane(D, P_SCR, 3, m),
+                          plane(D, P_SCR, 4, m), plane(D, P_SCR, 5, m), nullptr);
     }
     // stage 2: u1, s+, e+ from (v1, e-, 0) with values (0, 0, 1) at row n
     double der[3];
     {
-        LineRef v1 = plane(D.fund + 0 * plane_sz, D.ny, m), em = plane(D.fund + 1 * plane_sz, D.ny, m);
+        LineRef v1 = plane(D, P_FUND, 0, m), em = plane(D, P_FUND, 1, m);
         LineRef f[3] = {v1, em, {nullptr, 0}};
         double fend[3] = {v1.get(1), em.get(1), 0.0}, bc[3] = {0.0, 0.0, 1.0};
-        LineRef res[3] = {plane(D.fund + 2 * plane_sz, D.ny, m), plane(D.fund + 3 * plane_sz, D.ny, m),
-                          plane(D.fund + 4 * plane_sz, D.ny, m)};
-        LineRef ysc[3] = {plane(D.scr + 0 * plane_sz, D.ny, m), plane(D.scr + 1 * plane_sz, D.ny, m),
-                          plane(D.scr + 2 * plane_sz, D.ny, m)};
+        LineRef res[3] = {plane(D, P_FUND, 2, m), plane(D, P_FUND, 3, m),
+                          plane(D, P_FUND, 4, m)};
+        LineRef ysc[3] = {plane(D, P_SCR, 0, m), plane(D, P_SCR, 1, m),
+                          plane(D, P_SCR, 2, m)};
         if (D.fac)
-            int1_solve<3, 1>(D.smax, -lam, f, 1.0, fend, bc, res, ysc, plane(D.fac + 6 * plane_sz, D.ny, m),
-                             plane(D.fac + 7 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), der,
-                             plane(D.fac + 4 * plane_sz, D.ny, m), plane(D.fac + 5 * plane_sz, D.ny, m));
+            int1_solve<3, 1>(D.smax, -lam, f, 1.0, fend, bc, res, ysc, plane(D, P_FAC, 6, m),
+                             plane(D, P_FAC, 7, m), plane(D, P_SCR, 5, m), der,
+                             plane(D, P_FAC, 4, m), plane(D, P_FAC, 5, m));
         else
-            int1_solve<3>(D.smax, -lam, f, 1.0, fend, bc, res, ysc, plane(D.scr + 3 * plane_sz, D.ny, m),
-                          plane(D.scr + 4 * plane_sz, D.ny, m), plane(D.scr + 5 * plane_sz, D.ny, m), der);
+            int1_solve<3>(D.smax, -lam, f, 1.0, fend, bc, res, ysc, plane(D, P_SCR, 3, m),
+                          plane(D, P_SCR, 4, m), plane(D, P_SCR, 5, m), der);
     }
     // boundary system (opr_odes.f90:329-348), stored LU-decomposed
-    const double v1n = plane(D.fund + 0 * plane_sz, D.ny, m).get(n), emn = plane(D.fund + 1 * plane_sz, D.ny, m).get(n);
-    const double u11 = plane(D.fund + 2 * plane_sz, D.ny, m).get(1), sp1 = plane(D.fund + 3 * plane_sz, D.ny, m).get(1);
-    const double ep1 = plane(D.fund + 4 * plane_sz, D.ny, m).get(1);
+    const double v1n = plane(D, P_FUND, 0, m).get(n), emn = plane(D, P_FUND, 1, m).get(n);
+    const double u11 = plane(D, P_FUND, 2, m).get(1), sp1 = plane(D, P_FUND, 3, m).get(1);
+    const double ep1 = plane(D, P_FUND, 4, m).get(1);
     double a11 = 1.0 + lam * sp1, a21 = emn, a31 = der[1];
     double a12 = lam * ep1, a22 = lam, a32 = der[2];
     double a13 = lam * u11, a23 = v1n, a33 = der[0];
@@ -405,19 +419,19 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
     for (int l = 0; l < NL; l++) {
         fl[l] = LineRef{cf + off + l0 + l, js};
         vl[l] = LineRef{cv + off + l0 + l, js};
-        ysc[l] = plane(D.scr + (l0 + l) * plane_sz, D.ny, m);
+        ysc[l] = plane(D, P_SCR, l0 + l, m);
         bcb[l] = fl[l].get(1) * norm;      // bcs(1:2,1) = f(1:2)
         bct[l] = fl[l].get(n) * norm;      // bcs(1:2,2) = f(2ny-1:2ny)
         zero[l] = 0.0;
     }
-    LineRef csc = plane(D.scr + 2 * plane_sz, D.ny, m), dsc = plane(D.scr + 3 * plane_sz, D.ny, m),
-            esc = plane(D.scr + 4 * plane_sz, D.ny, m);
+    LineRef csc = plane(D, P_SCR, 2, m), dsc = plane(D, P_SCR, 3, m),
+            esc = plane(D, P_SCR, 4, m);
     // v^(0): v' + lam v = f, f(n) = 0, v(1) = 0
     {
         if (FAC)
-            int1_solve<NL, 2>(D.smin, lam, fl, norm, zero, zero, vl, ysc, plane(D.fac + 2 * plane_sz, D.ny, m),
-                              plane(D.fac + 3 * plane_sz, D.ny, m), esc, nullptr, plane(D.fac + 0 * plane_sz, D.ny, m),
-                              plane(D.fac + 1 * plane_sz, D.ny, m));
+            int1_solve<NL, 2>(D.smin, lam, fl, norm, zero, zero, vl, ysc, plane(D, P_FAC, 2, m),
+                              plane(D, P_FAC, 3, m), esc, nullptr, plane(D, P_FAC, 0, m),
+                              plane(D, P_FAC, 1, m));
         else
             int1_solve<NL>(D.smin, lam, fl, norm, zero, zero, vl, ysc, csc, dsc, esc, nullptr);
     }
@@ -428,9 +442,9 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
 #pragma unroll
         for (int l = 0; l < NL; l++) fend[l] = vl[l].get(1);
         if (FAC)
-            int1_solve<NL, 2>(D.smax, -lam, vl, 1.0, fend, zero, fl, ysc, plane(D.fac + 6 * plane_sz, D.ny, m),
-                              plane(D.fac + 7 * plane_sz, D.ny, m), esc, du0, plane(D.fac + 4 * plane_sz, D.ny, m),
-                              plane(D.fac + 5 * plane_sz, D.ny, m));
+            int1_solve<NL, 2>(D.smax, -lam, vl, 1.0, fend, zero, fl, ysc, plane(D, P_FAC, 6, m),
+                              plane(D, P_FAC, 7, m), esc, du0, plane(D, P_FAC, 4, m),
+                              plane(D, P_FAC, 5, m));
         else
             int1_solve<NL>(D.smax, -lam, vl, 1.0, fend, zero, fl, ysc, csc, dsc, esc, du0);
     }
@@ -439,9 +453,9 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
     const double a11 = A[0 * NM + m], a21 = A[1 * NM + m], a31 = A[2 * NM + m];
     const double a12 = A[3 * NM + m], a22 = A[4 * NM + m], a32 = A[5 * NM + m];
     const double a13 = A[6 * NM + m], a23 = A[7 * NM + m], a33 = A[8 * NM + m];
-    LineRef v1 = plane(D.fund + 0 * plane_sz, D.ny, m), em = plane(D.fund + 1 * plane_sz, D.ny, m);
-    LineRef u1 = plane(D.fund + 2 * plane_sz, D.ny, m), sp = plane(D.fund + 3 * plane_sz, D.ny, m),
-            ep = plane(D.fund + 4 * plane_sz, D.ny, m);
+    LineRef v1 = plane(D, P_FUND, 0, m), em = plane(D, P_FUND, 1, m);
+    LineRef u1 = plane(D, P_FUND, 2, m), sp = plane(D, P_FUND, 3, m),
+            ep = plane(D, P_FUND, 4, m);
     const LineRef (&ul)[NL] = fl;
     double fn[NL], v_1[NL], u_n[NL];
 #pragma unroll
@@ -508,11 +522,11 @@ __device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ 
     LineRef vre = {cv + off, js}, vim = {cv + off + 1, js};
     const double norm = D.norm;
     const double bct[2] = {fre.get(n) * norm, fim.get(n) * norm};
-    LineRef ysc[2] = {plane(D.scr + 0 * plane_sz, D.ny, m), plane(D.scr + 1 * plane_sz, D.ny, m)};
-    LineRef csc = plane(D.scr + 2 * plane_sz, D.ny, m), dsc = plane(D.scr + 3 * plane_sz, D.ny, m),
-            esc = plane(D.scr + 4 * plane_sz, D.ny, m);
+    LineRef ysc[2] = {plane(D, P_SCR, 0, m), plane(D, P_SCR, 1, m)};
+    LineRef csc = plane(D, P_SCR, 2, m), dsc = plane(D, P_SCR, 3, m),
+            esc = plane(D, P_SCR, 4, m);
     // fundamental lines of this mode live in the (otherwise unused) fund planes of the mode
-    LineRef v1 = plane(D.fund + 0 * plane_sz, D.ny, m), u1 = plane(D.fund + 2 * plane_sz, D.ny, m);
+    LineRef v1 = plane(D, P_FUND, 0, m), u1 = plane(D, P_FUND, 2, m);
     const double zero2[2] = {0.0, 0.0};
     // v^(0): v' = f with f(1) = 0, v(n) = bcs(:,2)
     {
@@ -745,6 +759,7 @@ int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz, int nz_loca
     if (int rc = make_side(gy->p.h.der1, BCS_MAX, D.smax, allocs)) return fail(rc, "integral operator (BCS_MAX) setup failed");
     const size_t plane_sz = (size_t)((D.nmodes + 31) / 32 * 32) * ny;
     D.plane_sz = (long long)plane_sz;
+    D.il = ctx().tune_poisson_il ? 1 : 0;
     double *fund = nullptr, *scr = nullptr, *amat = nullptr;
     if (cudaMalloc(&fund, 5 * plane_sz * sizeof(double)) != cudaSuccess ||
         cudaMalloc(&scr, 6 * plane_sz * sizeof(double)) != cudaSuccess ||

@@ -19,6 +19,7 @@ struct PoissonDev {
     int nxh = 0, ny = 0, nz = 0;
     long long nmodes = 0;
     long long plane_sz = 0;           // doubles per scratch / fundamental plane (modes padded to 32)
+    int il = 1;                       // planes that are read together are interleaved row by row (see plane() in poisson.cu)
     double norm = 1.0;
     int i_sing0 = 0, i_sing1 = 0, k_sing0 = 0, k_sing1 = 0;
     const double* lambda = nullptr;   // [nmodes]

@@ -102,27 +102,31 @@ def main():
                 timeit(lambda: B[d](opr.OPR_B_SELF, 0, nx, ny, nz, bcs, u, u, r1), 16 * N, "OPR_Burgers_%s SELF" % nm.upper() + tag)
                 timeit(lambda: B[d](opr.OPR_B_U_IN, 1, nx, ny, nz, bcs, u, v, r1), 24 * N, "OPR_Burgers_%s U_IN" % nm.upper() + tag)
     if args.poisson:
-        opr.OPR_Elliptic_Initialize(g)
         t1 = torch.zeros((nx + 2) * ny * nz, dtype=torch.float64, device=dev)
         t2 = torch.zeros_like(t1)
         hb = torch.zeros(nx * nz, dtype=torch.float64, device=dev)
         ht = torch.zeros_like(hb)
         p = u.clone()
-        for minb, split in ((3, 0), (3, 1), (4, 1), (2, 1)):
-            tl.check(L.tlab_gpu_set_tuning(b"poisson_minb", minb))
-            tl.check(L.tlab_gpu_set_tuning(b"poisson_split", split))
-            tl.check(L.tlab_gpu_profile(1))
-            timeit(lambda: opr.OPR_Poisson(nx, ny, nz, 3, p, t1, t2, hb, ht, r1), 120 * N,
-                   "OPR_Poisson (120 B/pt model) minb=%d split=%d" % (minb, split))
-            ms = (ctypes.c_double * 16)()
-            cn = (ctypes.c_int * 16)()
-            tl.check(L.tlab_gpu_profile_report(ms, cn, 16))
-            tl.check(L.tlab_gpu_profile(0))
-            if rows and cn[8]:
-                rows[-1]["poisson_y_ms"] = ms[8] / cn[8]
-                print("      y solves %.3f ms per call" % (ms[8] / cn[8]), flush=True)
-            if rows:
-                rows[-1]["GBs_at_24B_floor"] = rows[-1]["GBs"] * 24.0 / 120.0
+        for il in [int(v) for v in os.environ.get("POISSON_IL", "1,0").split(",")]:
+            tl.check(L.tlab_gpu_set_tuning(b"poisson_il", il))
+            opr.OPR_Elliptic_Initialize(g)
+            for minb, split in [tuple(int(c) for c in v.split(":")) for v in os.environ.get("POISSON_CFG", "3:0,3:1,4:0,4:1").split(",")]:
+                tl.check(L.tlab_gpu_set_tuning(b"poisson_minb", minb))
+                tl.check(L.tlab_gpu_set_tuning(b"poisson_split", split))
+                tl.check(L.tlab_gpu_profile(1))
+                timeit(lambda: opr.OPR_Poisson(nx, ny, nz, 3, p, t1, t2, hb, ht, r1), 120 * N,
+                       "OPR_Poisson (120 B/pt model) il=%d minb=%d split=%d" % (il, minb, split))
+                ms = (ctypes.c_double * 16)()
+                cn = (ctypes.c_int * 16)()
+                tl.check(L.tlab_gpu_profile_report(ms, cn, 16))
+                tl.check(L.tlab_gpu_profile(0))
+                if rows and cn[8]:
+                    rows[-1]["poisson_y_ms"] = ms[8] / cn[8]
+                    rows[-1]["GBs_at_24B_floor"] = rows[-1]["GBs"] * 24.0 / 120.0
+                    print("      y solves %.3f ms per call" % (ms[8] / cn[8]), flush=True)
+        tl.check(L.tlab_gpu_set_tuning(b"poisson_il", 0))
+        tl.check(L.tlab_gpu_set_tuning(b"poisson_minb", 3))
+        tl.check(L.tlab_gpu_set_tuning(b"poisson_split", -1))
     if args.json:
         json.dump({"shape": [nx, ny, nz], "peak_GBs": peak, "peak_kind": kind, "rows": rows}, open(args.json, "w"), indent=1)
 
