@@ -371,13 +371,19 @@ def run_gpu(args):
         rate, cores, desc = cpu_port_rate((128, 64, 128), 1, None)
         cpu = {"value": rate, "unit": "Gpts/s", "cores": cores, "kind": "port", "sample": desc}
 
+    zc = ctypes.c_longlong(0)
+    tl.check(L.tlab_gpu_get_counter(b"splitz_ops", ctypes.byref(zc)))
+    z_path = "whole lines on one GPU" if world == 1 else (
+        "on the slabs: halo planes + chunk ends exchanged with the neighbours over peer memory (splitz)" if zc.value > 0
+        else "K-transposes to z pencils (all-to-all)")
     out = {"metric": "rk_substep_throughput", "value": value, "unit": "Gpts/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": "incompressible Boussinesq CBL %dx%dx%d, RK4-5 substep, 1 scalar, CompactJacobian6 + "
                                   "CompactJacobian6Hyper, tanh-stretched y" % (nx, ny, nz),
                       "l2": "working set per substep >> 126 MB L2 (each field %.2f GB)" % (N * 8 / 1e9),
-                      "decomposition": "z-slabs x%d" % world},
+                      "decomposition": "z-slabs x%d" % world,
+                      "z_operators": z_path},
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
            "breakdown_ms": breakdown}
     if rank == 0:
