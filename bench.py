@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # name: (nx, ny, nz)
     "c3": (1024, 512, 1024),      # BASELINE.json configs[2], single GPU
+    "c4": (2048, 1024, 2048),     # BASELINE.json configs[3], 8 GPUs (2^29 points per GPU)
     "c3-half": (1024, 512, 512),
     "c2": (512, 512, 512),
     "small": (256, 128, 256),

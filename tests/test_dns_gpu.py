@@ -231,3 +231,19 @@ def test_split_z_operators_on_virtual_slabs(cuda, shape, pv):
     for a, b, c in zip(split, whole, ref):
         assert rel_l2(a, c) <= 1e-11
         assert rel_l2(a, b) <= 1e-13
+
+
+def test_restart_files_round_trip(cuda, tmp_path):
+    """q, s written as tlab restart files (flow.<it>.<n>, scal.<it>.<n>; tlab_b200/io.py) and read back into a second
+    instance: the next RK step of both instances is identical."""
+    o, g = _pair(32, 33, 16, "tanh")
+    g.runge_kutta(1e-3)
+    flow, scal = str(tmp_path / "flow.1"), str(tmp_path / "scal.1")
+    g.write_restart(flow, scal, nt=1, rtime=1e-3, visc=1.0 / 5000.0, schmidt=[1.0])
+    _, g2 = _pair(32, 33, 16, "tanh")
+    nt, rtime = g2.read_restart(flow, scal)
+    assert nt == 1 and rtime == 1e-3
+    g.runge_kutta(1e-3)
+    g2.runge_kutta(1e-3)
+    for name in ("q1", "q2", "q3", "s1"):
+        assert np.array_equal(g.get(name), g2.get(name))

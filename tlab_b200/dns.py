@@ -72,6 +72,30 @@ class Dns:
         _lib.check(_lib.load().tlab_dns_download_host(self.handle, name.encode(), a.ctypes.data_as(ctypes.c_void_p)))
         return a
 
+    def read_restart(self, flow_name, scal_name=None, koff=0, nz_total=None):
+        """Load tlab restart files (`flow.<it>.1..3`, `scal.<it>.1..ns`, tlab_b200/io.py) into q and s; with `nz_total`
+        this rank takes its z-slab `[koff, koff + nz)` of the global field.  Returns (nt, rtime)."""
+        from . import io as tio
+        nzt = self.nz if nz_total is None else int(nz_total)
+        q, nt, params = tio.read_fields(flow_name, self.nx, self.ny, nzt, 3, koff=koff, kmax=self.nz)
+        for i in range(3):
+            self.set("q%d" % (i + 1), q[i])
+        if scal_name is not None and self.inb_scal > 0:
+            s, _, _ = tio.read_fields(scal_name, self.nx, self.ny, nzt, self.inb_scal, koff=koff, kmax=self.nz)
+            for i in range(self.inb_scal):
+                self.set("s%d" % (i + 1), s[i])
+        return nt, (float(params[0]) if len(params) else 0.0)
+
+    def write_restart(self, flow_name, scal_name, nt, rtime, visc, schmidt=(), koff=0, nz_total=None):
+        """Write q and s as tlab restart files (IO_Write_Fields with the headers of tlab_consistency_check.f90:148-163)."""
+        from . import io as tio
+        tio.write_fields(flow_name, nt, [self.get("q%d" % (i + 1)) for i in range(3)], tio.flow_params(rtime, visc),
+                         koff=koff, nz_total=nz_total)
+        if self.inb_scal > 0:
+            tio.write_fields(scal_name, nt, [self.get("s%d" % (i + 1)) for i in range(self.inb_scal)],
+                             [tio.scal_params(rtime, visc, schmidt[i]) for i in range(self.inb_scal)],
+                             koff=koff, nz_total=nz_total)
+
     def device_ptr(self, name):
         p = ctypes.c_void_p()
         _lib.check(_lib.load().tlab_dns_field(self.handle, name.encode(), ctypes.byref(p)))
