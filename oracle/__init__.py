@@ -10,12 +10,20 @@ does.
 Parity pinning (see DESIGN.md "Oracle"): the reference cannot be built here
 (Fortran 2008 + FFTW3; no Fortran compiler in the image), and ships no binary
 golden fields.  The oracle is pinned against
+  * the reference build's own log of examples/Case10 (``dns.out.ref``, copied to
+    tests/golden/case10_dns.out.ref): from the case's restated initial condition
+    (tests/case10.py) the oracle reproduces all ten logged iterations -- time,
+    dt, CFL and diffusion numbers, min/max dilatation -- to every printed digit
+    (6 significant digits for the dilatation), tests/test_case10_cpu.py; this
+    covers grid, compact schemes on the stretched grid, OPR_Burgers, the Poisson
+    solver (FFT included), the RK4-5 advance, TIME_COURANT, DNS_BOUNDS_CONTROL,
   * the reference's own numpy restatement of the C1N6 schemes,
     ``scripts/python/compact_lib.py`` (imported in this container by
     ``tests/golden/make_golden.py``; outputs committed under tests/golden/),
   * the uniform-grid coefficient limits quoted in the reference sources,
   * the reference's self-consistency recipes (vburgers, vpoisson, vintegral,
     vpartial analytic convergence).
-FFT values alone (FFTW3, external, un-pinned version) are "parity unpinned";
-they are pinned only through the Poisson round-trip identity.
+FFT values alone (FFTW3, external, un-pinned version) have no golden of their
+own; they are pinned through the Poisson round-trip identity and through the
+Case10 log (whose dilatation after each step is what the Poisson solve leaves).
 """
