@@ -10,9 +10,10 @@ does.
 Parity pinning (see DESIGN.md "Oracle"): the reference cannot be built here
 (Fortran 2008 + FFTW3; no Fortran compiler in the image), and ships no binary
 golden fields.  The oracle is pinned against
-  * the reference build's own log of examples/Case10 (``dns.out.ref``, copied to
-    tests/golden/case10_dns.out.ref): from the case's restated initial condition
-    (tests/case10.py) the oracle reproduces all ten logged iterations -- time,
+  * the reference build's own logs of examples/Case10, Case06 and Case07
+    (``dns.out.ref``, copied to tests/golden/case*_dns.out.ref): from each case's
+    restated initial condition
+    (tests/tlab_cases.py) the oracle reproduces all ten logged iterations -- time,
     dt, CFL and diffusion numbers, min/max dilatation -- to every printed digit
     (6 significant digits for the dilatation), tests/test_case10_cpu.py; this
     covers grid, compact schemes on the stretched grid, OPR_Burgers, the Poisson
