@@ -97,7 +97,7 @@ def test_opr_burgers(cuda, case):
         assert rel_l2(res.cpu().numpy(), ident) <= 1e-11
 
 
-@pytest.mark.parametrize("shape", [(40, 37, 24), (32, 256, 16)])     # general kernel / fast kernel (wall chunks only)
+@pytest.mark.parametrize("shape", [(40, 37, 24), (32, 256, 16), (64, 512, 16)])     # general kernel / fast kernel: CTAs of the wall chunks only, 32 and 64 lines
 def test_boundary_bcs_neumann_y(cuda, shape):
     import torch
     from oracle import operators as O

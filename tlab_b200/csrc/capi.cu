@@ -113,6 +113,19 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
     std::memcpy(b.neu_bot, a.neu_bot, sizeof(b.neu_bot));
     std::memcpy(b.neu_top, a.neu_top, sizeof(b.neu_top));
     b.neu_lu_bot = a.neu_lu_bot; b.neu_lu_top = a.neu_lu_top;
+    if (mode == MODE_NEUMANN && ctx().tune_neu_compact && !contig) {
+        // wall chunks only: more lines per CTA (long row segments), no idle threads
+        const int nb = a.bcs_hb ? LB2 : 0, nt = a.bcs_ht ? LB2 : 0;
+        if (nb + nt > 0 && nb + nt < b.T) {
+            int Lc = 64;
+            while (Lc > 1 && (Lc * (nb + nt) > 512 || a.inner % Lc != 0)) Lc >>= 1;
+            if ((size_t)8 * b.T * Lc * sizeof(double) <= 200 * 1024) {
+                b.neu_nb = nb; b.neu_nt = nt; b.L = Lc;
+                b.lshift = 0;
+                while ((1 << b.lshift) < Lc) b.lshift++;
+            }
+        }
+    }
     b.tma_rb = 16;
     while (b.tma_rb < 256 && b.n % (b.tma_rb * 2) == 0) b.tma_rb *= 2;
     b.tma_l2 = ctx().tune_tma_l2;
@@ -379,6 +392,7 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "pf_dist")) ctx().tune_pf_dist = value;
     else if (!std::strcmp(key, "persist")) ctx().tune_persist = value;
     else if (!std::strcmp(key, "tma")) ctx().tune_tma = value;
+    else if (!std::strcmp(key, "neu_compact")) ctx().tune_neu_compact = value;
     else if (!std::strcmp(key, "tma_l2")) ctx().tune_tma_l2 = value;
     else if (!std::strcmp(key, "splitz")) ctx().tune_splitz = value;
     else if (!std::strcmp(key, "split_emulate")) ctx().tune_split_emulate = value;

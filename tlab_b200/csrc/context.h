@@ -35,6 +35,7 @@ struct Context {
     int tune_overlap = 1;     // split domain: z operators on a second stream, overlapped with the x/y operators
     int tune_pf_l1 = 0;       // strided fast kernels: early L1 prefetch of the operands needed after the solve
     int tune_persist = 0;     // strided fast kernels: persistent CTAs with asynchronous staging
+    int tune_neu_compact = 1; // BOUNDARY_BCS_NEUMANN_Y: CTAs made of the wall chunks only
     int tune_splitz = 1;      // split domain: z operators on the slabs with halo / chunk-end exchange (splitz.cu) instead of transposes
     int tune_split_emulate = 0;  // P = 1: run the split-z kernels over this many virtual slabs of the field (tests)
     int tune_tma_l2 = 0;      // L2 promotion of the tensor maps of the TMA kernels

@@ -324,6 +324,13 @@ __global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__
     c.L = a.L; c.T = a.T;
     c.l = threadIdx.x & (a.L - 1);
     c.t = threadIdx.x >> a.lshift;
+    if (MODE == MODE_NEUMANN && a.neu_nb + a.neu_nt > 0) {
+        // only the chunks next to the walls are resident (the wall derivative feels nothing else, see strided_field): thread
+        // row t' -> chunk t' at the bottom, T - nt + (t' - nb) at the top; the exchange slots of the absent chunks read as zero
+        for (int i = threadIdx.x; i < 2 * a.T * a.L; i += blockDim.x) sm[i] = 0.0;
+        __syncthreads();
+        if (c.t >= a.neu_nb) c.t = a.T - a.neu_nt + (c.t - a.neu_nb);
+    }
     strided_field<MODE, PER, NEED1, false>(a, c, sm, a.u, a.out1, a.s2);
 }
 
@@ -1052,7 +1059,7 @@ cudaError_t launch2_tma(const Line2Args& a_in, dim3 grid, cudaStream_t stream) {
 template <int MODE, bool PER, bool NEED1>
 cudaError_t launch2(const Line2Args& a_in, bool contig, dim3 grid, cudaStream_t stream) {
     Line2Args a = a_in;
-    const int threads = a.L * a.T;
+    const int threads = (MODE == MODE_NEUMANN && a.neu_nb + a.neu_nt > 0) ? a.L * (a.neu_nb + a.neu_nt) : a.L * a.T;
     if (!contig && a.tma && (MODE == MODE_P1 || MODE == MODE_P2 || MODE == MODE_BURGERS)) {
         constexpr int M = (MODE == MODE_P1 || MODE == MODE_P2 || MODE == MODE_BURGERS) ? MODE : MODE_P1;
         const cudaError_t e = launch2_tma<M, PER, NEED1>(a, grid, stream);
