@@ -153,14 +153,15 @@ def test_case01_shape_two_dimensional_step(cuda):
 
 
 @pytest.mark.parametrize("tune", [{"fuse": 1}, {"fuse": 1, "pf_next": 1}, {"persist": 1}, {"pf_dist": 3}, {"fast": 0},
-                                  {"tma": 1}, {"poisson_split": 0}, {"poisson_split": 1}])
+                                  {"tma": 1}, {"poisson_split": 0}, {"poisson_split": 1},
+                                  {"neu_compact": 0}])
 def test_tuning_variants_give_the_same_step(cuda, tune):
     """The optional kernel variants (fused multi-field Burgers launch, next-field / next-tile L2 prefetch, persistent
     cp.async staging, general kernels) are alternative schedules of the same arithmetic: one RK step on full chunks
     (64 x 64 x 32) must agree with the oracle like the default path does."""
     from tlab_b200 import lib as tl
     L = tl.load()
-    defaults = {"fuse": 0, "pf_next": 0, "persist": 0, "pf_dist": -1, "fast": 1, "tma": 0, "poisson_split": -1}
+    defaults = {"fuse": 0, "pf_next": 0, "persist": 0, "pf_dist": -1, "fast": 1, "tma": 0, "poisson_split": -1, "neu_compact": 1}
     try:
         for k, v in tune.items():
             tl.check(L.tlab_gpu_set_tuning(k.encode(), v))
@@ -247,3 +248,21 @@ def test_restart_files_round_trip(cuda, tmp_path):
     g2.runge_kutta(1e-3)
     for name in ("q1", "q2", "q3", "s1"):
         assert np.array_equal(g.get(name), g2.get(name))
+
+
+@pytest.mark.parametrize("pair", [1, 0])
+def test_long_periodic_lines_cta_pairs(cuda, pair):
+    """z lines of 64 chunks (nz = 1024): with pair = 1 a line is shared by a cluster of 2 CTAs exchanging chunk ends through
+    distributed shared memory (16 lines per tile, 128-byte rows); pair = 0 (default) keeps one CTA of 8 lines.  Same step."""
+    from tlab_b200 import lib as tl
+    L = tl.load()
+    try:
+        tl.check(L.tlab_gpu_set_tuning(b"pair", pair))
+        o, g = _pair(16, 32, 1024, "tanh")
+        o.runge_kutta(1e-3)
+        g.runge_kutta(1e-3)
+    finally:
+        tl.check(L.tlab_gpu_set_tuning(b"pair", 0))
+    for i in range(3):
+        assert rel_l2(g.get("q%d" % (i + 1)), o.q[i]) <= 1e-11
+    assert rel_l2(g.get("s1"), o.s[0]) <= 1e-11

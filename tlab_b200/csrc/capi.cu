@@ -113,6 +113,11 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
     std::memcpy(b.neu_bot, a.neu_bot, sizeof(b.neu_bot));
     std::memcpy(b.neu_top, a.neu_top, sizeof(b.neu_top));
     b.neu_lu_bot = a.neu_lu_bot; b.neu_lu_top = a.neu_lu_top;
+    if (!contig && ctx().tune_pair && p.periodic && !p.need_1der && (mode == MODE_P1 || mode == MODE_P2 || mode == MODE_BURGERS) &&
+        b.T > 32 && b.T % 2 == 0 && 16 * (b.T / 2) <= 512 && a.inner % 16 == 0 && !(a.u2 && mode == MODE_BURGERS)) {
+        // long periodic lines: a cluster of 2 CTAs per tile of 16 lines (128-byte rows), see lines2_strided_pair
+        b.L = 16; b.lshift = 4; b.pair = 1; b.persist = 0;
+    }
     if (mode == MODE_NEUMANN && ctx().tune_neu_compact && !contig) {
         // wall chunks only: more lines per CTA (long row segments), no idle threads
         const int nb = a.bcs_hb ? LB2 : 0, nt = a.bcs_ht ? LB2 : 0;
@@ -129,7 +134,7 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
     b.tma_rb = 16;
     while (b.tma_rb < 256 && b.n % (b.tma_rb * 2) == 0) b.tma_rb *= 2;
     b.tma_l2 = ctx().tune_tma_l2;
-    b.tma = (!contig && ctx().tune_tma && lines2_tma_eligible(mode, b)) ? 1 : 0;
+    b.tma = (!contig && !b.pair && ctx().tune_tma && lines2_tma_eligible(mode, b)) ? 1 : 0;
     return true;
 }
 
@@ -393,6 +398,7 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "persist")) ctx().tune_persist = value;
     else if (!std::strcmp(key, "tma")) ctx().tune_tma = value;
     else if (!std::strcmp(key, "neu_compact")) ctx().tune_neu_compact = value;
+    else if (!std::strcmp(key, "pair")) ctx().tune_pair = value;
     else if (!std::strcmp(key, "tma_l2")) ctx().tune_tma_l2 = value;
     else if (!std::strcmp(key, "splitz")) ctx().tune_splitz = value;
     else if (!std::strcmp(key, "split_emulate")) ctx().tune_split_emulate = value;

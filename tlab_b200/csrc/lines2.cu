@@ -25,10 +25,13 @@
 // latency of a tile is paid while earlier tiles are being solved.
 #include "lines2_dev.cuh"
 #include <cuda.h>
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <cstring>
 #include <map>
 #include <tuple>
+
+namespace cg = cooperative_groups;
 
 namespace tlab {
 
@@ -78,12 +81,12 @@ __device__ __forceinline__ void solve_one(double (&f)[C], const Sys2& S, const C
     double yend, part = 0.0;
     if (isc) local_const(f, S, yend);
     else local_tab<PER>(f, tp, yend, part);
-    y[c.t * c.L + c.l] = yend;
-    __syncthreads();
+    publish(&y[c.t * c.L + c.l], yend, c);
+    exchange_barrier(c);
     const double A = look_back(y, cr, c);
-    z[c.t * c.L + c.l] = fma(q0pp.x, A, f[0]);
-    if (PER) w[c.t * c.L + c.l] = fma(q0pp.y, A, part);
-    __syncthreads();
+    publish(&z[c.t * c.L + c.l], fma(q0pp.x, A, f[0]), c);
+    if (PER) publish(&w[c.t * c.L + c.l], fma(q0pp.y, A, part), c);
+    exchange_barrier(c);
     const double B = look_ahead(z, cr, c);
     if (isc) finish_const(f, S, A, B);
     else {
@@ -116,14 +119,14 @@ __device__ __forceinline__ void solve_two(double (&f0)[C], double (&f1)[C], cons
         if (c1) local_const(f1, S1, ye1); else local_tab<PER>(f1, tp1, ye1, p1);
     }
     const int me = c.t * c.L + c.l;
-    y0[me] = ye0;
-    y1[me] = ye1;
-    __syncthreads();
+    publish(&y0[me], ye0, c);
+    publish(&y1[me], ye1, c);
+    exchange_barrier(c);
     const double A0 = look_back(y0, cr0, c), A1 = look_back(y1, cr1, c);
-    z0[me] = fma(q0.x, A0, f0[0]);
-    z1[me] = fma(q1.x, A1, f1[0]);
-    if (PER) { w0[me] = fma(q0.y, A0, p0); w1[me] = fma(q1.y, A1, p1); }
-    __syncthreads();
+    publish(&z0[me], fma(q0.x, A0, f0[0]), c);
+    publish(&z1[me], fma(q1.x, A1, f1[0]), c);
+    if (PER) { publish(&w0[me], fma(q0.y, A0, p0), c); publish(&w1[me], fma(q1.y, A1, p1), c); }
+    exchange_barrier(c);
     const double B0 = look_ahead(z0, cr0, c), B1 = look_ahead(z1, cr1, c);
     if (c0 && c1) {
 #pragma unroll
@@ -203,7 +206,7 @@ template <int MODE, bool PER, bool NEED1, bool KEEPV>
 __device__ __forceinline__ void strided_field(const Line2Args& a, const ChunkCtx& c, double* sm, const double* __restrict__ fu,
                                               double* __restrict__ fo, const Sys2& S2) {
     const long long st = a.stride;
-    const long long tile0 = (long long)blockIdx.y * a.outer_stride + (long long)blockIdx.x * a.L;
+    const long long tile0 = (long long)blockIdx.y * a.outer_stride + (long long)c.bx * a.L;
     const long long lbase = tile0 + c.l;
     const int n = a.n;
     const bool has_u2 = (a.u2 != nullptr);
@@ -211,7 +214,7 @@ __device__ __forceinline__ void strided_field(const Line2Args& a, const ChunkCtx
 
     // ---- L2 prefetch of a later tile (one row segment per request); not for the Neumann kernel, which reads a few rows only
     if (a.pf_dist > 0 && MODE != MODE_NEUMANN) {
-        const unsigned tile = blockIdx.y * gridDim.x + blockIdx.x + (unsigned)a.pf_dist;
+        const unsigned tile = blockIdx.y * gridDim.x + (unsigned)c.bx + (unsigned)a.pf_dist;
         if (tile < gridDim.x * gridDim.y) {
             const unsigned ty = tile / gridDim.x, tx = tile - ty * gridDim.x;
             const long long pb = (long long)ty * a.outer_stride + (long long)tx * a.L;
@@ -278,7 +281,7 @@ __device__ __forceinline__ void strided_field(const Line2Args& a, const ChunkCtx
 
     if (MODE == MODE_NEUMANN) {
         // boundary values such that the normal derivative vanishes (BOUNDARY_BCS_NEUMANN_Y)
-        const long long line = (long long)blockIdx.y * a.inner + (long long)blockIdx.x * a.L + c.l;
+        const long long line = (long long)blockIdx.y * a.inner + (long long)c.bx * a.L + c.l;
         if (c.t == 0 && a.bcs_hb != nullptr) a.bcs_hb[line] = nb_sum + a.neu_lu_bot * d1[1];
         if (c.t == c.T - 1 && a.bcs_ht != nullptr) a.bcs_ht[line] = nt_sum + a.neu_lu_top * d1[C - 2];
         return;
@@ -324,6 +327,7 @@ __global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__
     c.L = a.L; c.T = a.T;
     c.l = threadIdx.x & (a.L - 1);
     c.t = threadIdx.x >> a.lshift;
+    c.bx = blockIdx.x;
     if (MODE == MODE_NEUMANN && a.neu_nb + a.neu_nt > 0) {
         // only the chunks next to the walls are resident (the wall derivative feels nothing else, see strided_field): thread
         // row t' -> chunk t' at the bottom, T - nt + (t' - nb) at the top; the exchange slots of the absent chunks read as zero
@@ -332,6 +336,29 @@ __global__ void __launch_bounds__(512, 1) lines2_strided(const __grid_constant__
         if (c.t >= a.neu_nb) c.t = a.T - a.neu_nt + (c.t - a.neu_nb);
     }
     strided_field<MODE, PER, NEED1, false>(a, c, sm, a.u, a.out1, a.s2);
+}
+
+// Long periodic lines (T > 32 chunks, z at C3): a CTA of 512 threads can hold only 8 lines of 64 chunks, i.e. 64-byte row
+// segments, which costs a fifth of the bandwidth (burgers_z 47 % against 58 % of the peak with 128-byte rows, measured).
+// Here a line is shared by a thread-block cluster of 2 CTAs, 16 lines x 32 chunks each (128-byte rows): the chunk ends
+// are published into both CTAs' exchange areas through distributed shared memory and the two block barriers of a solve
+// become cluster barriers; everything else is strided_field.  Periodic, uniform directions only (no Jacobian term).
+template <int MODE>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) lines2_strided_pair(const __grid_constant__ Line2Args a) {
+    extern __shared__ double sm[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const unsigned rank = cluster.block_rank();
+    ChunkCtx c;
+    c.L = a.L; c.T = a.T;
+    c.l = threadIdx.x & (a.L - 1);
+    c.t = (threadIdx.x >> a.lshift) + (int)rank * (a.T / 2);
+    c.bx = blockIdx.x >> 1;
+    c.pair = true;
+    // generic address of the peer's exchange area (same offset in its shared-memory window)
+    c.rsm = cluster.map_shared_rank(sm, rank ^ 1u);
+    c.sm0 = sm;
+    cluster.sync();             // both CTAs are running: their shared memory may be written from now on
+    strided_field<MODE, true, false, false>(a, c, sm, a.u, a.out1, a.s2);
 }
 
 // fused Burgers launch: the fields fu[0..nf) of a tile are advected by the same velocity (OPR_Burgers_X/Y/Z of u, v, w
@@ -343,6 +370,7 @@ __global__ void __launch_bounds__(512, 1) lines2_strided_multi(const __grid_cons
     c.L = a.L; c.T = a.T;
     c.l = threadIdx.x & (a.L - 1);
     c.t = threadIdx.x >> a.lshift;
+    c.bx = blockIdx.x;
     for (int f = 0; f < a.nf; f++) {
         if (f > 0) __syncthreads();                 // the exchange areas of the previous field are free again
         if (a.pf_next && f + 1 < a.nf) {
@@ -1099,6 +1127,17 @@ cudaError_t launch2(const Line2Args& a_in, bool contig, dim3 grid, cudaStream_t 
         a.ntiles = grid.x * grid.y;
         const unsigned g = std::min<unsigned>(a.ntiles, (unsigned)ctas);
         k<<<g, threads, smem, stream>>>(a);
+    } else if (a.pair && PER && !NEED1 && (MODE == MODE_P1 || MODE == MODE_P2 || MODE == MODE_BURGERS)) {
+        constexpr int M = (MODE == MODE_P1 || MODE == MODE_P2 || MODE == MODE_BURGERS) ? MODE : MODE_P1;
+        auto k = lines2_strided_pair<M>;
+        static size_t set = 48 * 1024;
+        if (smem > set) {
+            cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            set = smem;
+        }
+        a.pf_dist = 0;
+        k<<<dim3(grid.x * 2, grid.y, 1), threads / 2, smem, stream>>>(a);
     } else {
         auto k = lines2_strided<MODE, PER, NEED1>;
         static size_t set = 48 * 1024;

@@ -13,6 +13,7 @@ struct Line2Args {
     int persist = 0;                  // strided kernel: persistent CTAs with cp.async staging
     unsigned ntiles = 0, tiles_x = 0; // persistent kernel: tile count and tiles per outer block
     int neu_nb = 0, neu_nt = 0;       // BOUNDARY_BCS_NEUMANN_Y: CTAs hold only these many chunks next to the bottom / top wall (0, 0: whole lines)
+    int pair = 0;                     // strided kernel: a line is shared by a cluster of 2 CTAs (L lines x T/2 chunks each)
     int tma = 0;                      // strided kernel: persistent CTAs fed and drained by the TMA unit (lines2_strided_tma)
     int tma_rb = 0;                   // rows per TMA box
     int tma_l2 = 0;                   // L2 promotion of the tensor maps (0 none, 1/2/3: 64/128/256 bytes)

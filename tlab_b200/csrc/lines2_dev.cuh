@@ -69,7 +69,26 @@ __host__ __device__ inline int exch2_per_system(int T, int L) { return 3 * T * L
 
 struct ChunkCtx {
     int t, T, l, L;
+    int bx = 0;                 // tile index along the line-index direction (blockIdx.x, or half of it for a CTA pair)
+    // CTA pair (thread-block cluster of 2 sharing a line): the peer's exchange area as the generic pointer that
+    // map_shared_rank returned (it must not be derived from the local array: the compiler would keep it a shared-window store)
+    double* rsm = nullptr;
+    const double* sm0 = nullptr;
+    bool pair = false;
 };
+
+// exchange of chunk ends: every value goes to this CTA's array and, for a CTA pair, to the peer's copy as well
+__device__ __forceinline__ void publish(double* slot, double v, const ChunkCtx& c) {
+    *slot = v;
+    if (c.pair) c.rsm[slot - c.sm0] = v;
+}
+__device__ __forceinline__ void exchange_barrier(const ChunkCtx& c) {
+    if (c.pair) {
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        __syncthreads();
+    }
+}
 
 __device__ __forceinline__ const double2* tab_ptr(const Sys2& S, int t) {
     return S.tab + ((size_t)(t >> 3) * C * 4) * 8 + (t & 7);
