@@ -154,14 +154,14 @@ def test_case01_shape_two_dimensional_step(cuda):
 
 @pytest.mark.parametrize("tune", [{"fuse": 1}, {"fuse": 1, "pf_next": 1}, {"persist": 1}, {"pf_dist": 3}, {"fast": 0},
                                   {"tma": 1}, {"poisson_split": 0}, {"poisson_split": 1},
-                                  {"neu_compact": 0}])
+                                  {"neu_compact": 0}, {"fuse_update": 0}])
 def test_tuning_variants_give_the_same_step(cuda, tune):
     """The optional kernel variants (fused multi-field Burgers launch, next-field / next-tile L2 prefetch, persistent
     cp.async staging, general kernels) are alternative schedules of the same arithmetic: one RK step on full chunks
     (64 x 64 x 32) must agree with the oracle like the default path does."""
     from tlab_b200 import lib as tl
     L = tl.load()
-    defaults = {"fuse": 0, "pf_next": 0, "persist": 0, "pf_dist": -1, "fast": 1, "tma": 0, "poisson_split": -1, "neu_compact": 1}
+    defaults = {"fuse": 0, "pf_next": 0, "persist": 0, "pf_dist": -1, "fast": 1, "tma": 0, "poisson_split": -1, "neu_compact": 1, "fuse_update": 1}
     try:
         for k, v in tune.items():
             tl.check(L.tlab_gpu_set_tuning(k.encode(), v))

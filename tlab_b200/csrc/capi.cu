@@ -399,6 +399,7 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "tma")) ctx().tune_tma = value;
     else if (!std::strcmp(key, "neu_compact")) ctx().tune_neu_compact = value;
     else if (!std::strcmp(key, "pair")) ctx().tune_pair = value;
+    else if (!std::strcmp(key, "fuse_update")) ctx().tune_fuse_update = value;
     else if (!std::strcmp(key, "tma_l2")) ctx().tune_tma_l2 = value;
     else if (!std::strcmp(key, "splitz")) ctx().tune_splitz = value;
     else if (!std::strcmp(key, "split_emulate")) ctx().tune_split_emulate = value;

@@ -35,6 +35,7 @@ struct Context {
     int tune_overlap = 1;     // split domain: z operators on a second stream, overlapped with the x/y operators
     int tune_pf_l1 = 0;       // strided fast kernels: early L1 prefetch of the operands needed after the solve
     int tune_persist = 0;     // strided fast kernels: persistent CTAs with asynchronous staging
+    int tune_fuse_update = 1; // RK substep: `hq2 -= dpdy` and the wall planes of hq2 folded into the update of q2 (2 sweeps less)
     int tune_pair = 0;        // long periodic strided lines (> 32 chunks): one line shared by a cluster of 2 CTAs (128-byte rows).
                               // Off: measured slower at C3 (burgers_z 23.1 vs 21.4 ms), the cluster barriers cost more than the rows gain
     int tune_neu_compact = 1; // BOUNDARY_BCS_NEUMANN_Y: CTAs made of the wall chunks only

@@ -71,6 +71,19 @@ __global__ void rk_update_kernel(double* __restrict__ q, double* __restrict__ h,
     }
 }
 
+// the same for the wall-normal velocity with the last two sweeps of the RHS folded in (rhs_global_incompressible_1.f90:
+// 334-352, 356-398 for a field with Dirichlet conditions at both walls): h = h - dpdy, h = 0 on the wall planes, then the update
+__global__ void rk_update_sub_kernel(double* __restrict__ q, double* __restrict__ h, const double* __restrict__ dpdy, double dte,
+                                     double kco, int scale_h, int nx, int ny, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)((i / nx) % ny);
+        double hv = h[i] - dpdy[i];
+        if (j == 0 || j == ny - 1) hv = 0.0;
+        q[i] = q[i] + dte * hv;
+        h[i] = scale_h ? kco * hv : hv;
+    }
+}
+
 // planes j = 0 and j = ny-1 of a field <-> (nx, nz) arrays
 __global__ void get_planes_kernel(const double* __restrict__ f, double* __restrict__ hb, double* __restrict__ ht,
                                   int nx, int ny, int nz) {
@@ -213,6 +226,8 @@ struct Dns {
     double* host_stage = nullptr;        // pinned staging buffer for the *_host entry points
     size_t host_stage_bytes = 0;
     long long launches = 0;
+    bool defer_v = false;      // substep(): `hq2 -= dpdy` and the wall planes of hq2 are left to the fused update of q2
+    bool v_deferred = false;   // ... and rhs() did leave them (non-overlapped schedule, Dirichlet at both walls)
 
     int alloc(double** p, long long count) {
         if (cudaMalloc(p, (size_t)count * sizeof(double)) != cudaSuccess) {
@@ -375,7 +390,9 @@ struct Dns {
     int rhs(double dte) {
         bool split = true;
         for (int is = 0; is <= ns && split; is++) split = use_split(is);
+        v_deferred = false;
         if (P > 1 && nzg > 1 && trp().zstream && ctx().tune_overlap && !split) return rhs_overlapped(dte);
+        v_deferred = defer_v && prm.bcs_flow_jmin[1] != TLAB_DNS_BCS_NEUMANN && prm.bcs_flow_jmax[1] != TLAB_DNS_BCS_NEUMANN;
         cudaStream_t st = ctx().stream;
         const int b0 = 0;   // bcs = 0: biased, non-zero (rhs_global_incompressible_1.f90:67)
         int rc = 0;
@@ -421,8 +438,10 @@ struct Dns {
         // hq -= grad p (:319-352)
         if ((rc = run_partial(1, TLAB_OPR_P1, nx, ny, nz, b0, g[0], tmp1, hq[0], nullptr, nullptr, 0.0, -1))) return rc;
         if ((rc = partial_z(tmp1, nullptr, 0.0, hq[2], -1))) return rc;
-        { ProfScope ps(PC_ELEMENTWISE);
-        sub_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(hq[1], tmp3, N); }
+        if (!v_deferred) {
+            ProfScope ps(PC_ELEMENTWISE);
+            sub_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(hq[1], tmp3, N);
+        }
         launches += 3;
         return rhs_bcs();
     }
@@ -433,6 +452,7 @@ struct Dns {
         const long long np = (long long)nx * nz;
         int rc = 0;
         for (int f = 0; f < 3 + ns; f++) {
+            if (f == 1 && v_deferred) continue;
             double* h = (f < 3) ? hq[f] : hs[f - 3];
             const int tmin = (f < 3) ? prm.bcs_flow_jmin[f] : prm.bcs_scal_jmin[f - 3];
             const int tmax = (f < 3) ? prm.bcs_flow_jmax[f] : prm.bcs_scal_jmax[f - 3];
@@ -454,11 +474,19 @@ struct Dns {
     int substep(double dte, double kcoef, int scale_h) {
         int rc = sources_flow();
         if (rc) return rc;
-        if ((rc = rhs(dte))) return rc;
+        defer_v = ctx().tune_fuse_update != 0;
+        rc = rhs(dte);
+        defer_v = false;
+        if (rc) { v_deferred = false; return rc; }
         cudaStream_t st = ctx().stream;
         ProfScope ps(PC_ELEMENTWISE);
-        for (int f = 0; f < 3; f++)
-            rk_update_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(q[f], hq[f], dte, kcoef, scale_h, 0, 0.0, 0.0, N);
+        for (int f = 0; f < 3; f++) {
+            if (f == 1 && v_deferred)
+                rk_update_sub_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(q[1], hq[1], tmp3, dte, kcoef, scale_h, nx, ny, N);
+            else
+                rk_update_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(q[f], hq[f], dte, kcoef, scale_h, 0, 0.0, 0.0, N);
+        }
+        v_deferred = false;
         for (int is = 0; is < ns; is++)
             rk_update_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(s[is], hs[is], dte, kcoef, scale_h, prm.scal_limit,
                                                                   prm.scal_min[is], prm.scal_max[is], N);
