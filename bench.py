@@ -182,7 +182,8 @@ def run_reference(args):
     out = {"impl": "reference", "metric": "rk_substep_throughput", "value": value, "unit": "Gpts/s", "n_gpus": args.gpus,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nx * ny * nz / (value * 1e9),
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": "incompressible Boussinesq CBL %dx%dx%d, RK4-5 substep, 1 scalar" % (nx, ny, nz),
+           "config": {"workload": "incompressible Boussinesq CBL %dx%dx%d, RK4-5 substep, 1 scalar, CompactJacobian6 + "
+                                  "CompactJacobian6Hyper, tanh-stretched y" % (nx, ny, nz),
                       "note": "CPU restatement of the reference algorithm (no Fortran compiler in the image); "
                               "rate measured on a bounded sample and quoted per point"},
            "cpu_baseline": {"value": value, "unit": "Gpts/s", "cores": cores, "kind": "port", "sample": desc},
