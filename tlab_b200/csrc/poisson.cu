@@ -657,14 +657,16 @@ int make_side(const HostDer& der1, int bc, Int1Dev& S, std::vector<void*>& alloc
 
 }  // namespace
 
-// One thread per mode, or (tuning key poisson_split: 1 always, 0 never, -1 when the modes of this GPU would fill less than
-// four waves of CTAs) one thread per component; the latter needs the stored factor lines.
+// One thread per mode, or (tuning key poisson_split: 1 always, 0 never, -1 when this GPU holds fewer than 200 000 modes)
+// one thread per component; the latter needs the stored factor lines.
 static void launch_modes(const PoissonDev& D, double* cf, double* cv, cudaStream_t st) {
-    const int minb = ctx().tune_poisson_minb;
     const int threads = 128;
     int split = ctx().tune_poisson_split;
-    if (split < 0) split = (D.nmodes < 4LL * 148 * 4 * threads) ? 1 : 0;
+    // measured (profiles/ncu_full_poisson_r01.json): 66 560 modes (C3 on 8 GPUs) 5.6 -> 5.1 ms with one thread per component and
+    // 4 CTAs/SM; 525 312 modes (C3 on one GPU) 17.4 -> 18.7 ms: only geometries that leave the SMs short of threads split
+    if (split < 0) split = (D.nmodes < 200000) ? 1 : 0;
     if (!D.fac) split = 0;
+    const int minb = split ? std::max(ctx().tune_poisson_minb, 4) : ctx().tune_poisson_minb;
     const long long work = split ? 2 * D.nmodes : D.nmodes;
     const unsigned blocks = (unsigned)((work + threads - 1) / threads);
     if (split) {
