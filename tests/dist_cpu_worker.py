@@ -1,4 +1,5 @@
-"""gloo worker (CPU, world_size 2): the K-transpose layout of tlab_b200.mpi against the global-array definition."""
+"""gloo worker (CPU, world_size 2): the K-transpose layout of tlab_b200.mpi against the global-array definition, and the
+slab-wise restart files of a split domain."""
 import os
 import sys
 
@@ -35,7 +36,28 @@ def main():
     assert np.array_equal(got, exp)
     # pack/unpack are inverse permutations
     assert torch.equal(mpi.unpack_k(mpi.pack_k(a, world)), a)
+    # restart files of a split domain (tlab_b200/io.py): every rank writes its z-slab in place, like the MPI-IO sub-array
+    # view of IO_Write_Fields (io_fields.f90:346-456); rank 0 owns the header; everybody reads its slab back
+    from tlab_b200 import io as tio
+    nx, ny = 6, 4
+    fields = [rng.standard_normal((nz, ny, nx)) for _ in range(2)]
+    fname = os.path.join(os.environ.get("TLAB_TMP", "/tmp"), "flow_gloo.7")
+    mine = [f[koff:koff + kmax] for f in fields]
+    for turn in range(world):                             # the rank holding plane 0 creates the files first
+        if turn == rank:
+            tio.write_fields(fname, 7, mine, tio.flow_params(0.5, 1e-3), koff=koff, nz_total=nz)
+        dist.barrier()
+    back_slab, nt, params = tio.read_fields(fname, nx, ny, nz, 2, koff=koff, kmax=kmax)
+    assert nt == 7 and list(params) == [0.5, 1e-3, 1.0, 1.0]
+    for got_f, exp_f in zip(back_slab, mine):
+        assert np.array_equal(got_f, exp_f)
+    whole, _, _ = tio.read_fields(fname, nx, ny, nz, 2)
+    for got_f, exp_f in zip(whole, fields):
+        assert np.array_equal(got_f, exp_f)
+    dist.barrier()
     if rank == 0:
+        for i in (1, 2):
+            os.remove(tio.field_name(fname, i))
         print("DIST_CPU_OK", flush=True)
     dist.destroy_process_group()
 

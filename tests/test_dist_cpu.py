@@ -1,4 +1,5 @@
-"""Host-side logic of the N > 1 path on CPUs: 2 gloo ranks exercise the K-transpose layout mirror."""
+"""Host-side logic of the N > 1 path on CPUs: 2 gloo ranks exercise the K-transpose layout mirror and the slab-wise
+restart files."""
 import os
 import subprocess
 import sys
@@ -6,10 +7,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_k_transpose_layout_gloo_world2():
+def test_k_transpose_layout_gloo_world2(tmp_path):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.join(ROOT, "tests", "dist_cpu_worker.py")]
-    env = dict(os.environ, OMP_NUM_THREADS="1")
+    env = dict(os.environ, OMP_NUM_THREADS="1", TLAB_TMP=str(tmp_path))
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300, env=env)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "DIST_CPU_OK" in r.stdout
