@@ -185,3 +185,98 @@ def test_one_rank_is_the_chunked_whole_line_solve():
     f = np.random.default_rng(12).standard_normal((1024, 3))
     err = np.linalg.norm(_split_solve(lu, f, 1) - _whole_line(lu, f)) / np.linalg.norm(_whole_line(lu, f))
     assert err <= 1e-13, err
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# non-periodic lines (y on the stretched grid): TRIDSS (linear3.f90:56-150) with windows of 6 chunks, and the claim behind
+# the compact BOUNDARY_BCS_NEUMANN_Y kernel: the derivative at a wall is determined by the 6 chunks next to that wall.
+def _biased_lu(n):
+    from oracle import fdm
+    from common import grid_tanh
+    g = fdm.Plan(grid_tanh(n), False, False, name="y")
+    return [g.der1.lu[1:, k].copy() for k in range(1, 4)]        # ibc = 0: alpha, beta, gamma of TRIDFS
+
+
+def _chunked_tridss(lu, f, only_chunks=None):
+    """x with look-back / look-ahead windows of LB chunks; `only_chunks`: the right-hand side of every other chunk is
+    treated as absent (zero), as the compact Neumann kernel does."""
+    alpha, beta, gamma = lu
+    n = alpha.size
+    T = n // C
+    a = alpha.copy(); a[0] = 0.0
+    d = beta.copy()
+    g = gamma * beta
+    g[n - 1] = 0.0
+    fz = f.copy()
+    if only_chunks is not None:
+        for t in range(T):
+            if t not in only_chunks:
+                fz[t * C:(t + 1) * C] = 0.0
+    P = np.zeros(n); Q = np.zeros(n); R = np.zeros(n); Af = np.zeros(T); Rb = np.zeros(T); Q0 = np.zeros(T)
+    xh = np.zeros_like(f); yend = np.zeros((T,) + f.shape[1:]); xh0 = np.zeros_like(yend)
+    for t in range(T):
+        s0 = t * C
+        w = 1.0
+        acc = 0.0
+        y = np.zeros((C,) + f.shape[1:])
+        for j in range(C):
+            w *= a[s0 + j]; P[s0 + j] = w
+            acc = fz[s0 + j] + a[s0 + j] * acc
+            y[j] = acc
+        Af[t] = w; yend[t] = acc
+        w, q, x = 1.0, 0.0, 0.0
+        for j in range(C - 1, -1, -1):
+            w *= g[s0 + j]; R[s0 + j] = w
+            q = d[s0 + j] * P[s0 + j] + g[s0 + j] * q; Q[s0 + j] = q
+            x = d[s0 + j] * y[j] + g[s0 + j] * x
+            xh[s0 + j] = x
+        Rb[t] = w; Q0[t] = q; xh0[t] = xh[s0]
+    A = np.zeros_like(yend)
+    for t in range(T):
+        w = 1.0
+        for k in range(1, LB + 1):
+            if t - k < 0:
+                break
+            A[t] = A[t] + w * yend[t - k]
+            w *= Af[t - k]
+    zeta = xh0 + Q0.reshape((T,) + (1,) * (f.ndim - 1)) * A
+    x = np.zeros_like(f)
+    for t in range(T):
+        B, w = 0.0, 1.0
+        for k in range(1, LB + 1):
+            if t + k > T - 1:
+                break
+            B = B + w * zeta[t + k]
+            w *= Rb[t + k]
+        sl = slice(t * C, (t + 1) * C)
+        shape = (C,) + (1,) * (f.ndim - 1)
+        x[sl] = xh[sl] + Q[sl].reshape(shape) * A[t] + R[sl].reshape(shape) * B
+    return x
+
+
+def test_chunked_biased_line_solve_equals_tridss():
+    from oracle import fdm
+    n = 512
+    lu = _biased_lu(n)
+    f = np.random.default_rng(13).standard_normal((n, 4))
+    ref = f.copy()
+    fdm.tridss(*lu, ref)
+    got = _chunked_tridss(lu, f)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) <= 1e-13
+
+
+def test_wall_values_feel_six_chunks_only():
+    """The solution next to a wall changes by less than 1e-15 of its size when the right-hand side beyond the 6 chunks
+    next to that wall is dropped (what the Neumann boundary-value kernel relies on)."""
+    from oracle import fdm
+    n = 512
+    T = n // C
+    lu = _biased_lu(n)
+    f = np.random.default_rng(14).standard_normal((n, 4))
+    ref = f.copy()
+    fdm.tridss(*lu, ref)
+    bottom = _chunked_tridss(lu, f, only_chunks=set(range(LB)))
+    top = _chunked_tridss(lu, f, only_chunks=set(range(T - LB, T)))
+    scale = np.abs(ref).max()
+    assert np.abs(bottom[:2] - ref[:2]).max() <= 1e-15 * scale
+    assert np.abs(top[-2:] - ref[-2:]).max() <= 1e-15 * scale
