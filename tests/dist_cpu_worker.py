@@ -1,4 +1,4 @@
-"""gloo worker (CPU, world_size 2): the K-transpose layout of tlab_b200.mpi against the global-array definition, and the
+"""gloo worker (CPU, world_size 2): the K-transpose layout (tests/trp_layout_ref.py) against the global-array definition, and the
 slab-wise restart files of a split domain."""
 import os
 import sys
@@ -9,6 +9,8 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import trp_layout_ref as R  # noqa: E402
 
 
 def main():
@@ -20,22 +22,22 @@ def main():
     rng = np.random.default_rng(5)
     full = rng.standard_normal((nz, nxy))                 # Fortran a(nxy, nz) = C (nz, nxy)
     a = torch.from_numpy(full[koff:koff + kmax].copy())
-    b = mpi.trp_k_forward_ref(a)                          # pencil (nz, nxy/P): lines rank*nl .. (rank+1)*nl
+    b = R.trp_k_forward_ref(a)                          # pencil (nz, nxy/P): lines rank*nl .. (rank+1)*nl
     nl = nxy // world
     expect = full[:, rank * nl:(rank + 1) * nl]
     assert np.array_equal(b.numpy(), expect), "forward map (tlab_mpi_transpose.f90:301-325)"
-    back = mpi.trp_k_backward_ref(b, kmax)
+    back = R.trp_k_backward_ref(b, kmax)
     assert torch.equal(back, a), "backward is the inverse"
     # complex data: (re, im) pairs travel together
     cf = rng.standard_normal((nz, nxy)) + 1j * rng.standard_normal((nz, nxy))
     ca = torch.from_numpy(np.ascontiguousarray(cf[koff:koff + kmax]).view(np.float64).copy())   # (kmax, 2*nxy)
     # treat complex elements as blocks of 2 doubles: partition by complex lines
-    cb = mpi.trp_k_forward_ref(ca.reshape(kmax, nxy, 2).reshape(kmax, nxy * 2))
+    cb = R.trp_k_forward_ref(ca.reshape(kmax, nxy, 2).reshape(kmax, nxy * 2))
     got = cb.numpy().reshape(nz, nl, 2)
     exp = np.ascontiguousarray(cf[:, rank * nl:(rank + 1) * nl]).view(np.float64).reshape(nz, nl, 2)
     assert np.array_equal(got, exp)
     # pack/unpack are inverse permutations
-    assert torch.equal(mpi.unpack_k(mpi.pack_k(a, world)), a)
+    assert torch.equal(R.unpack_k(R.pack_k(a, world)), a)
     # restart files of a split domain (tlab_b200/io.py): every rank writes its z-slab in place, like the MPI-IO sub-array
     # view of IO_Write_Fields (io_fields.f90:346-456); rank 0 owns the header; everybody reads its slab back
     from tlab_b200 import io as tio

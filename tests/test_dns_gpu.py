@@ -266,3 +266,78 @@ def test_long_periodic_lines_cta_pairs(cuda, pair):
     for i in range(3):
         assert rel_l2(g.get("q%d" % (i + 1)), o.q[i]) <= 1e-11
     assert rel_l2(g.get("s1"), o.s[0]) <= 1e-11
+
+
+def test_two_scalars_with_different_diffusivities(cuda):
+    """inb_scal = 2: the "further scalars" branch of the RHS (rhs_global_incompressible_1.f90:149-162 loops over every
+    scalar with its own diffusivity visc/Sc_is and its own boundary conditions).  Two RK steps against the oracle.
+    (The reference examples with two prognostic scalars -- Case11/12/17-19 -- all add physics outside SURVEY section 8:
+    buffer-zone relaxation, AirWaterLinear thermodynamics, radiation; hence the oracle, not a dns.out.ref golden.)"""
+    from oracle import fdm, dns as OD
+    from tlab_b200 import opr, dns as GD
+    nx, ny, nz = 48, 64, 32
+    x, y, z = grid_periodic(nx), grid_tanh(ny), grid_periodic(nz)
+    go = [fdm.Plan(x, True, True, name="x"), fdm.Plan(y, False, False, name="y"), fdm.Plan(z, True, True, name="z")]
+    gg = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, False, name="y"), opr.FdmPlan(z, True, True, name="z")]
+    D, N = OD.DNS_BCS_DIRICHLET, OD.DNS_BCS_NEUMANN
+    kw = dict(visc=1.0 / 5000.0, schmidt=[1.0, 0.7], buoyancy_type="linear", buoyancy_params=(1.0, 0.0),
+              buoyancy_vector=(0.0, 1.0, 0.0), bcs_flow_jmin=(D, D, D), bcs_flow_jmax=(N, D, N),
+              bcs_scal_jmin=(D, N), bcs_scal_jmax=(N, D))
+    o, g = OD.Dns(go, **kw), GD.Dns(gg, **kw)
+    shape = (nz, ny, nx)
+    wall = np.sin(0.5 * np.pi * y / y[-1])[None, :, None]
+    for i in range(3):
+        f = 0.5 * smooth_field(shape, (x, y, z), seed=31 + i) * wall
+        o.q[i][...] = f
+        g.set("q%d" % (i + 1), f)
+    for i in range(2):
+        sc = 0.5 + 0.1 * smooth_field(shape, (x, y, z), seed=40 + i) * wall
+        o.s[i][...] = sc
+        g.set("s%d" % (i + 1), sc)
+    o.dte = 1e-3
+    o.sources_flow()
+    o.rhs_global_incompressible_1()
+    g.substep(1e-3, 0.0, False)
+    for i in range(2):
+        assert rel_l2(g.get("hs%d" % (i + 1)), o.hs[i]) <= 1e-12
+    _, g = None, GD.Dns(gg, **kw)
+    o = OD.Dns(go, **kw)
+    for i in range(3):
+        f = 0.5 * smooth_field(shape, (x, y, z), seed=31 + i) * wall
+        o.q[i][...] = f
+        g.set("q%d" % (i + 1), f)
+    for i in range(2):
+        sc = 0.5 + 0.1 * smooth_field(shape, (x, y, z), seed=40 + i) * wall
+        o.s[i][...] = sc
+        g.set("s%d" % (i + 1), sc)
+    for _ in range(2):
+        o.runge_kutta(1e-3)
+        g.runge_kutta(1e-3)
+    for i in range(3):
+        assert rel_l2(g.get("q%d" % (i + 1)), o.q[i]) <= 1e-11
+    for i in range(2):
+        assert rel_l2(g.get("s%d" % (i + 1)), o.s[i]) <= 1e-11
+
+
+def test_two_live_states_of_different_size(cuda):
+    """Two tlab_dns_t handles alive at once, different grids and different viscosities, stepped alternately: each owns its
+    Poisson solver (cuFFT plans, eigenvalues, per-mode planes) and re-points the diffusion-scaled LU sets of its plans
+    before every RHS, so neither disturbs the other (the reference has one set of module variables per process; a library
+    with handles must not)."""
+    o1, g1 = _pair(32, 33, 16, "tanh")
+    o2, g2 = _pair(64, 48, 32, "stretched", free_slip_top=False)
+    for _ in range(2):
+        o1.runge_kutta(1e-3)
+        o2.runge_kutta(2e-3)
+        g1.runge_kutta(1e-3)
+        g2.runge_kutta(2e-3)
+    for o, g in ((o1, g1), (o2, g2)):
+        for i in range(3):
+            assert rel_l2(g.get("q%d" % (i + 1)), o.q[i]) <= 1e-11
+        assert rel_l2(g.get("s1"), o.s[0]) <= 1e-11
+    # the stand-alone operator API keeps its own (process-wide) solver: initialising it must not disturb the handles either
+    from tlab_b200 import opr
+    opr.OPR_Elliptic_Initialize(g2.g)
+    o1.runge_kutta(1e-3)
+    g1.runge_kutta(1e-3)
+    assert rel_l2(g1.get("q2"), o1.q[1]) <= 1e-11

@@ -33,11 +33,15 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")) + glob.glob(os.path.join(CSRC, "*.cpp")))
 
 
+def headers():
+    return glob.glob(os.path.join(CSRC, "*.h")) + glob.glob(os.path.join(CSRC, "*.cuh"))
+
+
 def needs_build():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.h")) + [os.path.join(HERE, "..", "include", "tlab_gpu.h"),
+    deps = sources() + headers() + [os.path.join(HERE, "..", "include", "tlab_gpu.h"),
                                                                os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
@@ -58,7 +62,7 @@ def build(force=False, verbose=False):
         obj = os.path.join(objdir, os.path.basename(src) + ".o")
         objs.append(obj)
         if (not force and os.path.exists(obj) and os.path.getmtime(obj) > os.path.getmtime(src)
-                and all(os.path.getmtime(obj) > os.path.getmtime(h) for h in glob.glob(os.path.join(CSRC, "*.h")))
+                and all(os.path.getmtime(obj) > os.path.getmtime(h) for h in headers())
                 and os.path.getmtime(obj) > os.path.getmtime(os.path.join(HERE, "..", "include", "tlab_gpu.h"))):
             continue
         cmd = common + (["-x", "cu"] if src.endswith(".cpp") else []) + ["-c", src, "-o", obj]

@@ -226,6 +226,11 @@ struct Dns {
     double* host_stage = nullptr;        // pinned staging buffer for the *_host entry points
     size_t host_stage_bytes = 0;
     long long launches = 0;
+    // Per-handle operator state (two live handles of different size must not share it): the Poisson solver with its
+    // cuFFT plans, eigenvalues and per-mode planes is owned here; the diffusion-scaled LU sets of OPR_Burgers live on the
+    // plans and are re-pointed by activate(); the split-z exchange blocks are re-sized by activate() when the geometry differs.
+    Poisson* pois = nullptr;
+    int bfirst[3] = {-1, -1, -1};
     bool defer_v = false;      // substep(): `hq2 -= dpdy` and the wall planes of hq2 are left to the fused update of q2
     bool v_deferred = false;   // ... and rhs() did leave them (non-overlapped schedule, Dirichlet at both walls)
 
@@ -366,7 +371,7 @@ struct Dns {
         { ProfScope ps(PC_ELEMENTWISE);
         get_planes_kernel<<<(unsigned)((np + 255) / 256), 256, 0, s0>>>(hq[1], hb, ht, nx, ny, nz); }
         launches++;
-        if ((rc = poisson().solve(tmp1, c1, c2, hb, ht, tmp3))) return rc;
+        if ((rc = pois->solve(tmp1, c1, c2, hb, ht, tmp3))) return rc;
         launches += 2;
         // -- hq -= grad p
         cudaEventRecord(event(0), s0);
@@ -387,7 +392,17 @@ struct Dns {
         return rhs_bcs();
     }
 
+    int activate() {
+        for (int i = 0; i < 3; i++) { g[i]->burgers_first = bfirst[i]; g[i]->burgers_count = ns + 1; }
+        if (!pois || !pois->ready || pois->nx != nx || pois->ny != ny || pois->nz != nz)
+            return fail(TLAB_ERR_DIMGRID, "tlab_dns: the Poisson solver of this handle is not initialised for its grid");
+        if (P > 1 && ctx().tune_splitz && nzg > 1)
+            return splitz().init((long long)nx * ny, nz, nzg, P, trp().rank, 0);
+        return 0;
+    }
+
     int rhs(double dte) {
+        if (int rc0 = activate()) return rc0;
         bool split = true;
         for (int is = 0; is <= ns && split; is++) split = use_split(is);
         v_deferred = false;
@@ -433,7 +448,7 @@ struct Dns {
         { ProfScope ps(PC_ELEMENTWISE);
         get_planes_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(hq[1], hb, ht, nx, ny, nz); }
         launches++;
-        if ((rc = poisson().solve(tmp1, c1, c2, hb, ht, tmp3))) return rc;     // (:284)
+        if ((rc = pois->solve(tmp1, c1, c2, hb, ht, tmp3))) return rc;     // (:284)
         launches += 2;   // boundary planes, per-mode y solves (cuFFT's own kernels not counted)
         // hq -= grad p (:319-352)
         if ((rc = run_partial(1, TLAB_OPR_P1, nx, ny, nz, b0, g[0], tmp1, hq[0], nullptr, nullptr, 0.0, -1))) return rc;
@@ -521,6 +536,7 @@ struct Dns {
         allocs.clear();
         if (host_stage) cudaFreeHost(host_stage);
         host_stage = nullptr;
+        if (pois) { pois->release(); delete pois; pois = nullptr; }
     }
 };
 
@@ -551,6 +567,9 @@ int tlab_dns_create(const tlab_dns_params* prm, tlab_plan_t gx, tlab_plan_t gy, 
     if (int rc = tlab_gpu_init(-1)) return rc;
     if (!prm || !gx || !gy || !gz || !out) return fail(TLAB_ERR_OPTION, "tlab_dns_create: null argument");
     if (prm->nscal < 0 || prm->nscal > TLAB_MAX_SCAL) return fail(TLAB_ERR_OPTION, "tlab_dns_create: too many scalars");
+    // Gravity_Buoyancy, EQNS_BOD_LINEAR (gravity.f90:248-260): this path implements the branch locProps%scalar(1) == 1,
+    // b = c1 s1 - (ref - c0), for any number of prognostic scalars.  buoyancy_params = (c1, c0): the caller passes
+    // c0 = parameters(inb_scal_array + 1) itself and must not select this path when scalar(1) > 1 (the Fortran shim checks).
     if (prm->rkm_mode != TLAB_RKM_EXP3 && prm->rkm_mode != TLAB_RKM_EXP4)
         return fail(TLAB_ERR_UNDEVELOP, "only the explicit RK3 / RK4(5) schemes are implemented");
     const int P = trp().P;
@@ -568,7 +587,8 @@ int tlab_dns_create(const tlab_dns_params* prm, tlab_plan_t gx, tlab_plan_t gy, 
     d.Nt = (long long)(d.nx + 2) * d.ny * d.nz;
     rk_tables(prm->rkm_mode, d.kdt, d.ktime, d.kco);
     int rc = tlab_opr_burgers_init(gx, gy, gz, prm->visc, prm->nscal, prm->schmidt);
-    if (!rc) rc = tlab_opr_elliptic_init(gx, gy, gz, prm->nz);
+    for (int i = 0; i < 3; i++) d.bfirst[i] = d.g[i]->burgers_first;
+    if (!rc) { d.pois = new Poisson(); rc = d.pois->init(gx, gy, gz, prm->nz); }
     d.q.resize(3); d.hq.resize(3); d.s.resize(d.ns); d.hs.resize(d.ns);
     for (int i = 0; i < 3 && !rc; i++) { rc = d.alloc(&d.q[i], d.N); if (!rc) rc = d.alloc(&d.hq[i], d.N); }
     for (int i = 0; i < d.ns && !rc; i++) { rc = d.alloc(&d.s[i], d.N); if (!rc) rc = d.alloc(&d.hs[i], d.N); }
@@ -654,6 +674,7 @@ int tlab_time_rungekutta(tlab_dns_t h, double dtime) {
 
 int tlab_time_rungekutta_host(tlab_dns_t h, double dtime, double* q_host, double* s_host) {
     if (!h || !q_host) return fail(TLAB_ERR_OPTION, "tlab_time_rungekutta_host: null argument");
+    if (h->d.ns > 0 && !s_host) return fail(TLAB_ERR_OPTION, "tlab_time_rungekutta_host: s_host is null but the state has scalars");
     Dns& d = h->d;
     cudaStream_t st = ctx().stream;
     const size_t fb = (size_t)d.N * sizeof(double);
@@ -699,6 +720,8 @@ int tlab_time_courant(tlab_dns_t h, double cfla, double cfld, double prandtl, do
             if (hp.size > 1) dx2i_y += mx;   // the maximum of the sum is the sum of the maxima on a tensor-product grid
         }
         d.dx2i = dx2i_y;
+    }
+    {   // the diffusivity factor depends on the caller's prandtl: recomputed on every call (time.f90:143-152)
         double sf = 1.0;
         sf = std::max(sf, 1.0 / prandtl);
         double smin = 1e300;

@@ -5,12 +5,10 @@ and the K-transpose index maps (src/base/tlab_mpi_transpose.f90:301-325).  torch
 exchange the NCCL unique id (the Fortran host would MPI_Bcast it); the transposes of the product run inside
 libtlab_gpu.so on its own NCCL communicator.
 
-The functions `pack_k`, `unpack_k`, `trp_k_forward_ref`, `trp_k_backward_ref` restate the pack/unpack layout
-of csrc/trp.cu on torch tensors so that the host-side logic can be tested with the gloo backend on CPUs.
+(The torch restatement of the pack/unpack layout used by the gloo CPU test lives in tests/trp_layout_ref.py.)
 """
 import ctypes
 
-import numpy as np
 import torch
 
 from . import lib as _lib
@@ -46,39 +44,3 @@ def slab(nz, rank, world):
         raise ValueError("Kmax(*) must divide the grid size in z")
     kmax = nz // world
     return kmax, rank * kmax
-
-
-# ---- layout restatement (torch, device agnostic) -------------------------------------------------------------
-def pack_k(a, P):
-    """a: slab (kmax, nxy) [C order = Fortran a(nxy, kmax)] -> send buffer (P, kmax, nxy/P)."""
-    kmax, nxy = a.shape
-    nl = nxy // P
-    return a.reshape(kmax, P, nl).permute(1, 0, 2).contiguous()
-
-
-def unpack_k(buf):
-    """receive buffer (P, kmax, nl) -> slab (kmax, P*nl)."""
-    P, kmax, nl = buf.shape
-    return buf.permute(1, 0, 2).reshape(kmax, P * nl).contiguous()
-
-
-def trp_k_forward_ref(a, group=None):
-    """TLabMPI_Trp_ExecK_Forward with torch.distributed.all_to_all_single: slab (kmax, nxy) -> pencil (nz, nxy/P)."""
-    import torch.distributed as dist
-    P = dist.get_world_size(group)
-    send = pack_k(a, P)
-    recv = torch.empty_like(send)
-    dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
-    kmax, nl = send.shape[1], send.shape[2]
-    return recv.reshape(P * kmax, nl)            # block q holds planes q*kmax .. (q+1)*kmax - 1
-
-
-def trp_k_backward_ref(b, kmax, group=None):
-    """TLabMPI_Trp_ExecK_Backward: pencil (nz, nl) -> slab (kmax, nl*P)."""
-    import torch.distributed as dist
-    P = dist.get_world_size(group)
-    nl = b.shape[1]
-    send = b.reshape(P, kmax, nl).contiguous()
-    recv = torch.empty_like(send)
-    dist.all_to_all_single(recv.view(-1), send.view(-1), group=group)
-    return unpack_k(recv)
