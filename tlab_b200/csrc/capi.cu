@@ -413,6 +413,8 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "pf_next")) ctx().tune_pf_next = value;
     else if (!std::strcmp(key, "poisson_minb")) ctx().tune_poisson_minb = value;
     else if (!std::strcmp(key, "poisson_split")) ctx().tune_poisson_split = value;
+    else if (!std::strcmp(key, "poisson_warp")) ctx().tune_poisson_warp = value;
+    else if (!std::strcmp(key, "poisson_pf")) ctx().tune_poisson_pf = value;
     else if (!std::strcmp(key, "poisson_il")) ctx().tune_poisson_il = value;
     else if (!std::strcmp(key, "poisson_factors")) ctx().tune_poisson_factors = value;
     else return fail(TLAB_ERR_OPTION, std::string("unknown tuning key ") + key);

@@ -28,6 +28,8 @@ struct Context {
     int tune_poisson_factors = 1;  // keep the per-mode LU factors of the Poisson y systems (8 more planes) instead of refactorising
     int tune_poisson_il = 0;      // Poisson: per-mode planes that are read together interleaved row by row (set before OPR_Elliptic_Initialize)
     int tune_poisson_split = -1;  // Poisson y solves: one thread per component instead of per mode (-1: when there are few modes)
+    int tune_poisson_warp = 4;    // Poisson y solves: team of warps per mode with the lines in registers (ny = 8 T <= 1024); value = kx per CTA (2, 4, 8), 0: off (set before OPR_Elliptic_Initialize)
+    int tune_poisson_pf = -1;     // team kernel: prefetch distance in CTAs (-1: two per SM, 0: off)
     int tune_poisson_minb = 3;  // resident CTAs per SM the Poisson y kernel is compiled for (register budget)
     int tune_pf_next = 0;     // fused Burgers launch: L2 prefetch of the tile's next field
     int tune_fuse = 0;        // RHS: one fused Burgers launch per direction (fields sharing the advecting velocity)

@@ -391,7 +391,7 @@ __global__ void poisson_fundamental_kernel(PoissonDev D) {
 
 // -------------------------------------------------------------------------------------------------
 // per call: regular modes, Neumann/Neumann (OPR_ODE2_Factorize_NN)
-__device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ cf, double* __restrict__ cv, int i, int k);
+__device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ cf, double* __restrict__ cv, int i, int k, long long slot);
 
 // NL = 2: one thread per mode, both components (real, imaginary) of the mode in the same thread, which shares the factor
 // and fundamental-solution loads.  NL = 1: one thread per component (adjacent lanes = re, im of a mode: unit-stride
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
     const int l0 = (NL == 1) ? (int)(h & 1) : 0;
     if (m >= D.nmodes) return;
     const int i = (int)(m % D.nxh), k = (int)(m / D.nxh);
-    if (mode_is_singular(D, i, k)) { if (l0 == 0) poisson_singular_mode(D, cf, cv, i, k); return; }
+    if (mode_is_singular(D, i, k)) { if (l0 == 0) poisson_singular_mode(D, cf, cv, i, k, m); return; }
     const double lam = sqrt(D.lambda[m]);
     const long long NM = D.nmodes;
     const long long plane_sz = D.plane_sz;
@@ -510,9 +510,10 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
 }
 
 // per call: the (up to four) singular modes, OPR_ODE2_Factorize_NN_Sing -> _DN_Sing
-__device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ cf, double* __restrict__ cv, int i, int k) {
-    const long long m = (long long)i + (long long)D.nxh * k;
-    const double lam = sqrt(D.lambda[m]);
+// `slot` selects the per-mode planes (the mode index for the full planes, 0..3 for the small planes of the warp path)
+__device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ cf, double* __restrict__ cv, int i, int k, long long slot) {
+    const double lam = sqrt(D.lambda[(long long)i + (long long)D.nxh * k]);
+    const long long m = slot;
     const long long NM = D.nmodes;
     const long long plane_sz = D.plane_sz;
     const int n = D.ny;
@@ -560,6 +561,510 @@ __device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ 
             ul[l].set(r, ul[l].get(r) + cdu * u1.get(r));
             vl[l].set(r, vl[l].get(r) + cdu * v1.get(r));
         }
+    }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Team-per-mode y solves (ny = 8 T, T <= 128).  A team of NW = 1, 2 or 4 warps owns one (kx, kz) mode, one lane one chunk of
+// 8 rows, the lines of both components (real, imaginary) live in registers.  The substitution stages of PENTADSS are
+// second-order linear recurrences,
+//     forward   y_r = f_r - b_r y_{r-1} - a_r y_{r-2},      backward  x_r = (y_r - d_r x_{r+1} - e_r x_{r+2}) / c_r,
+// so a chunk maps its two inflow values to its two outflow values by an affine 2x2 map.  Every lane sweeps its chunk once
+// with zero inflow (end values and the homogeneous map only), the true inflow of all chunks follows from a scan of the maps
+// (Kogge-Stone over the lanes of a warp, 5 shuffle steps, then the warp totals through shared memory; unlike the
+// tridiagonal line kernels the maps do not decay for small wavenumbers, so no window), and a second sweep produces the rows.
+// Per (mode, row) the kernel reads the forcing (2 doubles), the upper LU factors 1/c, -d of both systems (4; the lower
+// factors a, b are rebuilt from them and the shared tables, the fifth diagonal from the tables) and the five fundamental
+// lines, and writes p^ and dp^/dy (4): 15 doubles against the 37 of the thread-per-mode kernel, which parks the
+// intermediate vector in global memory and re-reads every line per sweep.
+// The complex lines are strided by nx/2+1 in memory: a CTA of MW teams takes MW adjacent kx and moves the (ny x MW) tile
+// through shared memory with row segments of MW * 16 bytes on the global side.
+constexpr int TR = 8;                          // rows per lane
+__host__ __device__ inline int tpad(int r0) { return (r0 >> 3) * 9 + (r0 & 7); }      // 0-based row -> tile slot (conflict-free chunk reads)
+
+__device__ __forceinline__ double2 operator*(double2 a, double s) { return make_double2(a.x * s, a.y * s); }
+__device__ __forceinline__ double2 operator+(double2 a, double2 b) { return make_double2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ double2 fma2(double s, double2 a, double2 c) { return make_double2(fma(s, a.x, c.x), fma(s, a.y, c.y)); }
+__device__ __forceinline__ double shfl_up_d(double v, int d) { return __shfl_up_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double shfl_dn_d(double v, int d) { return __shfl_down_sync(0xffffffffu, v, d); }
+__device__ __forceinline__ double2 shfl_up_2(double2 v, int d) { return make_double2(shfl_up_d(v.x, d), shfl_up_d(v.y, d)); }
+__device__ __forceinline__ double2 shfl_dn_2(double2 v, int d) { return make_double2(shfl_dn_d(v.x, d), shfl_dn_d(v.y, d)); }
+
+// affine map of a chunk: (s1, s2) -> (m11 s1 + m12 s2 + p1, m21 s1 + m22 s2 + p2); s1 is the value next to the chunk
+struct Aff { double m11, m12, m21, m22; double2 p1, p2; };
+
+__device__ __forceinline__ void prefetch_l2g(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <int NW>
+__device__ __forceinline__ void team_barrier(int id) {
+    if (NW == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(NW * 32) : "memory");
+}
+
+// Scan over the chunks of a team; DIR = +1: chunk j follows chunk j-1 (forward sweep), DIR = -1: chunk j follows chunk j+1.
+// Returns the inflow of this lane's chunk, i.e. the outflow of the composition of all chunks before it (zero state first).
+// xch: NW slots of shared memory of this team and this scan.
+template <int DIR, int NW>
+__device__ __forceinline__ void team_scan(Aff a, int lane, int wt, Aff* __restrict__ xch, int barid, double2& in1, double2& in2) {
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        Aff e;      // the earlier group
+        if (DIR > 0) {
+            e.m11 = shfl_up_d(a.m11, off); e.m12 = shfl_up_d(a.m12, off); e.m21 = shfl_up_d(a.m21, off); e.m22 = shfl_up_d(a.m22, off);
+            e.p1 = shfl_up_2(a.p1, off); e.p2 = shfl_up_2(a.p2, off);
+        } else {
+            e.m11 = shfl_dn_d(a.m11, off); e.m12 = shfl_dn_d(a.m12, off); e.m21 = shfl_dn_d(a.m21, off); e.m22 = shfl_dn_d(a.m22, off);
+            e.p1 = shfl_dn_2(a.p1, off); e.p2 = shfl_dn_2(a.p2, off);
+        }
+        const bool has = (DIR > 0) ? (lane >= off) : (lane + off < 32);
+        if (has) {      // a := a o e
+            Aff r;
+            r.m11 = a.m11 * e.m11 + a.m12 * e.m21; r.m12 = a.m11 * e.m12 + a.m12 * e.m22;
+            r.m21 = a.m21 * e.m11 + a.m22 * e.m21; r.m22 = a.m21 * e.m12 + a.m22 * e.m22;
+            r.p1 = fma2(a.m11, e.p1, fma2(a.m12, e.p2, a.p1));
+            r.p2 = fma2(a.m21, e.p1, fma2(a.m22, e.p2, a.p2));
+            a = r;
+        }
+    }
+    double2 c1 = make_double2(0.0, 0.0), c2 = c1;          // state entering this warp
+    double2 o1 = a.p1, o2 = a.p2;                            // state leaving this lane's chunk
+    if (NW > 1) {
+        if (lane == (DIR > 0 ? 31 : 0)) xch[wt] = a;
+        team_barrier<NW>(barid);
+#pragma unroll
+        for (int s = 0; s < NW - 1; s++) {
+            const int wq = (DIR > 0) ? s : NW - 1 - s;
+            const bool before = (DIR > 0) ? (wq < wt) : (wq > wt);
+            if (before) {
+                const Aff e = xch[wq];
+                const double2 n1 = fma2(e.m11, c1, fma2(e.m12, c2, e.p1));
+                const double2 n2 = fma2(e.m21, c1, fma2(e.m22, c2, e.p2));
+                c1 = n1; c2 = n2;
+            }
+        }
+        o1 = fma2(a.m11, c1, fma2(a.m12, c2, a.p1));
+        o2 = fma2(a.m21, c1, fma2(a.m22, c2, a.p2));
+    }
+    if (DIR > 0) {
+        in1 = shfl_up_2(o1, 1); in2 = shfl_up_2(o2, 1);
+        if (lane == 0) { in1 = c1; in2 = c2; }
+    } else {
+        in1 = shfl_dn_2(o1, 1); in2 = shfl_dn_2(o2, 1);
+        if (lane == 31) { in1 = c1; in2 = c2; }
+    }
+}
+
+// One first-order integral problem u' + lam u = f of one mode, both components, on a team.
+//   X[q]     in: forcing (already scaled) at row r0 + q, r0 = 8 j + 1 (j = chunk); out: result rows (rows 1 and n included)
+//   Fm1, Fp1 the forcing rows before / after the chunk
+//   F1, FN   the values used instead of rows 1 and n of the forcing (see int1_solve), bc the imposed value
+//   fac      upper LU factors (1/c, -d) of this mode and side in lane order
+//   cs       64 doubles of shared memory of this team: the reduced boundary rows (they depend on lambda; every lane would
+//            otherwise hold ~50 doubles of them in registers although only the first and the last lane use them)
+//   xch      2 * NW scan slots of this team;  du: derivative at row n (BCS_MAX only; valid in the last lane)
+enum { CS_LE = 0, CS_LA = 5, CS_LB = 10, CS_RB = 16, CS_RT = 28 };       // Le[1..5], La[1..5], Lb[1..5], rb[1..3][0..3], rt[0..2][1..4]
+template <bool IS_MIN, int NW>
+__device__ __forceinline__ void team_int1(const Int1Dev& P, const WarpSide& W, const double2* __restrict__ fac, double lam, int T, int j,
+                                          int lane, int wt, int barid, double2 (&X)[TR], double2 Fm1, double2 Fp1, double2 F1, double2 FN,
+                                          double2 bc, double* __restrict__ cs, Aff* __restrict__ xch, double2* du) {
+    const int n = P.n;
+    const bool active = j < T, first = (j == 0), last = (j == T - 1);
+    const double2 zero = make_double2(0.0, 0.0);
+    auto Lrow = [&](int r, double (&row)[6]) {
+#pragma unroll
+        for (int k = 1; k <= 5; k++) row[k] = __ldg(&P.L0[(r - 1) * 5 + k - 1]) + lam * __ldg(&P.L1[(r - 1) * 5 + k - 1]);
+    };
+    auto rhs = [&](int r, int k) { return __ldg(&P.rhs[(r - 1) * 3 + k - 1]); };
+    // ---- reduction of the far-end row into its neighbours (as in int1_solve), by the first lane into shared memory
+    if (first) {
+        double Le[6], La[6], Lb[6];
+        double rb[4][4], rt[3][5];
+#pragma unroll
+        for (int r = 1; r <= 3; r++)
+#pragma unroll
+            for (int c = 0; c <= 3; c++) rb[r][c] = P.rb[r][c];
+#pragma unroll
+        for (int r = 0; r <= 2; r++)
+#pragma unroll
+            for (int c = 1; c <= 4; c++) rt[r][c] = P.rt[r][c];
+        if (IS_MIN) {
+            Lrow(n, Le); Lrow(n - 1, La); Lrow(n - 2, Lb);
+            const double dummy = 1.0 / Le[3];
+#pragma unroll
+            for (int k = 1; k <= 5; k++) Le[k] = -Le[k] * dummy;
+            Le[3] = 1.0;
+            La[1] = La[1] + La[4] * Le[5]; La[2] = La[2] + La[4] * Le[1]; La[3] = La[3] + La[4] * Le[2];
+            Lb[2] = Lb[2] + Lb[5] * Le[5]; Lb[3] = Lb[3] + Lb[5] * Le[1]; Lb[4] = Lb[4] + Lb[5] * Le[2];
+#pragma unroll
+            for (int r = 0; r <= 2; r++)
+#pragma unroll
+                for (int c = 1; c <= 3; c++) rt[r][c] = rhs(n - 2 + r, c);
+#pragma unroll
+            for (int c = 1; c <= 3; c++) rt[2][c] = rt[2][c] * dummy;
+            rt[1][1] = rt[1][1] - La[4] * rt[2][3]; rt[1][2] = rt[1][2] - La[4] * rt[2][1]; rt[1][3] = rt[1][3] - La[4] * rt[2][2];
+            rt[0][2] = rt[0][2] - Lb[5] * rt[2][3]; rt[0][3] = rt[0][3] - Lb[5] * rt[2][1]; rt[0][4] = rt[0][4] - Lb[5] * rt[2][2];
+        } else {
+            Lrow(1, Le); Lrow(2, La); Lrow(3, Lb);
+            const double dummy = 1.0 / Le[3];
+#pragma unroll
+            for (int k = 1; k <= 5; k++) Le[k] = -Le[k] * dummy;
+            Le[3] = 1.0;
+            La[3] = La[3] + La[2] * Le[4]; La[4] = La[4] + La[2] * Le[5]; La[5] = La[5] + La[2] * Le[1];
+            Lb[2] = Lb[2] + Lb[1] * Le[4]; Lb[3] = Lb[3] + Lb[1] * Le[5]; Lb[4] = Lb[4] + Lb[1] * Le[1];
+#pragma unroll
+            for (int r = 1; r <= 3; r++)
+#pragma unroll
+                for (int c = 1; c <= 3; c++) rb[r][c] = rhs(r, c);
+#pragma unroll
+            for (int c = 1; c <= 3; c++) rb[1][c] = rb[1][c] * dummy;
+            rb[2][1] = rb[2][1] - La[2] * rb[1][2]; rb[2][2] = rb[2][2] - La[2] * rb[1][3]; rb[2][3] = rb[2][3] - La[2] * rb[1][1];
+            rb[3][0] = rb[3][0] - Lb[1] * rb[1][2]; rb[3][1] = rb[3][1] - Lb[1] * rb[1][3]; rb[3][2] = rb[3][2] - Lb[1] * rb[1][1];
+        }
+#pragma unroll
+        for (int k = 1; k <= 5; k++) { cs[CS_LE + k - 1] = Le[k]; cs[CS_LA + k - 1] = La[k]; cs[CS_LB + k - 1] = Lb[k]; }
+#pragma unroll
+        for (int r = 1; r <= 3; r++)
+#pragma unroll
+            for (int c = 0; c <= 3; c++) cs[CS_RB + (r - 1) * 4 + c] = rb[r][c];
+#pragma unroll
+        for (int r = 0; r <= 2; r++)
+#pragma unroll
+            for (int c = 1; c <= 4; c++) cs[CS_RT + r * 4 + c - 1] = rt[r][c];
+    }
+    team_barrier<NW>(barid);
+    auto Le = [&](int k) { return cs[CS_LE + k - 1]; };
+    auto La = [&](int k) { return cs[CS_LA + k - 1]; };
+    auto Lb = [&](int k) { return cs[CS_LB + k - 1]; };
+    auto rb = [&](int r, int c) { return cs[CS_RB + (r - 1) * 4 + c]; };
+    auto rt = [&](int r, int c) { return cs[CS_RT + r * 4 + c - 1]; };
+
+    // ---- right-hand side (MatMul_3d with the reduced boundary rows) in place; rows 1 and n are not part of the system
+    double2 bcs_far = zero, fn1 = zero;                       // fn1 = forcing at row n-1 (for du)
+    {
+        double2 s1 = zero, s2 = zero, s5 = zero, s6 = zero;
+        if (first) {
+            if (!IS_MIN) bcs_far = F1 * rb(1, 2) + X[1] * rb(1, 3) + X[2] * rb(1, 1);
+            s1 = F1 * rb(2, 1) + X[1] * rb(2, 2) + X[2] * rb(2, 3);
+            s2 = F1 * rb(3, 0) + X[1] * rb(3, 1) + X[2] * rb(3, 2) + X[3] * rb(3, 3);
+        }
+        if (last) {       // rows n-2 (q = 5), n-1 (q = 6), n (q = 7)
+            if (IS_MIN) bcs_far = X[5] * rt(2, 3) + X[6] * rt(2, 1) + FN * rt(2, 2);
+            s5 = X[4] * rt(0, 1) + X[5] * rt(0, 2) + X[6] * rt(0, 3) + FN * rt(0, 4);
+            s6 = X[5] * rt(1, 1) + X[6] * rt(1, 2) + FN * rt(1, 3);
+            fn1 = X[6];
+        }
+        double2 prev = Fm1;
+#pragma unroll
+        for (int q = 0; q < TR; q++) {
+            const double2 cur = X[q], up = (q < TR - 1) ? X[q < TR - 1 ? q + 1 : q] : Fp1;
+            const double2 c = active ? __ldg(W.rh + q * T + j) : zero;
+            X[q] = prev * c.x + cur * c.y + up;
+            prev = cur;
+        }
+        if (first) { X[0] = zero; X[1] = s1; X[2] = s2; }
+        if (last) { X[5] = s5; X[6] = s6; X[7] = zero; }
+        if (!active) {
+#pragma unroll
+            for (int q = 0; q < TR; q++) X[q] = zero;
+        }
+    }
+
+    // ---- forward sweep.  The lower factors -a, -b of a row are rebuilt from the stored upper factors (1/c, -d) of the two
+    // previous rows and the table rows (PENTADFS: a = A / c(r-2), b = (B - a d(r-2)) / c(r-1)).
+    {
+        double na[TR], nb[TR];
+        double2 f1 = (active && j > 0) ? __ldg(fac + (TR - 1) * T + j - 1) : zero;      // factors of rows r0 - 1, r0 - 2
+        double2 f2 = (active && j > 0) ? __ldg(fac + (TR - 2) * T + j - 1) : zero;
+        Aff a;
+        double2 p1 = zero, p2 = zero;
+        double h11 = 1.0, h12 = 0.0, h21 = 0.0, h22 = 1.0;       // (y_{q-1}, y_{q-2}) as functions of the inflow (s1, s2)
+#pragma unroll
+        for (int q = 0; q < TR; q++) {
+            const double2 ta = active ? __ldg(W.ab0 + q * T + j) : zero, tb = active ? __ldg(W.ab1 + q * T + j) : zero;
+            double Ar = ta.x + lam * ta.y, Br = tb.x + lam * tb.y;
+            if (IS_MIN && last && q == 5) { Ar = Lb(1); Br = Lb(2); }        // rows n-2, n-1: the reduced rows Lb, La
+            if (IS_MIN && last && q == 6) { Ar = La(1); Br = La(2); }
+            if (!IS_MIN && first && q == 2) Br = Lb(2);                        // row 3 of a BCS_MAX system: reduced row Lb
+            double av = Ar * f2.x;
+            if (first && q <= 2) av = 0.0;                                     // rows 2, 3 (m = 1, 2): no second sub-diagonal
+            double bv = (Br + av * f2.y) * f1.x;
+            if ((first && q <= 1) || (last && q == TR - 1)) { av = 0.0; bv = 0.0; }     // rows 1, n (not in the system), row 2 (m = 1)
+            na[q] = -av; nb[q] = -bv;
+            f2 = f1; f1 = active ? __ldg(fac + q * T + j) : zero;
+            const double2 y = fma2(nb[q], p1, fma2(na[q], p2, X[q]));
+            const double g1 = nb[q] * h11 + na[q] * h21, g2 = nb[q] * h12 + na[q] * h22;
+            p2 = p1; p1 = y;
+            h21 = h11; h22 = h12; h11 = g1; h12 = g2;
+        }
+        a.m11 = h11; a.m12 = h12; a.m21 = h21; a.m22 = h22; a.p1 = p1; a.p2 = p2;
+        double2 s1, s2;
+        team_scan<+1, NW>(a, lane, wt, xch, barid, s1, s2);
+#pragma unroll
+        for (int q = 0; q < TR; q++) {
+            const double2 y = fma2(nb[q], s1, fma2(na[q], s2, X[q]));
+            X[q] = y;
+            s2 = s1; s1 = y;
+        }
+    }
+
+    // ---- backward sweep.  The fifth diagonal is untouched by the elimination: -e from the tables (row 2 of a BCS_MAX system
+    // is the one reduced row whose e changed).
+    {
+        double ic[TR], nd[TR], ne[TR];
+#pragma unroll
+        for (int q = 0; q < TR; q++) {
+            const double2 t = active ? __ldg(fac + q * T + j) : zero;
+            const double2 e = active ? __ldg(W.e + q * T + j) : zero;
+            ic[q] = t.x; nd[q] = t.y;
+            ne[q] = -(e.x + lam * e.y);
+        }
+        if (!IS_MIN && first) ne[1] = -La(5);
+        Aff a;
+        double2 p1 = zero, p2 = zero;
+        double h11 = 1.0, h12 = 0.0, h21 = 0.0, h22 = 1.0;
+#pragma unroll
+        for (int q = TR - 1; q >= 0; q--) {
+            const double2 x = fma2(nd[q], p1, fma2(ne[q], p2, X[q])) * ic[q];
+            const double g1 = (nd[q] * h11 + ne[q] * h21) * ic[q], g2 = (nd[q] * h12 + ne[q] * h22) * ic[q];
+            p2 = p1; p1 = x;
+            h21 = h11; h22 = h12; h11 = g1; h12 = g2;
+        }
+        a.m11 = h11; a.m12 = h12; a.m21 = h21; a.m22 = h22; a.p1 = p1; a.p2 = p2;
+        double2 s1, s2;
+        team_scan<-1, NW>(a, lane, wt, xch + NW, barid, s1, s2);
+#pragma unroll
+        for (int q = TR - 1; q >= 0; q--) {
+            const double2 x = fma2(nd[q], s1, fma2(ne[q], s2, X[q])) * ic[q];
+            X[q] = x;
+            s2 = s1; s1 = x;
+        }
+    }
+
+    // ---- closure rows
+    if (IS_MIN) {
+        if (first) X[0] = bc;
+        if (last) {
+            double2 v = bcs_far;
+            v = v + X[6] * Le(2);
+            v = v + X[5] * Le(1);
+            v = v + X[4] * Le(5);
+            X[7] = v;
+        }
+    } else {
+        if (last) {
+            X[7] = bc;
+            if (du) {
+                double row[6];
+                Lrow(n, row);
+                double2 v = bc * row[3];
+                v = v + X[6] * row[2];
+                v = v + X[5] * row[1];
+                v = v + X[4] * row[5];
+                v = v + fn1 * rhs(n, 1);
+                *du = v;
+            }
+        }
+        if (first) {
+            double2 v = bcs_far;
+            v = v + X[1] * Le(4);
+            v = v + X[2] * Le(5);
+            v = v + X[3] * Le(1);
+            X[0] = v;
+        }
+    }
+}
+
+// shared memory of one team, after the tile: reduced boundary rows, scan slots (4 scans), broadcast values
+struct TeamShared {
+    double cs[64];
+    Aff xch[4 * 4];
+    double2 bcb, bct, fend, v0n, u01, du0;
+};
+
+template <int NW, int MW>
+__global__ void __launch_bounds__(32 * NW * MW, (32 * NW * MW <= 256) ? 2 : 1)
+poisson_team_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ cv) {
+    extern __shared__ double2 wtile[];                 // [MW][TP] tiles, then [MW] TeamShared
+    const int T = D.T, n = D.ny;
+    const int TP = (T * 9) | 1;                        // odd: adjacent modes of a row land in adjacent 16-byte slots
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int mt = w / NW, wt = w - mt * NW;           // team in the CTA, warp in the team
+    const int j = wt * 32 + lane;                      // chunk
+    const int barid = 1 + mt;
+    constexpr int NT = 32 * NW * MW;
+    if (blockIdx.y == 0) {
+        // The (up to four) singular modes are marched by one thread each (OPR_ODE2_Factorize_NN_Sing: a different, rank-deficient
+        // problem) on small planes of their own.  They take as long as ~1000 dependent loads; the first CTA of the grid starts
+        // them so that they run beside the regular modes instead of behind them.
+        if (blockIdx.x == 0 && threadIdx.x < 4) {
+            const int t = threadIdx.x;
+            const int is = (t & 1) ? D.i_sing1 : D.i_sing0, ks = (t & 2) ? D.k_sing1 : D.k_sing0;
+            const bool dup = ((t & 2) && D.k_sing1 == D.k_sing0) || ((t & 1) && D.i_sing1 == D.i_sing0);
+            if (!dup && is >= 0 && is < D.nxh && ks >= 0 && ks < D.nz) {
+                PoissonDev Ds = D;
+                Ds.fund = D.sing; Ds.scr = D.sing + (size_t)5 * 32 * n; Ds.fac = nullptr; Ds.plane_sz = 32LL * n; Ds.il = 0;
+                poisson_singular_mode(Ds, cf, cv, is, ks, t);
+            }
+        }
+        return;
+    }
+    const int k = blockIdx.y - 1;
+    const int i0 = blockIdx.x * MW;
+    const size_t plane0 = (size_t)D.nxh * n * k;       // complex elements before this z plane
+    double2* cf2 = reinterpret_cast<double2*>(cf);
+    double2* cv2 = reinterpret_cast<double2*>(cv);
+    const double norm = D.norm;
+    const int i = i0 + mt;
+    const bool work = (i < D.nxh) && !mode_is_singular(D, i, k);
+    // ---- L2 prefetch: what this team reads later (upper factors of both systems, fundamental lines), and the forcing tile of
+    // the CTA that takes this CTA's place on the SM (pf_dist CTAs later), so that its first wait is an L2 hit
+    if (work) {
+        const long long m = (long long)i + (long long)D.nxh * k;
+        const char* f0 = reinterpret_cast<const char*>(D.wfac_min + (size_t)m * n);
+        const char* f1 = reinterpret_cast<const char*>(D.wfac_max + (size_t)m * n);
+        const char* f2 = reinterpret_cast<const char*>(D.wfund + (size_t)m * 5 * n);
+        const int tt = wt * 32 + lane;
+        for (int l = tt; l < n / 8; l += 32 * NW) { prefetch_l2g(f0 + (size_t)l * 128); prefetch_l2g(f1 + (size_t)l * 128); }
+        for (int l = tt; l < (5 * n) / 16; l += 32 * NW) prefetch_l2g(f2 + (size_t)l * 128);
+    }
+    if (D.pf_dist > 0) {
+        const unsigned lin = (blockIdx.y - 1) * gridDim.x + blockIdx.x + (unsigned)D.pf_dist;
+        const unsigned ky = lin / gridDim.x, bx = lin - ky * gridDim.x;
+        if (ky < gridDim.y - 1) {
+            const double2* base = cf2 + (size_t)D.nxh * n * ky + (size_t)bx * MW;
+            const int last_mw = min(MW, D.nxh - (int)bx * MW) - 1;
+            for (int row = threadIdx.x; row < n; row += NT) {
+                prefetch_l2g(base + (size_t)D.nxh * row);
+                prefetch_l2g(base + (size_t)D.nxh * row + last_mw);
+            }
+        }
+    }
+    // ---- forcing tile in (row segments of MW complex numbers), scaled
+    for (int idx = threadIdx.x; idx < n * MW; idx += NT) {
+        const int row = idx / MW, mw = idx - row * MW;
+        if (i0 + mw < D.nxh) {
+            const double2 v = __ldcs(cf2 + plane0 + (size_t)D.nxh * row + i0 + mw);
+            wtile[mw * TP + tpad(row)] = make_double2(v.x * norm, v.y * norm);
+        }
+    }
+    __syncthreads();
+    double2* tile = wtile + mt * TP;
+    TeamShared& sh = reinterpret_cast<TeamShared*>(wtile + MW * TP)[mt];
+    double2 X[TR];
+    const bool active = j < T, first = (j == 0), last = (j == T - 1);
+    const int c9 = j * 9;
+    const double2 zero = make_double2(0.0, 0.0);
+    if (work) {
+        const long long m = (long long)i + (long long)D.nxh * k;
+        const double lam = sqrt(D.lambda[m]);
+#pragma unroll
+        for (int q = 0; q < TR; q++) X[q] = active ? tile[c9 + q] : zero;
+        double2 Fm1 = (active && j > 0) ? tile[c9 - 2] : zero;               // slot of row r0 - 1: (j-1)*9 + 7
+        double2 Fp1 = (j < T - 1) ? tile[c9 + 9] : zero;
+        if (first) sh.bcb = X[0];                                             // bcs(1:2,1) = f(1:2)
+        if (last) sh.bct = X[TR - 1];                                         // bcs(1:2,2) = f(2ny-1:2ny)
+        // v^(0): v' + lam v = f, f(n) = 0, v(1) = 0   (in place)
+        team_int1<true, NW>(D.smin, D.wmin, D.wfac_min + (size_t)m * n, lam, T, j, lane, wt, barid, X, Fm1, Fp1, zero, zero, zero,
+                            sh.cs, sh.xch, nullptr);
+        // v^(0) is parked in the tile (needed again in the correction); u^(0): u' - lam u = v, u(n) = 0
+        if (active) {
+#pragma unroll
+            for (int q = 0; q < TR; q++) tile[c9 + q] = X[q];
+        }
+        if (first) sh.fend = X[0];
+        if (last) sh.v0n = X[TR - 1];
+        team_barrier<NW>(barid);
+        Fm1 = (active && j > 0) ? tile[c9 - 2] : zero;
+        Fp1 = (j < T - 1) ? tile[c9 + 9] : zero;
+        double2 du0 = zero;
+        team_int1<false, NW>(D.smax, D.wmax, D.wfac_max + (size_t)m * n, -lam, T, j, lane, wt, barid, X, Fm1, Fp1, sh.fend, zero, zero,
+                             sh.cs, sh.xch + 2 * NW, &du0);
+        if (first) sh.u01 = X[0];
+        if (last) sh.du0 = du0;
+        team_barrier<NW>(barid);
+        // constraint and boundary conditions (opr_odes.f90:350-367)
+        const long long NM = D.nmodes;
+        const double* A = D.amat;
+        const double a11 = A[0 * NM + m], a21 = A[1 * NM + m], a31 = A[2 * NM + m];
+        const double a12 = A[3 * NM + m], a22 = A[4 * NM + m], a32 = A[5 * NM + m];
+        const double a13 = A[6 * NM + m], a23 = A[7 * NM + m], a33 = A[8 * NM + m];
+        const double2 bcb = sh.bcb, bct = sh.bct, u0_1 = sh.u01, v0_n = sh.v0n;
+        du0 = sh.du0;
+        double2 v_1, u_n, fn;
+        v_1 = make_double2((bcb.x - lam * u0_1.x) / a11, (bcb.y - lam * u0_1.y) / a11);
+        u_n = make_double2((bct.x - v0_n.x - a21 * v_1.x) / a22, (bct.y - v0_n.y - a21 * v_1.y) / a22);
+        fn = make_double2((bct.x - du0.x - a31 * v_1.x - a32 * u_n.x) / a33, (bct.y - du0.y - a31 * v_1.y - a32 * u_n.y) / a33);
+        u_n = make_double2(u_n.x - a23 * fn.x, u_n.y - a23 * fn.y);
+        v_1 = make_double2(v_1.x - a12 * u_n.x - a13 * fn.x, v_1.y - a12 * u_n.y - a13 * fn.y);
+        const double* fu = D.wfund + (size_t)m * 5 * n;
+        if (active) {
+            // rows of this chunk: v^(0) comes back from the tile row by row and dp^/dy takes its place; p^ stays in registers
+#pragma unroll
+            for (int q = 0; q < TR; q++) {
+                const int o = q * T + j;
+                const double f0 = __ldcs(fu + o), f1 = __ldcs(fu + n + o), f2 = __ldcs(fu + 2 * n + o), f3 = __ldcs(fu + 3 * n + o),
+                             f4 = __ldcs(fu + 4 * n + o);
+                const int r = j * TR + q + 1;
+                const double2 v0 = tile[c9 + q];
+                double2 uu, vv;
+                if (r == n) {
+                    uu = u_n;
+                    vv = make_double2(v0.x + fn.x * f0 + v_1.x * f1 + lam * uu.x, v0.y + fn.y * f0 + v_1.y * f1 + lam * uu.y);
+                } else {
+                    uu = make_double2(X[q].x + fn.x * f2 + v_1.x * f3 + u_n.x * f4, X[q].y + fn.y * f2 + v_1.y * f3 + u_n.y * f4);
+                    if (r == 1) vv = make_double2(v_1.x + lam * uu.x, v_1.y + lam * uu.y);
+                    else vv = make_double2(v0.x + fn.x * f0 + v_1.x * f1 + lam * uu.x, v0.y + fn.y * f0 + v_1.y * f1 + lam * uu.y);
+                }
+                X[q] = uu;
+                tile[c9 + q] = vv;
+            }
+        }
+    }
+    // ---- results out through the tile: dp^/dy into the second array, then p^ over the forcing
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n * MW; idx += NT) {
+        const int row = idx / MW, mw = idx - row * MW;
+        if (i0 + mw < D.nxh && !mode_is_singular(D, i0 + mw, k))
+            __stcs(cv2 + plane0 + (size_t)D.nxh * row + i0 + mw, wtile[mw * TP + tpad(row)]);
+    }
+    __syncthreads();
+    if (work && active) {
+#pragma unroll
+        for (int q = 0; q < TR; q++) tile[c9 + q] = X[q];
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n * MW; idx += NT) {
+        const int row = idx / MW, mw = idx - row * MW;
+        if (i0 + mw < D.nxh && !mode_is_singular(D, i0 + mw, k))
+            __stcs(cf2 + plane0 + (size_t)D.nxh * row + i0 + mw, wtile[mw * TP + tpad(row)]);
+    }
+}
+
+// full planes (blocked by 32 modes, see plane()) -> lane order of the warp kernel, one plane per launch.  One CTA per group
+// of 32 modes: coalesced reads along the modes, transposed through shared memory, coalesced writes along the rows of a mode.
+// dst element of (mode m, 0-based row r): dst[(m * n + (r % 8) * T + r / 8) * dstride + doff]
+__global__ void poisson_relayout_kernel(PoissonDev D, int which, int kplane, bool inner_only, double* __restrict__ dst,
+                                        long long mode_stride, int dstride, int doff) {
+    __shared__ double t[32][33];
+    const int n = D.ny, T = D.T;
+    const long long m0 = (long long)blockIdx.x * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;       // 32 x 8
+    for (int r0 = 0; r0 < n; r0 += 32) {
+        for (int rr = ty; rr < 32; rr += 8) {
+            const int r = r0 + rr + 1;
+            const long long m = m0 + tx;
+            bool ok = (m < D.nmodes) && (r <= n);
+            if (inner_only) ok = ok && r > 1 && r < n;
+            t[rr][tx] = ok ? plane(D, which, kplane, m).get(r) : 0.0;
+        }
+        __syncthreads();
+        for (int mm = ty; mm < 32; mm += 8) {
+            const long long m = m0 + mm;
+            const int rb = r0 + tx;                 // 0-based row
+            if (m < D.nmodes && rb < n)
+                dst[((size_t)m * mode_stride + (size_t)((rb & 7) * T + (rb >> 3))) * dstride + doff] = t[tx][mm];
+        }
+        __syncthreads();
     }
 }
 
@@ -655,11 +1160,55 @@ int make_side(const HostDer& der1, int bc, Int1Dev& S, std::vector<void*>& alloc
     return (S.L0 && S.L1 && S.rhs) ? 0 : TLAB_ERR_ALLOC;
 }
 
+// lane-order copies of the shared tables of one side (see WarpSide): entry of row r = 8 j + q + 1 at [q * T + j]
+int make_warp_side(const HostDer& der1, int bc, int T, WarpSide& Ws, std::vector<void*>& allocs) {
+    HostInt1 H;
+    int rc = int1_create_base(der1, bc, H);
+    if (rc) return rc;
+    const int n = H.n;
+    std::vector<double> t[4];
+    for (auto& v : t) v.assign((size_t)2 * n, 0.0);
+    for (int r = 1; r <= n; r++) {
+        const size_t o = (size_t)(((r - 1) & 7) * T + ((r - 1) >> 3)) * 2;
+        t[0][o] = H.rhs(r, 1); t[0][o + 1] = H.rhs(r, 2);
+        t[1][o] = H.L0(r, 1); t[1][o + 1] = H.L1(r, 1);
+        t[2][o] = H.L0(r, 2); t[2][o + 1] = H.L1(r, 2);
+        t[3][o] = H.L0(r, 5); t[3][o + 1] = H.L1(r, 5);
+    }
+    const double* d[4];
+    for (int k = 0; k < 4; k++) { d[k] = up(allocs, t[k].data(), t[k].size()); if (!d[k]) return TLAB_ERR_ALLOC; }
+    Ws.rh = reinterpret_cast<const double2*>(d[0]);
+    Ws.ab0 = reinterpret_cast<const double2*>(d[1]);
+    Ws.ab1 = reinterpret_cast<const double2*>(d[2]);
+    Ws.e = reinterpret_cast<const double2*>(d[3]);
+    return 0;
+}
+
 }  // namespace
 
 // One thread per mode, or (tuning key poisson_split: 1 always, 0 never, -1 when this GPU holds fewer than 200 000 modes)
 // one thread per component; the latter needs the stored factor lines.
 static void launch_modes(const PoissonDev& D, double* cf, double* cv, cudaStream_t st) {
+    if (D.T > 0) {
+        // team per mode: MW adjacent kx per CTA (row segments of MW * 16 bytes), one z plane per blockIdx.y
+        const int NW = D.T <= 32 ? 1 : (D.T <= 64 ? 2 : 4);
+        int MW = ctx().tune_poisson_warp;
+        if (MW != 2 && MW != 4 && MW != 8) MW = 4;
+        if (NW * MW > 16) MW = 16 / NW;
+        const int TP = (D.T * 9) | 1;
+        const size_t smem = (size_t)MW * TP * sizeof(double2) + (size_t)MW * sizeof(TeamShared);
+        const dim3 grid((unsigned)((D.nxh + MW - 1) / MW), (unsigned)D.nz + 1);      // row 0: singular modes
+        PoissonDev Dl = D;
+        Dl.pf_dist = ctx().tune_poisson_pf < 0 ? 2 * 148 : ctx().tune_poisson_pf;
+        auto go = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<grid, 32 * NW * MW, smem, st>>>(Dl, cf, cv);
+        };
+        if (NW == 1) { if (MW == 8) go(poisson_team_kernel<1, 8>); else if (MW == 4) go(poisson_team_kernel<1, 4>); else go(poisson_team_kernel<1, 2>); }
+        else if (NW == 2) { if (MW == 8) go(poisson_team_kernel<2, 8>); else if (MW == 4) go(poisson_team_kernel<2, 4>); else go(poisson_team_kernel<2, 2>); }
+        else { if (MW == 4) go(poisson_team_kernel<4, 4>); else go(poisson_team_kernel<4, 2>); }
+        return;
+    }
     const int threads = 128;
     int split = ctx().tune_poisson_split;
     // measured (profiles/ncu_full_poisson_r01.json): 66 560 modes (C3 on 8 GPUs) 5.6 -> 5.1 ms with one thread per component and
@@ -810,6 +1359,43 @@ int Poisson::init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz, int nz_loca
     const unsigned blocks = (unsigned)((D.nmodes + threads - 1) / threads);
     poisson_fundamental_kernel<<<blocks, threads, 0, st>>>(D);
     if (int rc = cuda_check(cudaStreamSynchronize(st), "poisson fundamental solutions")) return rc;
+    D.T = 0;
+    if (ctx().tune_poisson_warp && D.fac && ny % 8 == 0 && ny / 8 <= 128) {
+        // warp-per-mode kernel: keep the upper factors and the fundamental lines in lane order, drop the full planes
+        auto drop = [&](double* b) {
+            cudaFree(b);
+            allocs.erase(std::remove(allocs.begin(), allocs.end(), (void*)b), allocs.end());
+        };
+        drop(scr); D.scr = nullptr;
+        D.T = ny / 8;
+        const size_t per_mode = (size_t)ny;
+        double *wmin = nullptr, *wmax = nullptr, *wfund = nullptr, *sing = nullptr;
+        if (cudaMalloc(&wmin, 2 * per_mode * D.nmodes * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&wmax, 2 * per_mode * D.nmodes * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&wfund, 5 * per_mode * D.nmodes * sizeof(double)) != cudaSuccess ||
+            cudaMalloc(&sing, (size_t)11 * 32 * ny * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            for (double* b : {wmin, wmax, wfund, sing}) if (b) cudaFree(b);
+            return fail(TLAB_ERR_ALLOC, "OPR_Elliptic_Initialize: out of device memory (lane-order planes)");
+        }
+        for (double* b : {wmin, wmax, wfund, sing}) allocs.push_back(b);
+        cudaMemsetAsync(sing, 0, (size_t)11 * 32 * ny * sizeof(double), st);
+        const unsigned groups = (unsigned)((D.nmodes + 31) / 32);
+        poisson_relayout_kernel<<<groups, 256, 0, st>>>(D, P_FAC, 2, true, wmin, (long long)ny, 2, 0);
+        poisson_relayout_kernel<<<groups, 256, 0, st>>>(D, P_FAC, 3, true, wmin, (long long)ny, 2, 1);
+        poisson_relayout_kernel<<<groups, 256, 0, st>>>(D, P_FAC, 6, true, wmax, (long long)ny, 2, 0);
+        poisson_relayout_kernel<<<groups, 256, 0, st>>>(D, P_FAC, 7, true, wmax, (long long)ny, 2, 1);
+        for (int f = 0; f < 5; f++)
+            poisson_relayout_kernel<<<groups, 256, 0, st>>>(D, P_FUND, f, false, wfund + (size_t)f * ny, 5LL * ny, 1, 0);
+        if (int rc = cuda_check(cudaStreamSynchronize(st), "poisson lane-order planes")) return rc;
+        drop(fund); drop(D.fac);
+        D.fund = nullptr; D.fac = nullptr;
+        D.wfac_min = reinterpret_cast<const double2*>(wmin);
+        D.wfac_max = reinterpret_cast<const double2*>(wmax);
+        D.wfund = wfund; D.sing = sing;
+        if (int rc = make_warp_side(gy->p.h.der1, BCS_MIN, D.T, D.wmin, allocs)) return fail(rc, "lane-order tables (BCS_MIN)");
+        if (int rc = make_warp_side(gy->p.h.der1, BCS_MAX, D.T, D.wmax, allocs)) return fail(rc, "lane-order tables (BCS_MAX)");
+    }
     ready = true;
     return 0;
 }

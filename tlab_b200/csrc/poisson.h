@@ -15,6 +15,15 @@ struct Int1Dev {
     int n = 0, bc = 0;
 };
 
+// Tables of one side in "lane order" for the team-per-mode kernel: the entry of row r = 8 j + q + 1 (chunk j, q-th row of
+// the chunk) sits at [q * T + j], so that the lanes of a team (lane = chunk) read consecutive addresses.
+struct WarpSide {
+    const double2* rh = nullptr;     // {rhs(r, 1), rhs(r, 2)}: interior rows of the tridiagonal right-hand side operator
+    const double2* ab0 = nullptr;    // second sub-diagonal {L0(r, 1), L1(r, 1)}
+    const double2* ab1 = nullptr;    // first sub-diagonal {L0(r, 2), L1(r, 2)}
+    const double2* e = nullptr;      // second super-diagonal {L0(r, 5), L1(r, 5)}
+};
+
 struct PoissonDev {
     int nxh = 0, ny = 0, nz = 0;
     long long nmodes = 0;
@@ -27,6 +36,15 @@ struct PoissonDev {
     double* fund = nullptr;           // 5 planes [ny][nmodes]: v1, e-, u1, s+, e+
     double* scr = nullptr;            // 6 planes [ny][nmodes] of per-mode scratch
     double* amat = nullptr;           // 9 x [nmodes]: LU-decomposed 3x3 boundary system
+    // team-per-mode kernel (ny a multiple of 8, at most 1024): per mode and side the upper LU factors (1/c, -d) of every
+    // row as double2 in lane order [mode][q * T + j], the five fundamental lines as [mode][line][q * T + j]
+    int T = 0;                        // chunks of 8 rows per line (0: kernel not available for this geometry)
+    WarpSide wmin, wmax;
+    const double2* wfac_min = nullptr;
+    const double2* wfac_max = nullptr;
+    const double* wfund = nullptr;
+    int pf_dist = 0;                  // team kernel: L2 prefetch of the forcing tile of the CTA this many places later
+    double* sing = nullptr;           // small planes (fund, scr layout, 32 slots) for the singular modes
     double* fac = nullptr;            // optional, 8 planes [ny][nmodes]: LU factors (la, lb, 1/c, -d) of the BCS_MIN(+lam) and
                                       // BCS_MAX(-lam) systems of every regular mode, computed once (they depend on lambda only)
 };
