@@ -43,7 +43,9 @@ def load_traffic():
     """Measured DRAM bytes per point and launch of the line-kernel classes in the RHS of this bench (they include the
     read-modify-write of hq that the launches fuse): profiles/ncu_dram_bench_r01.json, written by tools/ncu_dram_summary.py
     from an `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` pass over one substep."""
-    path = os.path.join(ROOT, "profiles", "ncu_dram_bench_r01.json")
+    path = os.path.join(ROOT, "profiles", "ncu_dram_bench_r02.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "ncu_dram_bench_r01.json")
     try:
         return {k: float(v) for k, v in json.load(open(path))["bytes_per_point_per_launch"].items()}
     except Exception:
@@ -213,6 +215,202 @@ def synth_field(torch, dev, shape, x, y, z, seed, amp):
     return out
 
 
+def make_sim(GD, opr, mpi, nx, ny, nz, world, rank):
+    """Plans + device state of the bench configuration (CBL-like: no-slip bottom, free-slip top, linear buoyancy, 1 scalar)."""
+    kmax, koff = nz, 0
+    if world > 1:
+        kmax, koff = mpi.slab(nz, rank, world)
+    x, z, y = grid_periodic(nx), grid_periodic(nz), grid_tanh(ny)
+    g = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, False, name="y"), opr.FdmPlan(z, True, True, name="z")]
+    D, Nn = GD.DNS_BCS_DIRICHLET, GD.DNS_BCS_NEUMANN
+    sim = GD.Dns(g, visc=PHYS["visc"], schmidt=PHYS["schmidt"], rkm_mode=GD.RKM_EXP4, buoyancy_type="linear",
+                 buoyancy_params=(1.0, 0.0), buoyancy_vector=(0.0, 1.0, 0.0),
+                 bcs_flow_jmin=(D, D, D), bcs_flow_jmax=(Nn, D, Nn), bcs_scal_jmin=(D,), bcs_scal_jmax=(Nn,),
+                 kmax=(kmax if world > 1 else None))
+    return sim, g, (x, y, z), kmax, koff
+
+
+def fill_fields(torch, tl, L, sim, dev, grids, kmax, koff):
+    import ctypes
+    x, y, z = grids
+    nx, ny = len(x), len(y)
+    N = nx * ny * kmax
+    for i, nm in enumerate(["q1", "q2", "q3", "s1"]):
+        f = synth_field(torch, dev, (kmax, ny, nx), x, y, z[koff:koff + kmax], 20261017 + i, 0.05)
+        if nm == "s1":
+            f = 0.5 + f
+        torch.cuda.synchronize()
+        tl.check(L.tlab_gpu_copy(ctypes.c_void_p(sim.device_ptr(nm)), ctypes.c_void_p(f.data_ptr()), N * 8))
+        del f
+    torch.cuda.empty_cache()
+
+
+def parity_block(torch, dist, tl, L, opr, GD, mpi, dev, world, rank):
+    """Correctness record of the multi-GPU paths, taken before anything is timed: one RK step of a small split-eligible grid
+    (32 x 32 x 96 P, slabs of 6 chunks) on the P ranks against the single-domain oracle on rank 0 -- once with the default path
+    (split-z operators over peer memory + kx-split Poisson stage) and once with splitz = 0 (K-transposes for every z operator).
+    The oracle is the checker here, never the thing measured."""
+    import ctypes
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from common import smooth_field, rel_l2
+    nx, ny, nz = 32, 32, 96 * world
+    out = {"grid": [nx, ny, nz], "paths": {}}
+    ref = None
+    for label, tune in (("default", None), ("splitz=0", ("splitz", 0))):
+        if tune:
+            tl.check(L.tlab_gpu_set_tuning(tune[0].encode(), tune[1]))
+        cnt0 = {}
+        for key in ("p2p_exchanges", "nccl_exchanges", "splitz_ops"):
+            c = ctypes.c_longlong()
+            tl.check(L.tlab_gpu_get_counter(key.encode(), ctypes.byref(c)))
+            cnt0[key] = c.value
+        sim, g, (x, y, z), kmax, koff = make_sim(GD, opr, mpi, nx, ny, nz, world, rank)
+        wall = np.sin(0.5 * np.pi * y / y[-1])[None, :, None]
+        full = [0.5 * smooth_field((nz, ny, nx), (x, y, z), seed=31 + i) * wall for i in range(3)]
+        full.append(0.5 + 0.1 * smooth_field((nz, ny, nx), (x, y, z), seed=40) * wall)
+        for nm, f in zip(["q1", "q2", "q3", "s1"], full):
+            sim.set(nm, f[koff:koff + kmax])
+        sim.runge_kutta(PHYS["dtime"])
+        mine = [sim.get(nm) for nm in ["q1", "q2", "q3", "s1"]]
+        gathered = []
+        for f in mine:
+            t = torch.from_numpy(f).to(dev)
+            parts = [torch.empty_like(t) for _ in range(world)]
+            dist.all_gather(parts, t)
+            gathered.append(torch.cat(parts, dim=0).cpu().numpy())
+        rec = {}
+        for key in cnt0:
+            c = ctypes.c_longlong()
+            tl.check(L.tlab_gpu_get_counter(key.encode(), ctypes.byref(c)))
+            rec[key] = c.value - cnt0[key]
+        if rank == 0:
+            if ref is None:
+                from oracle import fdm, dns as OD
+                go = [fdm.Plan(x, True, True, name="x"), fdm.Plan(y, False, False, name="y"), fdm.Plan(z, True, True, name="z")]
+                D, Nn = OD.DNS_BCS_DIRICHLET, OD.DNS_BCS_NEUMANN
+                o = OD.Dns(go, visc=PHYS["visc"], schmidt=PHYS["schmidt"], buoyancy_type="linear", buoyancy_params=(1.0, 0.0),
+                           buoyancy_vector=(0.0, 1.0, 0.0), bcs_flow_jmin=(D, D, D), bcs_flow_jmax=(Nn, D, Nn),
+                           bcs_scal_jmin=(D,), bcs_scal_jmax=(Nn,))
+                for i in range(3):
+                    o.q[i][...] = full[i]
+                o.s[0][...] = full[3]
+                o.runge_kutta(PHYS["dtime"])
+                ref = o.q + o.s
+            rec["max_rel_l2"] = float(max(rel_l2(a, b) for a, b in zip(gathered, ref)))
+        out["paths"][label] = rec
+        sim.close()
+        if tune:
+            tl.check(L.tlab_gpu_set_tuning(tune[0].encode(), 1))
+    if rank == 0:
+        out["max_rel_l2"] = max(r["max_rel_l2"] for r in out["paths"].values())
+        out["tolerance"] = 1e-11
+        out["ok"] = bool(out["max_rel_l2"] <= 1e-11)
+    return out
+
+
+def time_substeps(torch, dist, tl, L, sim, stream, dev, world, steps, warmup, dtime=None, nstage=5):
+    """W untimed + K timed substeps, CUDA events on the library stream, max over ranks.  Returns ms per substep."""
+    dtime = PHYS["dtime"] if dtime is None else dtime
+    tl.check(L.tlab_gpu_set_async(1))
+    for i in range(warmup):
+        sim.runge_kutta_stage(dtime, i % nstage)
+    tl.check(L.tlab_gpu_synchronize())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0.record(stream)
+    for i in range(warmup, warmup + steps):
+        sim.runge_kutta_stage(dtime, i % nstage)
+    e1.record(stream)
+    tl.check(L.tlab_gpu_synchronize())
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        dist.barrier()
+        tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms = float(tmax.item())
+    tl.check(L.tlab_gpu_set_async(0))
+    return ms / steps
+
+
+def extra_records(torch, tl, L, opr, dev, stream, peak):
+    """BASELINE.json configs[1] and configs[4], driver-run: OPR_Partial X/Y/Z (P1, P2, P2_P1) on 512^3 with the non-uniform y
+    of the bench, and OPR_Poisson alone on 256^3 ... 1024^3 (120 B/pt stage-streaming model, the y stage against 24 B/pt)."""
+    import ctypes
+    out = {"opr_partial_512": [], "poisson_sweep": []}
+
+    def timeit(fn, iters=10, warm=3):
+        tl.check(L.tlab_gpu_set_async(1))
+        for _ in range(warm):
+            fn()
+        tl.check(L.tlab_gpu_synchronize())
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            fn()
+        e1.record(stream)
+        tl.check(L.tlab_gpu_synchronize())
+        torch.cuda.synchronize()
+        tl.check(L.tlab_gpu_set_async(0))
+        return e0.elapsed_time(e1) / iters
+
+    nx = ny = nz = 512
+    N = nx * ny * nz
+    x, z, y = grid_periodic(nx), grid_periodic(nz), grid_tanh(ny)
+    g = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, False, name="y"), opr.FdmPlan(z, True, True, name="z")]
+    u = torch.randn(N, dtype=torch.float64, device=dev)
+    r1, r2 = torch.empty_like(u), torch.empty_like(u)
+    bcs = [[0, 0], [0, 0]]
+    P = [opr.OPR_Partial_X, opr.OPR_Partial_Y, opr.OPR_Partial_Z]
+    for d, nm in enumerate("XYZ"):
+        for tname, typ, nb in (("P1", opr.OPR_P1, 16), ("P2", opr.OPR_P2, 16), ("P2_P1", opr.OPR_P2_P1, 24)):
+            ms = timeit(lambda: P[d](typ, nx, ny, nz, bcs, g[d], u, r1, r2 if typ == opr.OPR_P2_P1 else None))
+            gbs = nb * N / (ms * 1e-3) / 1e9
+            out["opr_partial_512"].append({"op": "OPR_Partial_%s %s" % (nm, tname), "ms": ms, "GBs": gbs,
+                                           "frac_measured_peak": gbs / peak, "frac_8TBs": gbs / 8000.0})
+    del u, r1, r2, g
+    torch.cuda.empty_cache()
+    for shape in ((256, 256, 256), (512, 512, 512), (1024, 512, 1024), (1024, 1024, 1024)):
+        nx, ny, nz = shape
+        N = nx * ny * nz
+        try:
+            x, z, y = grid_periodic(nx), grid_periodic(nz), grid_tanh(ny)
+            g = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, False, name="y"), opr.FdmPlan(z, True, True, name="z")]
+            opr.OPR_Elliptic_Initialize(g)
+            p = torch.randn(N, dtype=torch.float64, device=dev)
+            t1 = torch.zeros((nx + 2) * ny * nz, dtype=torch.float64, device=dev)
+            t2 = torch.zeros_like(t1)
+            dp = torch.empty_like(p)
+            hb = torch.zeros(nx * nz, dtype=torch.float64, device=dev)
+            ht = torch.zeros_like(hb)
+            tl.check(L.tlab_gpu_profile(1))
+            ms = timeit(lambda: opr.OPR_Poisson(nx, ny, nz, 3, p, t1, t2, hb, ht, dp), iters=5, warm=2)
+            mc, cc = (ctypes.c_double * 16)(), (ctypes.c_int * 16)()
+            tl.check(L.tlab_gpu_profile_report(mc, cc, 16))
+            tl.check(L.tlab_gpu_profile(0))
+            yms = mc[8] / cc[8] if cc[8] else None
+            gbs = 120.0 * N / (ms * 1e-3) / 1e9
+            out["poisson_sweep"].append({"grid": list(shape), "ms": ms, "GBs_120B_model": gbs, "frac_measured_peak": gbs / peak,
+                                         "frac_8TBs": gbs / 8000.0, "GBs_24B_floor": 24.0 * N / (ms * 1e-3) / 1e9,
+                                         "y_stage_ms": yms,
+                                         "y_stage_frac_measured_peak": (24.0 * N / (yms * 1e-3) / 1e9 / peak) if yms else None})
+            del p, t1, t2, dp, hb, ht, g
+        except Exception as ex:      # e.g. out of memory on a smaller part
+            out["poisson_sweep"].append({"grid": list(shape), "error": str(ex)[:200]})
+        torch.cuda.empty_cache()
+    # release the process-wide solver of the stand-alone API (re-initialise on a tiny grid)
+    try:
+        x, z, y = grid_periodic(16), grid_periodic(16), grid_tanh(16)
+        opr.OPR_Elliptic_Initialize([opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, False, name="y"),
+                                     opr.FdmPlan(z, True, True, name="z")])
+    except Exception:
+        pass
+    return out
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
@@ -238,30 +436,15 @@ def run_gpu(args):
     if args.nx:
         nx, ny, nz = args.nx, args.ny, args.nz
     from tlab_b200 import mpi
-    kmax, koff = nz, 0
+    parity = None
     if world > 1:
         mpi.init_from_torch_distributed()
-        kmax, koff = mpi.slab(nz, rank, world)
-    x, z, y = grid_periodic(nx), grid_periodic(nz), grid_tanh(ny)
-    g = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, False, name="y"), opr.FdmPlan(z, True, True, name="z")]
-    D, Nn = GD.DNS_BCS_DIRICHLET, GD.DNS_BCS_NEUMANN
-    sim = GD.Dns(g, visc=PHYS["visc"], schmidt=PHYS["schmidt"], rkm_mode=GD.RKM_EXP4, buoyancy_type="linear",
-                 buoyancy_params=(1.0, 0.0), buoyancy_vector=(0.0, 1.0, 0.0),
-                 bcs_flow_jmin=(D, D, D), bcs_flow_jmax=(Nn, D, Nn), bcs_scal_jmin=(D,), bcs_scal_jmax=(Nn,),
-                 kmax=(kmax if world > 1 else None))
+        if not args.no_parity:
+            parity = parity_block(torch, dist, tl, L, opr, GD, mpi, dev, world, rank)
+    sim, g, (x, y, z), kmax, koff = make_sim(GD, opr, mpi, nx, ny, nz, world, rank)
     Nglobal = nx * ny * nz
     N = nx * ny * kmax                       # points of this rank's slab
-    shape = (kmax, ny, nx)
-    z_loc = z[koff:koff + kmax]
-    names = ["q1", "q2", "q3", "s1"]
-    for i, nm in enumerate(names):
-        f = synth_field(torch, dev, shape, x, y, z_loc, 20261017 + i, 0.05)
-        if nm == "s1":
-            f = 0.5 + f
-        torch.cuda.synchronize()
-        tl.check(L.tlab_gpu_copy(ctypes.c_void_p(sim.device_ptr(nm)), ctypes.c_void_p(f.data_ptr()), N * 8))
-        del f
-    torch.cuda.empty_cache()
+    fill_fields(torch, tl, L, sim, dev, (x, y, z), kmax, koff)
 
     sp = ctypes.c_void_p()
     tl.check(L.tlab_gpu_stream(ctypes.byref(sp)))
@@ -309,33 +492,49 @@ def run_gpu(args):
     ms_per_step = ms_total / args.steps
     value = Nglobal / (ms_per_step * 1e-3) / 1e9
 
-    # roofline of the dominant kernel class (by device time inside the timed region)
+    # roofline: every kernel class against the algorithmic bytes of SURVEY.md 8(d) (compulsory traffic at the reference's
+    # operator surface).  Per launch: OPR_Burgers SELF 16 / U_IN 24 B/pt -> mean of the 1 + 3 launches of a direction 22;
+    # OPR_Partial P1 16; the y stage of OPR_Poisson 24 (1r + 2w); the five FFT stages together 96 (6r + 6w).  The line-kernel
+    # launches of the RHS also perform the reference's separate accumulation / pressure-forcing sweeps (`hq = hq + tmp`,
+    # `tmp = hq + q/dte`), which fused cost one more operand: `fused_bytes` (30 / 28 / 24 B/pt) is what the launch must move.
     peak, peak_kind = load_peaks()
-    # Algorithmic bytes per point of one launch = compulsory traffic at the reference's operator surface:
-    # OPR_Burgers SELF 16 / U_IN 24 B/pt, mean over the 1 + 3 launches of a direction = 22; every launch of the RHS also
-    # performs the reference's separate `hq = hq + tmp` sweep (24 B/pt there), which fused costs one more read of hq: +8.
-    # OPR_Partial P1 in the RHS: 16 B/pt + 8 for the second input (hq + q/dte) and/or + 8 for the accumulation target:
-    # y: 24 (one launch); x and z: (32 + 24)/2 = 28 (divergence term and pressure gradient).
-    line_classes = {"burgers_x": 30.0, "burgers_y": 30.0, "burgers_z": 30.0,
-                    "partial_x": 28.0, "partial_y": 24.0, "partial_z": 28.0}
-    surface_only = {"burgers_x": 22.0, "burgers_y": 22.0, "burgers_z": 22.0, "partial_x": 16.0, "partial_y": 16.0, "partial_z": 16.0}
-    dom = max((k for k in breakdown if k in line_classes), key=lambda k: breakdown[k]["ms_per_step"])
-    avg_ms = ms_cls[cls_names.index(dom)] / cnt_cls[cls_names.index(dom)]
-    achieved = line_classes[dom] * N / (avg_ms * 1e-3) / 1e9
+    contract = {"burgers_x": 22.0, "burgers_y": 22.0, "burgers_z": 22.0, "partial_x": 16.0, "partial_y": 16.0, "partial_z": 16.0,
+                "poisson_y": 24.0}
+    fused = {"burgers_x": 30.0, "burgers_y": 30.0, "burgers_z": 30.0, "partial_x": 28.0, "partial_y": 24.0, "partial_z": 28.0,
+             "poisson_y": 24.0}
     traffic = load_traffic()
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": achieved / peak,
+    per_class = {}
+    for k in breakdown:
+        i = cls_names.index(k)
+        if k in contract:
+            avg = ms_cls[i] / cnt_cls[i]
+            per_class[k] = {"avg_launch_ms": avg, "launches_per_step": cnt_cls[i] / args.steps,
+                            "achieved": contract[k] * N / (avg * 1e-3) / 1e9, "frac": contract[k] * N / (avg * 1e-3) / 1e9 / peak,
+                            "achieved_fused_bytes": fused[k] * N / (avg * 1e-3) / 1e9,
+                            "frac_fused_bytes": fused[k] * N / (avg * 1e-3) / 1e9 / peak}
+        elif k == "fft":
+            t = ms_cls[i] / args.steps          # all FFT stages of a substep together (cuFFT's own kernels)
+            per_class[k] = {"ms_per_step": t, "achieved": 96.0 * N / (t * 1e-3) / 1e9, "frac": 96.0 * N / (t * 1e-3) / 1e9 / peak,
+                            "note": "cuFFT (library), 12 sweeps of 8 B/pt"}
+    own = [k for k in per_class if k != "fft"]
+    dom = max(own, key=lambda k: breakdown[k]["ms_per_step"])            # largest share of the substep
+    worst = min(own, key=lambda k: per_class[k]["frac"])                  # furthest below its roofline
+    d = per_class[dom]
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": d["achieved"], "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": d["frac"], "frac_of_8TBs": d["achieved"] / 8000.0,
                 "traffic": (traffic[dom] * N if dom in traffic else None),
-                "algorithmic_bytes_per_launch": line_classes[dom] * N, "avg_launch_ms": avg_ms,
-                "algorithmic_bytes_note": "operator surface (%g B/pt) + the extra operand(s) of the reference's separate "
-                                          "accumulation / pressure-forcing sweeps that the launch fuses" % surface_only[dom],
-                "achieved_operator_surface_only": surface_only[dom] * N / (avg_ms * 1e-3) / 1e9,
-                "per_class": {k: {"achieved": line_classes[k] * N / (ms_cls[cls_names.index(k)] / cnt_cls[cls_names.index(k)] * 1e-3) / 1e9,
-                                  "frac": line_classes[k] * N / (ms_cls[cls_names.index(k)] / cnt_cls[cls_names.index(k)] * 1e-3) / 1e9 / peak}
-                              for k in breakdown if k in line_classes},
+                "traffic_source": "profiles/ncu_dram_bench_r02.json (ncu dram__bytes_read+write of this command, per launch); "
+                                  "not measurable inside an unprofiled run",
+                "algorithmic_bytes_per_launch": contract[dom] * N, "avg_launch_ms": d["avg_launch_ms"],
+                "algorithmic_bytes_note": "SURVEY 8(d) operator surface, %g B/pt; the launch also fuses the reference's separate "
+                                          "accumulation sweep (%g B/pt in total): achieved_fused_bytes" % (contract[dom], fused[dom]),
+                "achieved_fused_bytes": d["achieved_fused_bytes"], "frac_fused_bytes": d["frac_fused_bytes"],
+                "worst_kernel": worst, "worst_frac": per_class[worst]["frac"],
+                "per_class": per_class,
                 "substep": {"algorithmic_bytes_per_gpu": ALG_BYTES_PER_PT_SUBSTEP * N,
                             "achieved_per_gpu": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9,
-                            "frac": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9 / peak}}
+                            "frac": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9 / peak,
+                            "frac_of_8TBs": ALG_BYTES_PER_PT_SUBSTEP * N / (ms_per_step * 1e-3) / 1e9 / 8000.0}}
 
     # end to end: one full RK step (5 substeps) from and to pinned host buffers through the C ABI
     tl.check(L.tlab_gpu_set_async(0))
@@ -378,6 +577,34 @@ def run_gpu(args):
     z_path = "whole lines on one GPU" if world == 1 else (
         "on the slabs: halo planes + chunk ends exchanged with the neighbours over peer memory (splitz)" if zc.value > 0
         else "K-transposes to z pencils (all-to-all)")
+    sim.close()
+    del sim
+    torch.cuda.empty_cache()
+
+    # BASELINE configs[3]: 2048 x 1024 x 2048 on 8 GPUs (2^29 points per GPU), timed in the same run
+    c4 = None
+    if world == 8 and args.workload == "c3" and not args.no_c4:
+        try:
+            cx, cy, cz = WORKLOADS["c4"]
+            sim4, g4, grids4, kmax4, koff4 = make_sim(GD, opr, mpi, cx, cy, cz, world, rank)
+            fill_fields(torch, tl, L, sim4, dev, grids4, kmax4, koff4)
+            k4 = min(args.steps, 5)
+            ms4 = time_substeps(torch, dist, tl, L, sim4, stream, dev, world, k4, 3)
+            c4 = {"workload": "2048x1024x2048 (BASELINE configs[3]), z-slabs x8", "ms_per_step": ms4, "steps": k4, "warmup": 3,
+                  "value": cx * cy * cz / (ms4 * 1e-3) / 1e9, "unit": "Gpts/s", "points_per_gpu": cx * cy * kmax4,
+                  "roofline_substep_frac": ALG_BYTES_PER_PT_SUBSTEP * cx * cy * kmax4 / (ms4 * 1e-3) / 1e9 / peak,
+                  "note": "weak-scaled against C3 on one GPU (same 2^29 points per GPU): efficiency = value / (8 x the N=1 value of "
+                          "this bench); the driver computes it from its own N=1 line"}
+            sim4.close()
+            del sim4
+            torch.cuda.empty_cache()
+        except Exception as ex:
+            c4 = {"error": str(ex)[:300]}
+
+    extra = None
+    if world == 1 and args.workload == "c3" and not args.no_extra:
+        extra = extra_records(torch, tl, L, opr, dev, stream, peak)
+
     out = {"metric": "rk_substep_throughput", "value": value, "unit": "Gpts/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -388,9 +615,14 @@ def run_gpu(args):
                       "z_operators": z_path},
            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
            "breakdown_ms": breakdown}
+    if parity is not None:
+        out["parity"] = parity
+    if c4 is not None:
+        out["c4"] = c4
+    if extra is not None:
+        out["extra"] = extra
     if rank == 0:
         print(json.dumps(out))
-    sim.close()
     if world > 1:
         mpi.finalize()
         dist.destroy_process_group()
@@ -407,6 +639,9 @@ def main():
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--nz", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the oracle parity record taken before the timed region")
+    ap.add_argument("--no-c4", action="store_true", help="N = 8: skip the additional 2048x1024x2048 timing")
+    ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the OPR_Partial 512^3 and OPR_Poisson sweep records")
     ap.add_argument("--tune", default="", help="library tuning knobs, e.g. fuse=0,pf_next=1 (tlab_gpu_set_tuning)")
     args = ap.parse_args()
     if args.warmup < 3:
