@@ -91,6 +91,7 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
         auto al = [](const void* q) { return (reinterpret_cast<size_t>(q) & 15) == 0; };
         fast = al(a.u) && al(a.u2) && al(a.vel) && al(a.out1) && al(a.out2);
     }
+    if (fast && p.need_1der && !p.cjac2) fast = false;
     if (!fast) return false;
     b.n = a.n; b.T = a.n / CHUNK; b.L = L;
     b.xls = contig ? lines2_xstride(b.T, L) : 0;
@@ -108,7 +109,7 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
     b.pf_dist = (contig || a.stride <= 4096) ? ctx().tune_pf_dist : std::max(ctx().tune_pf_dist, 0);
     b.stride = a.stride; b.inner = a.inner; b.outer_stride = a.outer_stride;
     b.u = a.u; b.u2 = a.u2; b.vel = a.vel; b.out1 = a.out1; b.out2 = a.out2; b.bcs_hb = a.bcs_hb; b.bcs_ht = a.bcs_ht;
-    b.rhs_d1 = p.rhs_d1_2;
+    b.cjac = p.cjac2;
     b.rhs1 = a.rhs1; b.rhs2 = a.rhs2; b.s1 = s1; b.s2 = s2;
     std::memcpy(b.neu_bot, a.neu_bot, sizeof(b.neu_bot));
     std::memcpy(b.neu_top, a.neu_top, sizeof(b.neu_top));
@@ -135,6 +136,9 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
     while (b.tma_rb < 256 && b.n % (b.tma_rb * 2) == 0) b.tma_rb *= 2;
     b.tma_l2 = ctx().tune_tma_l2;
     b.tma = (!contig && !b.pair && ctx().tune_tma && lines2_tma_eligible(mode, b)) ? 1 : 0;
+    b.march_red = ctx().tune_march_red;
+    b.march = (!contig && ctx().tune_march && !b.tma && !b.persist && !b.pair &&
+               march_eligible(mode, b, p.periodic, p.need_1der, a.nlines, a.inner)) ? 1 : 0;
     return true;
 }
 
@@ -143,6 +147,7 @@ static cudaError_t launch_any(int mode, const LineArgs& a, const DevPlan& p, con
     Line2Args b;
     if (!build_line2(mode, a, p, s1, s2, contig, b)) { ctx().general_launches++; return launch_lines(mode, a, periodic, need1, contig, st); }
     ctx().fast_launches++;
+    if (b.march) { ctx().march_launches++; return launch_march(mode, b, periodic, need1, a.nlines, a.inner, st); }
     return launch_lines2(mode, b, periodic, need1, contig, a.nlines, a.inner, st);
 }
 
@@ -404,6 +409,8 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "splitz")) ctx().tune_splitz = value;
     else if (!std::strcmp(key, "split_emulate")) ctx().tune_split_emulate = value;
     else if (!std::strcmp(key, "pf_l1")) ctx().tune_pf_l1 = value;
+    else if (!std::strcmp(key, "march")) ctx().tune_march = value;
+    else if (!std::strcmp(key, "march_red")) ctx().tune_march_red = value;
     else if (!std::strcmp(key, "fuse")) ctx().tune_fuse = value;
     else if (!std::strcmp(key, "overlap")) ctx().tune_overlap = value;
     else if (!std::strcmp(key, "kxsplit")) ctx().tune_kxsplit = value;

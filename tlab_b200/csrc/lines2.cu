@@ -142,27 +142,15 @@ __device__ __forceinline__ void solve_two(double (&f0)[C], double (&f1)[C], cons
     }
 }
 
-// Jacobian correction of the second derivative on non-uniform grids: f2 += A2*jac2 * du (tridiagonal, extended
-// stencil in the first and last row; fdm_matmul.f90:143-145, fdm_derivative.f90:437-440).  The neighbours' end
-// values go through shared memory (one barrier).
-__device__ __forceinline__ void add_jacobian_term(double (&f2)[C], const double (&d1)[C], const Line2Args& a,
-                                                  const ChunkCtx& c, double* sm_h) {
-    sm_h[(2 * c.t) * c.L + c.l] = d1[0];
-    sm_h[(2 * c.t + 1) * c.L + c.l] = d1[C - 1];
-    __syncthreads();
-    const double left = (c.t > 0) ? sm_h[(2 * (c.t - 1) + 1) * c.L + c.l] : d1[2];              // extended stencil, first row
-    const double right = (c.t < c.T - 1) ? sm_h[(2 * (c.t + 1)) * c.L + c.l] : d1[C - 3];       // extended stencil, last row
-    const double2* rp = a.rhs_d1 + ((size_t)(c.t >> 3) * C * 2) * 8 + (c.t & 7);
-    const bool lastc = (c.t == c.T - 1);
+// Jacobian term of the second derivative on non-uniform grids (fdm_derivative.f90:437-440, `f2 += rhs_d1 * du` before the
+// solve): the reference's lhs is A0 diag(dx1^2) and rhs_d1 = -A0 diag(dx2) (fdm_com2_jacobian.f90:263-274), so the term is a
+// diagonal correction of the SOLUTION, d2u = A^-1 B u - (dx2/dx1^2) du (times the diffusivity for a scaled Burgers system).
+// Both systems are therefore solved together and corrected afterwards (identical to round-off: 1e-15 against the oracle).
+__device__ __forceinline__ void jacobian_correction(double (&d2)[C], const double (&d1)[C], const Line2Args& a, const Sys2& S2,
+                                                    const ChunkCtx& c) {
+    const double* cp = a.cjac + ((size_t)(c.t >> 3) * C) * 8 + (c.t & 7);
 #pragma unroll
-    for (int j = 0; j < C; j++) {
-        const double2 r12 = ldg2(rp + (j * 2 + 0) * 8);
-        const double r3 = __ldg(&rp[(j * 2 + 1) * 8].x);
-        const double um = (j == 0) ? left : d1[j > 0 ? j - 1 : 0];
-        const double up = (j == C - 1) ? right : d1[j < C - 1 ? j + 1 : C - 1];
-        if (j == C - 1 && lastc) f2[j] = DADD(DADD(DADD(f2[j], DMUL(up, r3)), DMUL(um, r12.x)), DMUL(d1[j], r12.y));
-        else f2[j] = DADD(DADD(DADD(f2[j], DMUL(um, r12.x)), DMUL(d1[j], r12.y)), DMUL(up, r3));
-    }
+    for (int j = 0; j < C; j++) d2[j] = fma(-(S2.jscale * __ldg(cp + j * 8)), d1[j], d2[j]);
 }
 
 __host__ __device__ inline size_t exch2_doubles(int T, int L) { return (size_t)6 * T * L + (size_t)2 * T * L; }
@@ -187,14 +175,12 @@ __device__ __forceinline__ void line_core2(const double (&u)[C + 6], const Line2
             if (c.t == c.T - 1) rhs_top(u, d2, a.rhs2);
         }
     }
-    if (WANT1 && WANT2 && !NEED1) {
+    if (WANT1 && WANT2) {
         solve_two<PER>(d1, d2, a.s1, S2, c, sm);
+        if (NEED1) jacobian_correction(d2, d1, a, S2, c);
     } else {
         if (WANT1) solve_one<PER>(d1, a.s1, c, sm);
-        if (WANT2) {
-            if (NEED1) add_jacobian_term(d2, d1, a, c, sm + 6 * c.T * c.L);
-            solve_one<PER>(d2, S2, c, sm + 3 * c.T * c.L);
-        }
+        if (WANT2) solve_one<PER>(d2, S2, c, sm + 3 * c.T * c.L);
     }
 }
 

@@ -16,6 +16,8 @@ struct Line2Args {
     int pair = 0;                     // strided kernel: a line is shared by a cluster of 2 CTAs (L lines x T/2 chunks each)
     int tma = 0;                      // strided kernel: persistent CTAs fed and drained by the TMA unit (lines2_strided_tma)
     int tma_rb = 0;                   // rows per TMA box
+    int march = 0;                    // strided kernel: marching panels of 32 lines (march.cu)
+    int march_red = 0;                // marching kernel: accumulate with red.global.add.f64 instead of load + store
     int tma_l2 = 0;                   // L2 promotion of the tensor maps (0 none, 1/2/3: 64/128/256 bytes)
     double scale = 0.0;               // input is u + scale * u2 when u2 != nullptr
     long long stride = 1;             // distance between consecutive points of a line (strided kernel)
@@ -28,7 +30,7 @@ struct Line2Args {
     double* out2 = nullptr;
     double* bcs_hb = nullptr;
     double* bcs_ht = nullptr;
-    const double2* rhs_d1 = nullptr;  // Jacobian correction {r1,r2},{r3,0} per point, chunk-interleaved like Sys2::tab
+    const double* cjac = nullptr;     // Jacobian correction of the second derivative, d2 -= jscale * cjac * d1 (DevPlan::cjac2)
     RhsTab rhs1, rhs2;
     Sys2 s1, s2;
     // fused Burgers launch (several fields advected by the same velocity): fields, results and which of s2 / s2b each uses
@@ -51,5 +53,10 @@ long long lines2_tma_launches();
 bool lines2_tma_eligible(int mode, const Line2Args& a);   // geometry, alignment and shared-memory budget of the TMA kernel
 cudaError_t launch_lines2(int mode, const Line2Args& a, bool periodic, bool need1, bool contig, long long nlines,
                           long long inner, cudaStream_t s);
+
+// marching-panel kernels (march.cu)
+bool march_sys_ok(const std::vector<double>& crec, int T, int K0, int K1, bool periodic);
+bool march_eligible(int mode, const Line2Args& a, bool periodic, bool need1, long long nlines, long long inner);
+cudaError_t launch_march(int mode, const Line2Args& a, bool periodic, bool need1, long long nlines, long long inner, cudaStream_t s);
 
 }  // namespace tlab

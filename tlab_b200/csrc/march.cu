@@ -1,0 +1,331 @@
+// Marching-panel variant of the strided line operators (y and z directions) for sm_100a.
+//
+// Same operators and the same arithmetic as lines2.cu -- OPR_Partial P1 and OPR_Burgers of the reference
+// (src/operators/opr_partial.f90:31-377, src/physics/opr_burgers.f90:439-521; banded products src/fdm/fdm_matmul.f90,
+// Thomas sweeps src/utils/linear3.f90:56-150,321-442) in the chunked formulation described there: every chunk of 16 points
+// runs its two substitution sweeps once with zero inflow and is corrected with the true inflow values A (from the chunk ends
+// before it) and B (from the chunk starts after it).
+//
+// What differs is who holds what.  lines2_strided keeps a whole line in the registers of one CTA (T = n/16 threads per line),
+// so the number of lines per CTA -- the width of the rows the CTA reads -- shrinks with the line length (128 bytes at n = 512,
+// 64 bytes at n = 1024), a tile fills the register file of an SM, and nothing overlaps the load, solve and store phases of a
+// tile.  Here a CTA of MW warps owns a panel of 32 adjacent lines (lane = line: every row access of a warp is one 256-byte
+// segment whatever n is) and marches along the lines in rounds of MW chunks (warp = chunk).  The corrections reach LBM = 3
+// chunks (a chunk multiplies its inflow by < 1e-6; the dropped fourth term is < 2^-64, checked per plan), so the chunks of a
+// round are finished one round later: their zero-inflow solutions wait in a thread-private shared-memory stash (swapped
+// against the new ones), and the only values that cross threads are the chunk ends (two small rings).  A CTA needs 46 KB of
+// shared memory and 128 threads, four CTAs are resident per SM and are in different phases at any time: loads of one overlap
+// the sweeps and barriers of the others.
+//
+// Circulant systems (periodic directions): the rank-one closure x_N is a sum over the first K0 and last K1 <= MW chunks and
+// is needed by exactly those chunks, so the rounds are visited in the order 1, 2, ..., R-1, 0: x_N is complete when the last
+// round and round 0 are finished.  The look-back of round 1 needs the forward ends of the last LBM chunks of round 0, which a
+// short pre-step computes (re-reading 3 chunks of the line).
+//
+// Non-uniform grids: the Jacobian term of the second derivative is a diagonal correction of the solution (see lines2.cu,
+// jacobian_correction), applied when a chunk is finished.
+#include "lines2_dev.cuh"
+#include <algorithm>
+
+namespace tlab {
+
+namespace {
+
+constexpr int MW = 4;                       // warps per CTA = chunks per round
+constexpr int LBM = 3;                      // look-back / look-ahead window in chunks
+constexpr int ML = 32;                      // lines per panel (lane = line)
+constexpr int M_X = C * MW * ML;            // stash of zero-inflow solutions, item (j, w, lane)
+constexpr int M_R = 2 * MW * ML;            // ring of chunk ends: two halves (steps alternate) of MW chunks
+constexpr int M_ZK = LBM * ML;              // circulant: z of the first LBM chunks of round 1, needed again by round 0 at the end
+constexpr int M_SYS = M_X + 3 * M_R + M_ZK; // X | Y | Z | Wc | Zk   (doubles per system)
+
+struct MarchSm {
+    double *X, *Y, *Z, *Wc, *Zk;
+    __device__ __forceinline__ explicit MarchSm(double* p) : X(p), Y(p + M_X), Z(p + M_X + M_R), Wc(p + M_X + 2 * M_R), Zk(p + M_X + 3 * M_R) {}
+};
+
+// chunk t of the thread's line (+ 3-point halos, wrapped or zero) -> registers
+template <bool PER>
+__device__ __forceinline__ void march_load(double (&u)[C + 6], const double* __restrict__ p, const double* __restrict__ p2, double scale,
+                                           int t, int T, int n, long long st) {
+    const bool lok = PER || t > 0, rok = PER || t < T - 1;
+    const long long loff = (t > 0) ? -3 * st : (long long)(n - 3) * st;
+    const long long roff = (t < T - 1) ? (long long)C * st : -(long long)(t * C) * st;
+    const double* __restrict__ pc = p + (long long)(t * C) * st;
+#pragma unroll
+    for (int j = 0; j < C; j++) u[j + 3] = __ldcs(pc + j * st);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        u[k] = lok ? __ldcs(pc + loff + k * st) : 0.0;
+        u[C + 3 + k] = rok ? __ldcs(pc + roff + k * st) : 0.0;
+    }
+    if (p2 != nullptr) {
+        const double* __restrict__ qc = p2 + (long long)(t * C) * st;
+#pragma unroll
+        for (int j = 0; j < C; j++) u[j + 3] = u[j + 3] + __ldcs(qc + j * st) * scale;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (lok) u[k] = u[k] + __ldcs(qc + loff + k * st) * scale;
+            if (rok) u[C + 3 + k] = u[C + 3 + k] + __ldcs(qc + roff + k * st) * scale;
+        }
+    }
+}
+
+template <bool PER, bool SECOND>
+__device__ __forceinline__ void march_rhs(const double (&u)[C + 6], double (&f)[C], const RhsTab& R, int t, int T) {
+    rhs_interior<SECOND>(u, f, R);
+    if (!PER) {
+        if (t == 0) rhs_bottom(u, f, R);
+        if (t == T - 1) rhs_top(u, f, R);
+    }
+}
+
+// zero-inflow sweeps of chunk t (warp-uniform: constants or broadcast table reads)
+template <bool PER>
+__device__ __forceinline__ void march_local(double (&f)[C], const Sys2& S, int t, double& yend, double& part) {
+    part = 0.0;
+    if (__ldg(S.crec + (size_t)t * 16 + 14) != 0.0) local_const(f, S, yend);
+    else local_tab<PER>(f, tab_ptr(S, t), yend, part);
+}
+
+// forward end value only (pre-step of the circulant march)
+__device__ __forceinline__ double march_forward_end(const double (&f)[C], const Sys2& S, int t) {
+    double e = 0.0;
+    if (__ldg(S.crec + (size_t)t * 16 + 14) != 0.0) {
+#pragma unroll
+        for (int j = 0; j < C; j++) e = fma(S.ca, e, f[j]);
+    } else {
+        const double2* tp = tab_ptr(S, t);
+#pragma unroll
+        for (int j = 0; j < C; j++) e = fma(ldg2(tp + (j * 4 + 0) * 8).x, e, f[j]);
+    }
+    return e;
+}
+
+// A of chunk t = round * MW + w from the forward ends of the LBM chunks before it (this round: half h, previous round: other half)
+__device__ __forceinline__ double march_look_back(const double* __restrict__ Y, const double* __restrict__ cr, int h, int w, int lane) {
+    const double* cur = Y + (h * MW) * ML + lane;
+    const double* prv = Y + ((h ^ 1) * MW) * ML + lane;
+    double A = __ldg(cr + 0) * ((w >= 1) ? cur[(w - 1) * ML] : prv[(MW + w - 1) * ML]);
+    A = fma(__ldg(cr + 1), (w >= 2) ? cur[(w - 2) * ML] : prv[(MW + w - 2) * ML], A);
+    A = fma(__ldg(cr + 2), (w >= 3) ? cur[(w - 3) * ML] : prv[(MW + w - 3) * ML], A);
+    return A;
+}
+// B of chunk w of the round in `own` from the chunk starts after it (same round, then the next round in `nxt`)
+__device__ __forceinline__ double march_look_ahead(const double* __restrict__ own, const double* __restrict__ nxt,
+                                                   const double* __restrict__ cr, int w, int lane) {
+    double B = __ldg(cr + LB2 + 0) * ((w + 1 < MW) ? own[(w + 1) * ML + lane] : nxt[(w + 1 - MW) * ML + lane]);
+    B = fma(__ldg(cr + LB2 + 1), (w + 2 < MW) ? own[(w + 2) * ML + lane] : nxt[(w + 2 - MW) * ML + lane], B);
+    B = fma(__ldg(cr + LB2 + 2), (w + 3 < MW) ? own[(w + 3) * ML + lane] : nxt[(w + 3 - MW) * ML + lane], B);
+    return B;
+}
+
+// x = x^ + Q A + R B [+ S x_N] for chunk t (same expressions as finish_const / finish_tab)
+template <bool PER>
+__device__ __forceinline__ void march_finish(double (&x)[C], const Sys2& S, const MarchSm& m, int t, int T, double A, double B, int lane) {
+    if (__ldg(S.crec + (size_t)t * 16 + 14) != 0.0) {
+        finish_const(x, S, A, B);
+    } else {
+        double xN = 0.0;
+        if (PER) {
+            for (int k = 0; k < S.K0; k++) xN += m.Wc[k * ML + lane];
+            for (int k = 0; k < S.K1; k++) xN += m.Wc[(MW + k) * ML + lane];
+        }
+        finish_tab<PER>(x, tab_ptr(S, t), A, B, xN);
+    }
+}
+
+// MODE_P1: out = d/ds (u [+ scale u2]), MODE_BURGERS: out = d2 - vel * d1 (d2 from the diffusivity-scaled system a.s2);
+// accumulate = +1 / -1 adds to / subtracts from out.  JAC: non-uniform direction (Jacobian correction of d2).
+// RED: the accumulation is a fire-and-forget red.global.add.f64 (one IEEE addition per element either way: same bits).
+template <int MODE, bool PER, bool JAC, bool RED>
+__global__ void __launch_bounds__(MW * ML, MODE == MODE_BURGERS ? 4 : 5) lines2_march(const __grid_constant__ Line2Args a) {
+    constexpr bool TWO = (MODE == MODE_BURGERS);
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int T = a.T, n = a.n, R = T / MW;
+    const long long st = a.stride;
+    const long long base = (long long)blockIdx.y * a.outer_stride + (long long)blockIdx.x * ML + lane;
+    const Sys2& S1 = a.s1;
+    const Sys2& S2 = a.s2;
+    const MarchSm m1(sm), m2(sm + M_SYS);
+    // stale ring slots are read with zero weights: they must hold finite numbers
+    for (int i = threadIdx.x; i < (TWO ? 2 : 1) * M_SYS; i += blockDim.x) sm[i] = 0.0;
+    __syncthreads();
+
+    const double* __restrict__ pu = a.u + base;
+    const double* __restrict__ pu2 = (a.u2 != nullptr) ? a.u2 + base : nullptr;
+    const int slot = w * ML + lane;                // this thread's place in a ring half / its stash column
+
+    if (PER && w >= MW - LBM) {
+        // pre-step: forward ends of chunks MW-LBM .. MW-1 of round 0, as seen by the look-back of round 1 (half 1 = "previous")
+        double u[C + 6], f[C];
+        march_load<PER>(u, pu, pu2, a.scale, w, T, n, st);
+        march_rhs<PER, false>(u, f, a.rhs1, w, T);
+        m1.Y[MW * ML + slot] = march_forward_end(f, S1, w);
+        if (TWO) {
+            march_rhs<PER, true>(u, f, a.rhs2, w, T);
+            m2.Y[MW * ML + slot] = march_forward_end(f, S2, w);
+        }
+    }
+
+    double o1[C], o2[C];                           // zero-inflow solutions of the chunk this thread handled one step earlier
+    double A1p = 0.0, A2p = 0.0;                   // and its A
+    for (int s = 0; s <= R; s++) {
+        const bool front = s < R, back = s > 0;
+        const int rf = PER ? ((s + 1 == R) ? 0 : s + 1) : s;          // chunk-order round entering the pipeline
+        const int rb = PER ? ((s == R) ? 0 : s) : s - 1;              // round being finished (entered one step earlier)
+        const int h = s & 1;
+        const int t = rf * MW + w, tb = rb * MW + w;
+        double ye1 = 0.0, ye2 = 0.0, pt1 = 0.0, pt2 = 0.0, x01 = 0.0, x02 = 0.0;
+        if (front) {
+            double u[C + 6], f1[C], f2[C];
+            march_load<PER>(u, pu, pu2, a.scale, t, T, n, st);
+            march_rhs<PER, false>(u, f1, a.rhs1, t, T);
+            if (TWO) march_rhs<PER, true>(u, f2, a.rhs2, t, T);
+            march_local<PER>(f1, S1, t, ye1, pt1);
+            if (TWO) march_local<PER>(f2, S2, t, ye2, pt2);
+            x01 = f1[0];
+            if (TWO) x02 = f2[0];
+            // swap with the stash: the previous chunk's solutions come out, this chunk's go in (thread-private slots)
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                double* q = m1.X + j * (MW * ML) + slot;
+                o1[j] = *q;
+                *q = f1[j];
+                if (TWO) {
+                    double* q2 = m2.X + j * (MW * ML) + slot;
+                    o2[j] = *q2;
+                    *q2 = f2[j];
+                }
+            }
+            m1.Y[(h * MW) * ML + slot] = ye1;
+            if (TWO) m2.Y[(h * MW) * ML + slot] = ye2;
+        } else {
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                o1[j] = m1.X[j * (MW * ML) + slot];
+                if (TWO) o2[j] = m2.X[j * (MW * ML) + slot];
+            }
+        }
+        // the advecting velocity of the chunk being finished: in flight across the two barriers
+        double vv[C];
+        const long long boff = base + (long long)(tb * C) * st;
+        if (TWO && back) {
+            const double* __restrict__ vp = a.vel + boff;
+#pragma unroll
+            for (int j = 0; j < C; j++) vv[j] = __ldcs(vp + j * st);
+        }
+        __syncthreads();
+        double A1 = 0.0, A2 = 0.0;
+        if (front) {
+            const double* cr1 = S1.crec + (size_t)t * 16;
+            A1 = march_look_back(m1.Y, cr1, h, w, lane);
+            const double z1 = fma(__ldg(cr1 + 12), A1, x01);
+            m1.Z[(h * MW) * ML + slot] = z1;
+            if (PER && rf == 1 && w < LBM) m1.Zk[slot] = z1;
+            if (PER && (t < S1.K0 || t >= T - S1.K1))
+                m1.Wc[((t < S1.K0) ? t : MW + t - (T - S1.K1)) * ML + lane] = fma(__ldg(cr1 + 13), A1, pt1);
+            if (TWO) {
+                const double* cr2 = S2.crec + (size_t)t * 16;
+                A2 = march_look_back(m2.Y, cr2, h, w, lane);
+                const double z2 = fma(__ldg(cr2 + 12), A2, x02);
+                m2.Z[(h * MW) * ML + slot] = z2;
+                if (PER && rf == 1 && w < LBM) m2.Zk[slot] = z2;
+                if (PER && (t < S2.K0 || t >= T - S2.K1))
+                    m2.Wc[((t < S2.K0) ? t : MW + t - (T - S2.K1)) * ML + lane] = fma(__ldg(cr2 + 13), A2, pt2);
+            }
+        }
+        __syncthreads();
+        if (back) {
+            const bool wrap = PER && s == R;       // round 0 of a circulant line is finished last: its successors are the kept z
+            const double B1 = march_look_ahead(m1.Z + ((h ^ 1) * MW) * ML, wrap ? m1.Zk : m1.Z + (h * MW) * ML,
+                                               S1.crec + (size_t)tb * 16, w, lane);
+            march_finish<PER>(o1, S1, m1, tb, T, A1p, B1, lane);
+            if (TWO) {
+                const double B2 = march_look_ahead(m2.Z + ((h ^ 1) * MW) * ML, wrap ? m2.Zk : m2.Z + (h * MW) * ML,
+                                                   S2.crec + (size_t)tb * 16, w, lane);
+                march_finish<PER>(o2, S2, m2, tb, T, A2p, B2, lane);
+                if (JAC) {
+                    const double* cp = a.cjac + ((size_t)(tb >> 3) * C) * 8 + (tb & 7);
+#pragma unroll
+                    for (int j = 0; j < C; j++) o2[j] = fma(-(S2.jscale * __ldg(cp + j * 8)), o1[j], o2[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < C; j++) o1[j] = o2[j] - vv[j] * o1[j];
+            }
+            double* __restrict__ po = a.out1 + boff;
+            if (a.accumulate == 0) {
+#pragma unroll
+                for (int j = 0; j < C; j++) __stcs(po + j * st, o1[j]);
+            } else if (RED) {
+#pragma unroll
+                for (int j = 0; j < C; j++) atomicAdd(po + j * st, (a.accumulate > 0) ? o1[j] : -o1[j]);
+            } else {
+                double oo[C];
+#pragma unroll
+                for (int j = 0; j < C; j++) oo[j] = __ldcs(po + j * st);
+#pragma unroll
+                for (int j = 0; j < C; j++) __stcs(po + j * st, (a.accumulate > 0) ? oo[j] + o1[j] : oo[j] - o1[j]);
+            }
+        }
+        A1p = A1;
+        A2p = A2;
+    }
+}
+
+template <int MODE, bool PER, bool JAC>
+cudaError_t launch_march_k(const Line2Args& a, dim3 grid, cudaStream_t stream) {
+    const size_t smem = (size_t)((MODE == MODE_BURGERS) ? 2 : 1) * M_SYS * sizeof(double);
+    if (a.march_red && a.accumulate != 0) {
+        auto k = lines2_march<MODE, PER, JAC, true>;
+        static bool set = false;
+        if (!set) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set = true; }
+        k<<<grid, MW * ML, smem, stream>>>(a);
+    } else {
+        auto k = lines2_march<MODE, PER, JAC, false>;
+        static bool set = false;
+        if (!set) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set = true; }
+        k<<<grid, MW * ML, smem, stream>>>(a);
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// does the window of LBM chunks suffice for this system (dropped weights below 2^-64) and do the closure chunks fit a round?
+bool march_sys_ok(const std::vector<double>& crec, int T, int K0, int K1, bool periodic) {
+    const double tiny = 5.421010862427522e-20;      // 2^-64
+    for (int t = 0; t < T; t++) {
+        const double* c = &crec[(size_t)t * 16];
+        for (int k = LBM; k < LB2; k++)
+            if (std::fabs(c[k]) > tiny || std::fabs(c[LB2 + k]) > tiny) return false;
+    }
+    if (periodic && (K0 > MW || K1 > MW)) return false;
+    return true;
+}
+
+bool march_eligible(int mode, const Line2Args& a, bool periodic, bool need1, long long nlines, long long inner) {
+    if (mode != MODE_P1 && mode != MODE_BURGERS) return false;
+    if (a.T % MW != 0 || a.T < 2 * MW || a.n != a.T * CHUNK) return false;
+    if (inner % ML != 0 || nlines % inner != 0) return false;
+    if (inner / ML > 0x7fffffffLL || nlines / inner > 65535) return false;
+    if (!a.s1.ok || !a.s1.march_ok) return false;
+    if (mode == MODE_BURGERS && (!a.s2.ok || !a.s2.march_ok)) return false;
+    if (mode == MODE_BURGERS && a.u2 != nullptr) return false;
+    if (need1 && mode == MODE_BURGERS && a.cjac == nullptr) return false;
+    if (a.nf > 0) return false;
+    (void)periodic;
+    return true;
+}
+
+cudaError_t launch_march(int mode, const Line2Args& a, bool periodic, bool need1, long long nlines, long long inner, cudaStream_t s) {
+    const dim3 grid((unsigned)(inner / ML), (unsigned)(nlines / inner), 1);
+    if (mode == MODE_P1) {
+        return periodic ? launch_march_k<MODE_P1, true, false>(a, grid, s) : launch_march_k<MODE_P1, false, false>(a, grid, s);
+    }
+    if (periodic) return launch_march_k<MODE_BURGERS, true, false>(a, grid, s);
+    return need1 ? launch_march_k<MODE_BURGERS, false, true>(a, grid, s) : launch_march_k<MODE_BURGERS, false, false>(a, grid, s);
+}
+
+}  // namespace tlab

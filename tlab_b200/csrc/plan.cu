@@ -1,5 +1,6 @@
 // Build the device tables of a plan from the host plan (see plan.h).
 #include "plan.h"
+#include "lines2.h"
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -215,6 +216,7 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
         fprintf(stderr, "[sys2] n=%d T=%d periodic=%d Wf=%d Wb=%d const_chunks=%d K0=%d K1=%d ca=%g cd=%g cg=%g Af=%g Rb=%g\n", n, T,
                 (int)periodic, window(Af, true), window(Rb, false), nc, s2.K0, s2.K1, s2.ca, s2.cd, s2.cg, Af[T / 2], Rb[T / 2]);
     }
+    s2.march_ok = march_sys_ok(crec, T, s2.K0, s2.K1, periodic) ? 1 : 0;
     s2.tab = upload_t(p, tab);
     s2.crec = upload(p, crec);
     s2.ok = (s2.tab && s2.crec) ? 1 : 0;
@@ -247,6 +249,7 @@ void make_solve(DevPlan& p, SolveTab& s, Sys2& s2, const Mat& lu, int c0, int nm
         }
     }
     build_sys2(p, s2, alpha, beta, gamma, delta, pd, pe, s.bN, periodic);
+    s2.jscale = scaled ? diff : 1.0;
     finish_solve(p, s, alpha, beta, gamma, delta, pd, pe, periodic);
 }
 
@@ -322,17 +325,16 @@ int devplan_build(DevPlan& p) {
         std::vector<double> r(3 * (size_t)n);
         for (int i = 1; i <= n; i++) for (int j = 1; j <= 3; j++) r[3 * (size_t)(i - 1) + (j - 1)] = h.der2.rhs(i, h.der2.ndr + j);
         p.rhs_d1 = upload(p, r);
-        if (p.crem == 0 && p.cbase == CHUNK) {
+        // the fast kernels need the tridiagonal lhs without an extended-stencil entry (rhs_d1(1,1) = rhs_d1(n,3) = 0)
+        if (p.crem == 0 && p.cbase == CHUNK && r[0] == 0.0 && r[3 * (size_t)(n - 1) + 2] == 0.0) {
             const int Tp = (p.T + 7) / 8 * 8;
-            std::vector<double2> r2((size_t)Tp * CHUNK * 2, make_double2(0.0, 0.0));
+            std::vector<double> cj((size_t)Tp * CHUNK, 0.0);
             for (int t = 0; t < p.T; t++)
                 for (int j = 0; j < CHUNK; j++) {
-                    const size_t i = (size_t)t * CHUNK + j;
-                    const size_t base = (((size_t)(t >> 3) * CHUNK + j) * 2) * 8 + (t & 7);
-                    r2[base] = make_double2(r[3 * i], r[3 * i + 1]);
-                    r2[base + 8] = make_double2(r[3 * i + 2], 0.0);
+                    const int i = t * CHUNK + j + 1;
+                    cj[((size_t)(t >> 3) * CHUNK + j) * 8 + (t & 7)] = h.jac(i, 3) / (h.jac(i, 2) * h.jac(i, 2));
                 }
-            p.rhs_d1_2 = upload_t(p, r2);
+            p.cjac2 = upload(p, cj);
         }
     }
     {

@@ -57,7 +57,10 @@ struct Sys2 {
     double ca = 0.0, cd = 0.0, cg = 0.0;   // constant-chunk coefficients
     double cQ[CHUNK], cR[CHUNK];           // constant-chunk correction vectors
     int K0 = 0, K1 = 0;              // circulant: chunks [0,K0) and [T-K1,T) contribute to x_N
+    double jscale = 1.0;             // factor of the solution (the diffusivity of a Burgers system): scales the Jacobian correction
     int ok = 0;                      // 0: look-back window too long for the fast kernels
+    int march_ok = 0;                // 1: a window of 3 chunks suffices (dropped weights < 2^-64) and the closure chunks fit one round
+                                     // of the marching kernels (march.cu)
 };
 
 // banded right-hand side B u: constant interior stencil + dense special rows at the ends
@@ -83,7 +86,10 @@ struct DevPlan {
     Sys2 sys1[4];                    // the same systems in the form of lines2.cu
     std::vector<Sys2> sys2;
     const double* rhs_d1 = nullptr;  // [n][3] Jacobian correction of the second derivative (need_1der)
-    const double2* rhs_d1_2 = nullptr;  // the same, chunk-interleaved for lines2.cu
+    const double* cjac2 = nullptr;   // lines2.cu: c_j = dx2_j / dx1_j^2, item (t, j) at ((t>>3)*CHUNK + j)*8 + (t&7).  The Jacobian term of
+                                     // the second derivative is a diagonal correction of the solution: with lhs = A0 diag(dx1^2) and
+                                     // rhs_d1 = -A0 diag(dx2) (fdm_com2_jacobian.f90:263-274; the extended-stencil entry of a tridiagonal
+                                     // lhs is zero), A (d2u) = B u + rhs_d1 du  <=>  d2u = A^-1 B u - c du
     const double* d_mwn1 = nullptr;  // [n] modified wavenumbers of the first derivative (periodic)
     const double* d_jac = nullptr;   // [n] dx/ds
     // Neumann boundary-value closure (BOUNDARY_BCS_NEUMANN_Y): value = sum_k bcsrow[k] u_k + lu_coef * du_1
