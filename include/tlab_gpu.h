@@ -81,6 +81,12 @@ int tlab_gpu_set_async(int on);
 int tlab_gpu_synchronize(void);
 int tlab_gpu_malloc(void** ptr, size_t bytes); /* TLab_Allocate_Real, src/base/tlab_memory.f90:164-216 */
 int tlab_gpu_free(void* ptr);
+/* Unified (managed) memory for a Fortran host that keeps q, s, txc as ordinary arrays (TLab_Allocate_Real with
+ * c_f_pointer on this pointer): the same address is valid on the host and on the device, so the signature-exact Fortran
+ * wrappers (fortran/tlab_gpu_mod.f90) pass c_loc(array) straight through.  tlab_gpu_prefetch moves the pages to the device
+ * (to_device != 0) or back to the host ahead of use; without it they migrate on first touch. */
+int tlab_gpu_malloc_managed(void** ptr, size_t bytes);
+int tlab_gpu_prefetch(const void* ptr, size_t bytes, int to_device);
 int tlab_gpu_upload(void* dst_device, const void* src_host, size_t bytes);
 int tlab_gpu_download(void* dst_host, const void* src_device, size_t bytes);
 int tlab_gpu_copy(void* dst_device, const void* src_device, size_t bytes);
@@ -170,6 +176,17 @@ int tlab_opr_elliptic_init(tlab_plan_t gx, tlab_plan_t gy, tlab_plan_t gz, int k
  * isize_txc_field); dpdy may be NULL.  Only ibc = BCS_NN. */
 int tlab_opr_poisson(int nx, int ny, int nz, int ibc, double* p, double* tmp1, double* tmp2,
                      const double* bcs_hb, const double* bcs_ht, double* dpdy_or_null);
+
+/* OPR_Fourier_X_Forward(nx, ny, nz, in, out) / _Backward, src/operators/opr_fourier.f90:219-329: real-to-complex transform
+ * along x of ny*nz lines; the half spectrum is c(nx/2+1, ny, nz) (interleaved re, im; element nx/2+1 = Nyquist), i.e.
+ * (nx+2)*ny*nz doubles = the reference's isize_txc_field.  Unnormalised like FFTW (backward(forward(a)) = nx * a); the
+ * backward transform may overwrite `in`.  OPR_Fourier_Z_Forward(in, out) / _Backward, opr_fourier.f90:333-433: complex transform
+ * along z of the (nx/2+1)*ny lines of that array (stride (nx/2+1)*ny), in-place allowed; the reference takes the sizes from
+ * module variables, here they are arguments.  cuFFT, as north_star specifies.  Single domain only. */
+int tlab_opr_fourier_x_forward(int nx, int ny, int nz, const double* in, double* out);
+int tlab_opr_fourier_x_backward(int nx, int ny, int nz, double* in, double* out);
+int tlab_opr_fourier_z_forward(int nx, int ny, int nz, double* in, double* out);
+int tlab_opr_fourier_z_backward(int nx, int ny, int nz, double* in, double* out);
 
 /* ---- domain decomposition (z slabs, one process per GPU) -------------------------------------- */
 /* TLabMPI_Initialize + TLabMPI_Trp_Initialize, src/base/tlab_mpi_procs.f90:17-116, tlab_mpi_transpose.f90:68-200,

@@ -48,6 +48,7 @@ struct Context {
                               // stores).  Off: measured slower than the LSU kernels, the TMA unit sustains ~20 GB/s per SM on
                               // rows of 32-128 bytes (profiles/ncu_full_tma_r01.json)
     int tune_march = 1;       // strided fast kernels: marching panels of 32 lines (march.cu) for OPR_Partial P1 and OPR_Burgers
+    int tune_march_cfg = 4;   // marching kernels: CTAs per SM they are compiled for (3 / 4; +10: velocity requested before the barriers)
     int tune_march_red = 0;   // marching kernels: accumulate with red.global.add.f64
     long long march_launches = 0;
     long long fast_launches = 0, general_launches = 0;    // L2 prefetch distance of the fast kernels in tiles (-1: automatic, 0: off)

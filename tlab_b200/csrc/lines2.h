@@ -17,6 +17,7 @@ struct Line2Args {
     int tma = 0;                      // strided kernel: persistent CTAs fed and drained by the TMA unit (lines2_strided_tma)
     int tma_rb = 0;                   // rows per TMA box
     int march = 0;                    // strided kernel: marching panels of 32 lines (march.cu)
+    int march_cfg = 4;                // marching kernel: resident CTAs per SM it is compiled for (+10: velocity requested before the barriers)
     int march_red = 0;                // marching kernel: accumulate with red.global.add.f64 instead of load + store
     int tma_l2 = 0;                   // L2 promotion of the tensor maps (0 none, 1/2/3: 64/128/256 bytes)
     double scale = 0.0;               // input is u + scale * u2 when u2 != nullptr

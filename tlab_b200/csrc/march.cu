@@ -11,13 +11,13 @@
 // 64 bytes at n = 1024), a tile fills the register file of an SM, and nothing overlaps the load, solve and store phases of a
 // tile.  Here a CTA of MW warps owns a panel of 32 adjacent lines (lane = line: every row access of a warp is one 256-byte
 // segment whatever n is) and marches along the lines in rounds of MW chunks (warp = chunk).  The corrections reach LBM = 3
-// chunks (a chunk multiplies its inflow by < 1e-6; the dropped fourth term is < 2^-64, checked per plan), so the chunks of a
+// chunks (a chunk multiplies its inflow by <= 1.5e-6; the dropped fourth term is < 2^-56, checked per plan), so the chunks of a
 // round are finished one round later: their zero-inflow solutions wait in a thread-private shared-memory stash (swapped
 // against the new ones), and the only values that cross threads are the chunk ends (two small rings).  A CTA needs 46 KB of
 // shared memory and 128 threads, four CTAs are resident per SM and are in different phases at any time: loads of one overlap
 // the sweeps and barriers of the others.
 //
-// Circulant systems (periodic directions): the rank-one closure x_N is a sum over the first K0 and last K1 <= MW chunks and
+// Circulant systems (periodic directions): the rank-one closure x_N is a sum over the first K0m and last K1m <= MW chunks and
 // is needed by exactly those chunks, so the rounds are visited in the order 1, 2, ..., R-1, 0: x_N is complete when the last
 // round and round 0 are finished.  The look-back of round 1 needs the forward ends of the last LBM chunks of round 0, which a
 // short pre-step computes (re-reading 3 chunks of the line).
@@ -52,21 +52,31 @@ __device__ __forceinline__ void march_load(double (&u)[C + 6], const double* __r
     const long long loff = (t > 0) ? -3 * st : (long long)(n - 3) * st;
     const long long roff = (t < T - 1) ? (long long)C * st : -(long long)(t * C) * st;
     const double* __restrict__ pc = p + (long long)(t * C) * st;
+    {
+        // running pointers: no table of j * stride offsets to keep in registers
+        const double* q = pc;
 #pragma unroll
-    for (int j = 0; j < C; j++) u[j + 3] = __ldcs(pc + j * st);
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        u[k] = lok ? __ldcs(pc + loff + k * st) : 0.0;
-        u[C + 3 + k] = rok ? __ldcs(pc + roff + k * st) : 0.0;
-    }
-    if (p2 != nullptr) {
-        const double* __restrict__ qc = p2 + (long long)(t * C) * st;
-#pragma unroll
-        for (int j = 0; j < C; j++) u[j + 3] = u[j + 3] + __ldcs(qc + j * st) * scale;
+        for (int j = 0; j < C; j++) { u[j + 3] = __ldcs(q); q += st; }
+        const double* ql = pc + loff;
+        const double* qr = pc + roff;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
-            if (lok) u[k] = u[k] + __ldcs(qc + loff + k * st) * scale;
-            if (rok) u[C + 3 + k] = u[C + 3 + k] + __ldcs(qc + roff + k * st) * scale;
+            u[k] = lok ? __ldcs(ql) : 0.0;
+            u[C + 3 + k] = rok ? __ldcs(qr) : 0.0;
+            ql += st; qr += st;
+        }
+    }
+    if (p2 != nullptr) {
+        const double* q = p2 + (long long)(t * C) * st;
+        const double* ql = q + loff;
+        const double* qr = q + roff;
+#pragma unroll
+        for (int j = 0; j < C; j++) { u[j + 3] = u[j + 3] + __ldcs(q) * scale; q += st; }
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            if (lok) u[k] = u[k] + __ldcs(ql) * scale;
+            if (rok) u[C + 3 + k] = u[C + 3 + k] + __ldcs(qr) * scale;
+            ql += st; qr += st;
         }
     }
 }
@@ -128,8 +138,8 @@ __device__ __forceinline__ void march_finish(double (&x)[C], const Sys2& S, cons
     } else {
         double xN = 0.0;
         if (PER) {
-            for (int k = 0; k < S.K0; k++) xN += m.Wc[k * ML + lane];
-            for (int k = 0; k < S.K1; k++) xN += m.Wc[(MW + k) * ML + lane];
+            for (int k = 0; k < S.K0m; k++) xN += m.Wc[k * ML + lane];
+            for (int k = 0; k < S.K1m; k++) xN += m.Wc[(MW + k) * ML + lane];
         }
         finish_tab<PER>(x, tab_ptr(S, t), A, B, xN);
     }
@@ -138,8 +148,8 @@ __device__ __forceinline__ void march_finish(double (&x)[C], const Sys2& S, cons
 // MODE_P1: out = d/ds (u [+ scale u2]), MODE_BURGERS: out = d2 - vel * d1 (d2 from the diffusivity-scaled system a.s2);
 // accumulate = +1 / -1 adds to / subtracts from out.  JAC: non-uniform direction (Jacobian correction of d2).
 // RED: the accumulation is a fire-and-forget red.global.add.f64 (one IEEE addition per element either way: same bits).
-template <int MODE, bool PER, bool JAC, bool RED>
-__global__ void __launch_bounds__(MW * ML, MODE == MODE_BURGERS ? 4 : 5) lines2_march(const __grid_constant__ Line2Args a) {
+template <int MODE, bool PER, bool JAC, bool RED, int MINB, bool VPRE>
+__global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_constant__ Line2Args a) {
     constexpr bool TWO = (MODE == MODE_BURGERS);
     extern __shared__ double sm[];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -211,10 +221,10 @@ __global__ void __launch_bounds__(MW * ML, MODE == MODE_BURGERS ? 4 : 5) lines2_
         // the advecting velocity of the chunk being finished: in flight across the two barriers
         double vv[C];
         const long long boff = base + (long long)(tb * C) * st;
-        if (TWO && back) {
-            const double* __restrict__ vp = a.vel + boff;
+        if (TWO && back && VPRE) {
+            const double* vp = a.vel + boff;
 #pragma unroll
-            for (int j = 0; j < C; j++) vv[j] = __ldcs(vp + j * st);
+            for (int j = 0; j < C; j++) { vv[j] = __ldcs(vp); vp += st; }
         }
         __syncthreads();
         double A1 = 0.0, A2 = 0.0;
@@ -224,20 +234,25 @@ __global__ void __launch_bounds__(MW * ML, MODE == MODE_BURGERS ? 4 : 5) lines2_
             const double z1 = fma(__ldg(cr1 + 12), A1, x01);
             m1.Z[(h * MW) * ML + slot] = z1;
             if (PER && rf == 1 && w < LBM) m1.Zk[slot] = z1;
-            if (PER && (t < S1.K0 || t >= T - S1.K1))
-                m1.Wc[((t < S1.K0) ? t : MW + t - (T - S1.K1)) * ML + lane] = fma(__ldg(cr1 + 13), A1, pt1);
+            if (PER && (t < S1.K0m || t >= T - S1.K1m))
+                m1.Wc[((t < S1.K0m) ? t : MW + t - (T - S1.K1m)) * ML + lane] = fma(__ldg(cr1 + 13), A1, pt1);
             if (TWO) {
                 const double* cr2 = S2.crec + (size_t)t * 16;
                 A2 = march_look_back(m2.Y, cr2, h, w, lane);
                 const double z2 = fma(__ldg(cr2 + 12), A2, x02);
                 m2.Z[(h * MW) * ML + slot] = z2;
                 if (PER && rf == 1 && w < LBM) m2.Zk[slot] = z2;
-                if (PER && (t < S2.K0 || t >= T - S2.K1))
-                    m2.Wc[((t < S2.K0) ? t : MW + t - (T - S2.K1)) * ML + lane] = fma(__ldg(cr2 + 13), A2, pt2);
+                if (PER && (t < S2.K0m || t >= T - S2.K1m))
+                    m2.Wc[((t < S2.K0m) ? t : MW + t - (T - S2.K1m)) * ML + lane] = fma(__ldg(cr2 + 13), A2, pt2);
             }
         }
         __syncthreads();
         if (back) {
+            if (TWO && !VPRE) {
+                const double* vp = a.vel + boff;
+#pragma unroll
+                for (int j = 0; j < C; j++) { vv[j] = __ldcs(vp); vp += st; }
+            }
             const bool wrap = PER && s == R;       // round 0 of a circulant line is finished last: its successors are the kept z
             const double B1 = march_look_ahead(m1.Z + ((h ^ 1) * MW) * ML, wrap ? m1.Zk : m1.Z + (h * MW) * ML,
                                                S1.crec + (size_t)tb * 16, w, lane);
@@ -254,19 +269,20 @@ __global__ void __launch_bounds__(MW * ML, MODE == MODE_BURGERS ? 4 : 5) lines2_
 #pragma unroll
                 for (int j = 0; j < C; j++) o1[j] = o2[j] - vv[j] * o1[j];
             }
-            double* __restrict__ po = a.out1 + boff;
+            double* po = a.out1 + boff;
             if (a.accumulate == 0) {
 #pragma unroll
-                for (int j = 0; j < C; j++) __stcs(po + j * st, o1[j]);
+                for (int j = 0; j < C; j++) { __stcs(po, o1[j]); po += st; }
             } else if (RED) {
 #pragma unroll
-                for (int j = 0; j < C; j++) atomicAdd(po + j * st, (a.accumulate > 0) ? o1[j] : -o1[j]);
+                for (int j = 0; j < C; j++) { atomicAdd(po, (a.accumulate > 0) ? o1[j] : -o1[j]); po += st; }
             } else {
                 double oo[C];
+                const double* pi = po;
 #pragma unroll
-                for (int j = 0; j < C; j++) oo[j] = __ldcs(po + j * st);
+                for (int j = 0; j < C; j++) { oo[j] = __ldcs(pi); pi += st; }
 #pragma unroll
-                for (int j = 0; j < C; j++) __stcs(po + j * st, (a.accumulate > 0) ? oo[j] + o1[j] : oo[j] - o1[j]);
+                for (int j = 0; j < C; j++) { __stcs(po, (a.accumulate > 0) ? oo[j] + o1[j] : oo[j] - o1[j]); po += st; }
             }
         }
         A1p = A1;
@@ -274,28 +290,40 @@ __global__ void __launch_bounds__(MW * ML, MODE == MODE_BURGERS ? 4 : 5) lines2_
     }
 }
 
+template <int MODE, bool PER, bool JAC, bool RED, int MINB, bool VPRE>
+cudaError_t launch_march_v(const Line2Args& a, dim3 grid, cudaStream_t stream) {
+    const size_t smem = (size_t)((MODE == MODE_BURGERS) ? 2 : 1) * M_SYS * sizeof(double);
+    auto k = lines2_march<MODE, PER, JAC, RED, MINB, VPRE>;
+    static bool set = false;
+    if (!set) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set = true; }
+    k<<<grid, MW * ML, smem, stream>>>(a);
+    return cudaGetLastError();
+}
+
+// march_cfg (tuning key "march_cfg"): CTAs per SM the kernel is compiled for (3: 168 registers, 4: 128) and whether the
+// velocity of the chunk being finished is requested before the barriers (+10) or after them
 template <int MODE, bool PER, bool JAC>
 cudaError_t launch_march_k(const Line2Args& a, dim3 grid, cudaStream_t stream) {
-    const size_t smem = (size_t)((MODE == MODE_BURGERS) ? 2 : 1) * M_SYS * sizeof(double);
-    if (a.march_red && a.accumulate != 0) {
-        auto k = lines2_march<MODE, PER, JAC, true>;
-        static bool set = false;
-        if (!set) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set = true; }
-        k<<<grid, MW * ML, smem, stream>>>(a);
-    } else {
-        auto k = lines2_march<MODE, PER, JAC, false>;
-        static bool set = false;
-        if (!set) { cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); if (e != cudaSuccess) return e; set = true; }
-        k<<<grid, MW * ML, smem, stream>>>(a);
+    const bool red = a.march_red && a.accumulate != 0;
+    const int cfg = a.march_cfg;
+    if (MODE != MODE_BURGERS) {
+        if (cfg % 10 == 3) return red ? launch_march_v<MODE, PER, JAC, true, 3, false>(a, grid, stream) : launch_march_v<MODE, PER, JAC, false, 3, false>(a, grid, stream);
+        if (cfg % 10 == 5) return red ? launch_march_v<MODE, PER, JAC, true, 5, false>(a, grid, stream) : launch_march_v<MODE, PER, JAC, false, 5, false>(a, grid, stream);
+        return red ? launch_march_v<MODE, PER, JAC, true, 4, false>(a, grid, stream) : launch_march_v<MODE, PER, JAC, false, 4, false>(a, grid, stream);
     }
-    return cudaGetLastError();
+    if (cfg == 3) return red ? launch_march_v<MODE, PER, JAC, true, 3, false>(a, grid, stream) : launch_march_v<MODE, PER, JAC, false, 3, false>(a, grid, stream);
+    if (cfg == 13) return red ? launch_march_v<MODE, PER, JAC, true, 3, true>(a, grid, stream) : launch_march_v<MODE, PER, JAC, false, 3, true>(a, grid, stream);
+    if (cfg == 14) return red ? launch_march_v<MODE, PER, JAC, true, 4, true>(a, grid, stream) : launch_march_v<MODE, PER, JAC, false, 4, true>(a, grid, stream);
+    return red ? launch_march_v<MODE, PER, JAC, true, 4, false>(a, grid, stream) : launch_march_v<MODE, PER, JAC, false, 4, false>(a, grid, stream);
 }
 
 }  // namespace
 
-// does the window of LBM chunks suffice for this system (dropped weights below 2^-64) and do the closure chunks fit a round?
+// does the window of LBM chunks suffice for this system (dropped weights below 2^-56 = eps/8: the compact schemes of the
+// reference multiply an inflow by 2e-7 (first derivative) and 1.5e-6 (second) per chunk, i.e. 8e-21 and 3.4e-18 after three) and
+// do the closure chunks fit a round?
 bool march_sys_ok(const std::vector<double>& crec, int T, int K0, int K1, bool periodic) {
-    const double tiny = 5.421010862427522e-20;      // 2^-64
+    const double tiny = 1.3877787807814457e-17;     // 2^-56
     for (int t = 0; t < T; t++) {
         const double* c = &crec[(size_t)t * 16];
         for (int k = LBM; k < LB2; k++)

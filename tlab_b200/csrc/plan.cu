@@ -182,6 +182,19 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
         for (int t = k0; t < T - k1; t++) if (carries(t)) { k0 = T; k1 = 0; break; }
         s2.K0 = k0; s2.K1 = k1;
         for (int t = 0; t < T; t++) if (t < k0 || t >= T - k1) isc[t] = 0;
+        // the same at 2^-56 (eps/8) for the marching kernels, whose closure chunks must fit one round
+        auto carries56 = [&](int t) {
+            for (int j = 0; j < CHUNK; j++) {
+                const int i = t * CHUNK + j;
+                if (std::fabs(pp[i]) > std::ldexp(pmax, -56) || std::fabs(S[i]) > std::ldexp(smax, -56)) return true;
+            }
+            return false;
+        };
+        int m0 = 0, m1 = 0;
+        while (m0 < T && carries56(m0)) m0++;
+        while (m1 < T - m0 && carries56(T - 1 - m1)) m1++;
+        for (int t = m0; t < T - m1; t++) if (carries56(t)) { m0 = T; m1 = 0; break; }
+        s2.K0m = m0; s2.K1m = m1;
     }
     const int Tp = (T + 7) / 8 * 8;
     std::vector<double2> tab((size_t)Tp * CHUNK * 4, make_double2(0.0, 0.0));
@@ -216,7 +229,7 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
         fprintf(stderr, "[sys2] n=%d T=%d periodic=%d Wf=%d Wb=%d const_chunks=%d K0=%d K1=%d ca=%g cd=%g cg=%g Af=%g Rb=%g\n", n, T,
                 (int)periodic, window(Af, true), window(Rb, false), nc, s2.K0, s2.K1, s2.ca, s2.cd, s2.cg, Af[T / 2], Rb[T / 2]);
     }
-    s2.march_ok = march_sys_ok(crec, T, s2.K0, s2.K1, periodic) ? 1 : 0;
+    s2.march_ok = march_sys_ok(crec, T, s2.K0m, s2.K1m, periodic) ? 1 : 0;
     s2.tab = upload_t(p, tab);
     s2.crec = upload(p, crec);
     s2.ok = (s2.tab && s2.crec) ? 1 : 0;

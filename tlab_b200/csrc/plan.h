@@ -57,6 +57,7 @@ struct Sys2 {
     double ca = 0.0, cd = 0.0, cg = 0.0;   // constant-chunk coefficients
     double cQ[CHUNK], cR[CHUNK];           // constant-chunk correction vectors
     int K0 = 0, K1 = 0;              // circulant: chunks [0,K0) and [T-K1,T) contribute to x_N
+    int K0m = 0, K1m = 0;            // the same with a threshold of 2^-56 instead of 2^-80 (march.cu)
     double jscale = 1.0;             // factor of the solution (the diffusivity of a Burgers system): scales the Jacobian correction
     int ok = 0;                      // 0: look-back window too long for the fast kernels
     int march_ok = 0;                // 1: a window of 3 chunks suffices (dropped weights < 2^-64) and the closure chunks fit one round

@@ -164,3 +164,25 @@ def OPR_Poisson(nx, ny, nz, ibc, p, tmp1, tmp2, bcs_hb, bcs_ht, dpdy=None):
         raise ValueError("tmp1/tmp2 must hold (nx+2)*ny*nz doubles")
     _call(_lib.load().tlab_opr_poisson, nx, ny, nz, ibc, _ptr(p), _ptr(tmp1), _ptr(tmp2), _ptr(bcs_hb), _ptr(bcs_ht),
           _ptr(dpdy))
+
+
+def OPR_Fourier_X_Forward(nx, ny, nz, in_, out):
+    """opr_fourier.f90:219-273: out = c(nx/2+1, ny, nz) as (nx+2)*ny*nz doubles (re, im interleaved)"""
+    if out.numel() < (nx + 2) * ny * nz:
+        raise ValueError("out must hold (nx+2)*ny*nz doubles")
+    _call(_lib.load().tlab_opr_fourier_x_forward, nx, ny, nz, _ptr(in_), _ptr(out))
+
+
+def OPR_Fourier_X_Backward(nx, ny, nz, in_, out):
+    """opr_fourier.f90:277-329 (unnormalised; may overwrite in_)"""
+    _call(_lib.load().tlab_opr_fourier_x_backward, nx, ny, nz, _ptr(in_), _ptr(out))
+
+
+def OPR_Fourier_Z_Forward(nx, ny, nz, in_, out):
+    """opr_fourier.f90:333-381 (the reference reads the sizes from module variables)"""
+    _call(_lib.load().tlab_opr_fourier_z_forward, nx, ny, nz, _ptr(in_), _ptr(out))
+
+
+def OPR_Fourier_Z_Backward(nx, ny, nz, in_, out):
+    """opr_fourier.f90:385-433 (unnormalised)"""
+    _call(_lib.load().tlab_opr_fourier_z_backward, nx, ny, nz, _ptr(in_), _ptr(out))
