@@ -154,14 +154,16 @@ def test_case01_shape_two_dimensional_step(cuda):
 
 @pytest.mark.parametrize("tune", [{"fuse": 1}, {"fuse": 1, "pf_next": 1}, {"persist": 1}, {"pf_dist": 3}, {"fast": 0},
                                   {"tma": 1}, {"poisson_split": 0}, {"poisson_split": 1},
-                                  {"neu_compact": 0}, {"fuse_update": 0}])
+                                  {"neu_compact": 0}, {"fuse_update": 0}, {"lazy_scale": 0}, {"lazy_scale": 1, "fuse": 1},
+                                  {"lazy_scale": 1, "fast": 0}, {"march": 0}, {"march": 2}])
 def test_tuning_variants_give_the_same_step(cuda, tune):
     """The optional kernel variants (fused multi-field Burgers launch, next-field / next-tile L2 prefetch, persistent
     cp.async staging, general kernels) are alternative schedules of the same arithmetic: one RK step on full chunks
     (64 x 64 x 32) must agree with the oracle like the default path does."""
     from tlab_b200 import lib as tl
     L = tl.load()
-    defaults = {"fuse": 0, "pf_next": 0, "persist": 0, "pf_dist": -1, "fast": 1, "tma": 0, "poisson_split": -1, "neu_compact": 1, "fuse_update": 1}
+    defaults = {"fuse": 0, "pf_next": 0, "persist": 0, "pf_dist": -1, "fast": 1, "tma": 0, "poisson_split": -1, "neu_compact": 1, "fuse_update": 1,
+                "lazy_scale": 1, "march": 1}
     try:
         for k, v in tune.items():
             tl.check(L.tlab_gpu_set_tuning(k.encode(), v))
@@ -341,3 +343,27 @@ def test_two_live_states_of_different_size(cuda):
     o1.runge_kutta(1e-3)
     g1.runge_kutta(1e-3)
     assert rel_l2(g1.get("q2"), o1.q[1]) <= 1e-11
+
+
+def test_pending_rk_factor_is_invisible_to_the_host(cuda):
+    """`hq = hq*kco` is not written by the update kernel but folded into the first accumulation of the next substep; a host that
+    reads hq / hs between stages (tlab_dns_download_host, tlab_dns_field) must still see the scaled arrays, bit for bit the ones
+    of the eager schedule, and the next stage must not apply the factor twice."""
+    from tlab_b200 import lib as tl
+    L = tl.load()
+    out = {}
+    for lazy in (0, 1):
+        tl.check(L.tlab_gpu_set_tuning(b"lazy_scale", lazy))
+        try:
+            o, g = _pair(64, 64, 32, "tanh")
+            g.runge_kutta_stage(1e-3, 0)
+            g.runge_kutta_stage(1e-3, 1)
+            mid = [g.get(n) for n in ("hq1", "hq2", "hq3", "hs1")]       # flushes the pending factor
+            g.runge_kutta_stage(1e-3, 2)
+            end = [g.get(n) for n in ("hq1", "hq2", "hq3", "hs1", "q1", "q2", "q3", "s1")]
+            out[lazy] = (mid, end)
+            g.close()
+        finally:
+            tl.check(L.tlab_gpu_set_tuning(b"lazy_scale", 1))
+    for a, b in zip(out[0][0] + out[0][1], out[1][0] + out[1][1]):
+        assert np.array_equal(a, b)

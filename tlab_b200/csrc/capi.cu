@@ -138,6 +138,7 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
     b.tma = (!contig && !b.pair && ctx().tune_tma && lines2_tma_eligible(mode, b)) ? 1 : 0;
     b.march_red = ctx().tune_march_red;
     b.march_cfg = ctx().tune_march_cfg;
+    b.march_pf = ctx().tune_march_pf;
     // marching panels: periodic directions by default (z: 21.8 -> 14.6 ms for the four Burgers launches at C3, 8.4 -> 5.2 ms for the two
     // derivatives); non-periodic directions (all chunks read coefficient tables) only on request (march = 2) or when the lines
     // are so long that the whole-line kernels are left with 64-byte rows (more than 32 chunks)
@@ -147,10 +148,31 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
     return true;
 }
 
-static cudaError_t launch_any(int mode, const LineArgs& a, const DevPlan& p, const Sys2& s1, const Sys2& s2, bool periodic,
+__global__ void scale_array_kernel(double* __restrict__ a, double k, long long n) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] = k * a[i];
+}
+
+void scale_array(double* a, double k, long long n, cudaStream_t st) {
+    const long long blocks = std::min<long long>((n + 255) / 256, 148LL * 16);
+    scale_array_kernel<<<(unsigned)blocks, 256, 0, st>>>(a, k, n);
+}
+
+static cudaError_t launch_any(int mode, const LineArgs& a_in, const DevPlan& p, const Sys2& s1, const Sys2& s2, bool periodic,
                               bool need1, bool contig, cudaStream_t st) {
+    LineArgs a = a_in;
     Line2Args b;
-    if (!build_line2(mode, a, p, s1, s2, contig, b)) { ctx().general_launches++; return launch_lines(mode, a, periodic, need1, contig, st); }
+    const bool fast = build_line2(mode, a, p, s1, s2, contig, b);
+    // a pending factor of the accumulation target is fused by the contiguous fast kernel only; otherwise it is applied first
+    const bool fuse_scale = fast && contig && !b.tma && a.accumulate != 0 && (mode == MODE_BURGERS || mode == MODE_P1);
+    if (a.acc_scale != 1.0 && a.accumulate != 0 && !fuse_scale) {
+        long long n = 0;
+        if (contig) n = a.nlines * a.n;
+        else n = (a.nlines / a.inner - 1) * a.outer_stride + (long long)(a.n - 1) * a.stride + a.inner;   // last element + 1
+        scale_array(a.out1, a.acc_scale, n, st);
+        a.acc_scale = 1.0;
+    }
+    b.acc_scale = fuse_scale ? a.acc_scale : 1.0;
+    if (!fast) { ctx().general_launches++; return launch_lines(mode, a, periodic, need1, contig, st); }
     ctx().fast_launches++;
     if (b.march) { ctx().march_launches++; return launch_march(mode, b, periodic, need1, a.nlines, a.inner, st); }
     return launch_lines2(mode, b, periodic, need1, contig, a.nlines, a.inner, st);
@@ -197,12 +219,13 @@ int run_partial(int dir, int type, int nx, int ny, int nz, int ibc, tlab_plan_s*
 }
 
 int run_burgers(int dir, int is, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* s, const double* vel,
-                double* result, int accumulate) {
+                double* result, int accumulate, double acc_scale) {
     int rc = check_dims(dir, nx, ny, nz, g);
     if (rc) return rc;
     cudaStream_t st = ctx().stream;
     if (g->p.n == 1) {       // opr_burgers.f90:207-210
         if (!accumulate) cudaMemsetAsync(result, 0, (size_t)nx * ny * nz * sizeof(double), st);
+        else if (acc_scale != 1.0) scale_array(result, acc_scale, (long long)nx * ny * nz, st);
         return 0;
     }
     if (g->burgers_first < 0) return fail(TLAB_ERR_OPTION, "tlab_opr_burgers_init has not been called for this plan");
@@ -213,7 +236,7 @@ int run_burgers(int dir, int is, int nx, int ny, int nz, int ibc, tlab_plan_s* g
     fill_common(a, p);
     bool contig;
     set_geometry(a, dir, nx, ny, nz, contig);
-    a.u = s; a.vel = vel; a.out1 = result; a.accumulate = accumulate;
+    a.u = s; a.vel = vel; a.out1 = result; a.accumulate = accumulate; a.acc_scale = acc_scale;
     a.rhs1 = p.rhs1[ibc];
     a.lu1 = p.lu1[ibc];
     a.lu2 = p.lu2[g->burgers_first + is];
@@ -431,8 +454,10 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "split_emulate")) ctx().tune_split_emulate = value;
     else if (!std::strcmp(key, "pf_l1")) ctx().tune_pf_l1 = value;
     else if (!std::strcmp(key, "march")) ctx().tune_march = value;
+    else if (!std::strcmp(key, "lazy_scale")) ctx().tune_lazy_scale = value;
     else if (!std::strcmp(key, "march_red")) ctx().tune_march_red = value;
     else if (!std::strcmp(key, "march_cfg")) ctx().tune_march_cfg = value;
+    else if (!std::strcmp(key, "march_pf")) ctx().tune_march_pf = value;
     else if (!std::strcmp(key, "fuse")) ctx().tune_fuse = value;
     else if (!std::strcmp(key, "overlap")) ctx().tune_overlap = value;
     else if (!std::strcmp(key, "kxsplit")) ctx().tune_kxsplit = value;

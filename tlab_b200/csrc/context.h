@@ -47,8 +47,11 @@ struct Context {
     int tune_tma = 0;         // strided fast kernels: persistent CTAs fed and drained by the TMA unit (tensor maps, reduce-add
                               // stores).  Off: measured slower than the LSU kernels, the TMA unit sustains ~20 GB/s per SM on
                               // rows of 32-128 bytes (profiles/ncu_full_tma_r01.json)
+    int tune_lazy_scale = 1;  // RK substep: `hq = hq*kco` is not written by the update but folded into the first accumulation of the next
+                              // substep (buoyancy source, OPR_Burgers_X): 8 B/pt less per field and substep, same bits
     int tune_march = 1;       // strided fast kernels: marching panels of 32 lines (march.cu) for OPR_Partial P1 and OPR_Burgers
     int tune_march_cfg = 4;   // marching kernels: CTAs per SM they are compiled for (3 / 4; +10: velocity requested before the barriers)
+    int tune_march_pf = 0;
     int tune_march_red = 0;   // marching kernels: accumulate with red.global.add.f64
     long long march_launches = 0;
     long long fast_launches = 0, general_launches = 0;    // L2 prefetch distance of the fast kernels in tiles (-1: automatic, 0: off)
@@ -77,7 +80,8 @@ int finish();          // synchronise unless async; maps errors
 int run_partial(int dir, int type, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* u, double* result,
                 double* tmp1, const double* u2 = nullptr, double scale = 0.0, int accumulate = 0);
 int run_burgers(int dir, int is, int nx, int ny, int nz, int ibc, tlab_plan_s* g, const double* s, const double* vel,
-                double* result, int accumulate);
+                double* result, int accumulate, double acc_scale = 1.0);   // accumulate != 0: result = acc_scale*result +|- operator
+void scale_array(double* a, double k, long long n, cudaStream_t st);
 int run_burgers_multi(int dir, int nf, const int* is, const double* const* sf, const double* vel, double* const* out,
                       int nx, int ny, int nz, tlab_plan_s* g, long long* launches);
 int run_neumann_y(int ibc, int nx, int ny, int nz, tlab_plan_s* g, const double* u, double* hb, double* ht);

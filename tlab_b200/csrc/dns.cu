@@ -35,10 +35,11 @@ inline unsigned ew_blocks(long long n) {
     return (unsigned)(b < cap ? b : cap);
 }
 
-// hq(iq) += vector(iq) * b,   b = c1*s1 - (ref(j) - c0)   (linear)  or  b = const (homogeneous)
+// hq(iq) = k(iq)*hq(iq) + vector(iq) * b,   b = c1*s1 - (ref(j) - c0)   (linear)  or  b = const (homogeneous)
 __global__ void buoyancy_kernel(double* __restrict__ hq1, double* __restrict__ hq2, double* __restrict__ hq3,
                                 const double* __restrict__ s1, const double* __restrict__ ref, double c1, double c0,
-                                double bhom, int linear, double g1, double g2, double g3, int nx, int ny, long long n) {
+                                double bhom, int linear, double g1, double g2, double g3, double k1, double k2, double k3,
+                                int nx, int ny, long long n) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         double b;
         if (linear) {
@@ -48,9 +49,10 @@ __global__ void buoyancy_kernel(double* __restrict__ hq1, double* __restrict__ h
         } else {
             b = bhom;
         }
-        if (g1 != 0.0) hq1[i] = hq1[i] + g1 * b;
-        if (g2 != 0.0) hq2[i] = hq2[i] + g2 * b;
-        if (g3 != 0.0) hq3[i] = hq3[i] + g3 * b;
+        // k: pending factor of the previous substep (`hq = hq*kco`, time.f90:290-297), rounded before the sum as there; 1 otherwise
+        if (g1 != 0.0) hq1[i] = __dmul_rn(k1, hq1[i]) + g1 * b;
+        if (g2 != 0.0) hq2[i] = __dmul_rn(k2, hq2[i]) + g2 * b;
+        if (g3 != 0.0) hq3[i] = __dmul_rn(k3, hq3[i]) + g3 * b;
     }
 }
 
@@ -231,6 +233,16 @@ struct Dns {
     // plans and are re-pointed by activate(); the split-z exchange blocks are re-sized by activate() when the geometry differs.
     Poisson* pois = nullptr;
     int bfirst[3] = {-1, -1, -1};
+    // `hq = hq*kco` of a substep is not written by the update kernels: the factor waits here (index 0-2: hq, 3+is: hs) and is
+    // applied by the first accumulation of the next substep (buoyancy source, OPR_Burgers_X) or by flush_pending()
+    double pending[3 + TLAB_MAX_SCAL] = {1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1};
+    double take_pending(int f) { const double k = pending[f]; pending[f] = 1.0; return k; }
+    void flush_pending() {
+        for (int f = 0; f < 3 + ns; f++) {
+            const double k = take_pending(f);
+            if (k != 1.0) { scale_array(f < 3 ? hq[f] : hs[f - 3], k, N, ctx().stream); launches++; }
+        }
+    }
     bool defer_v = false;      // substep(): `hq2 -= dpdy` and the wall planes of hq2 are left to the fused update of q2
     bool v_deferred = false;   // ... and rhs() did leave them (non-overlapped schedule, Dirichlet at both walls)
 
@@ -250,9 +262,11 @@ struct Dns {
         const int linear = (prm.buoyancy_type == 2);
         if (linear && ns < 1) return fail(TLAB_ERR_OPTION, "linear buoyancy needs a scalar");
         ProfScope ps(PC_ELEMENTWISE);
+        const double k1 = (g1 != 0.0) ? take_pending(0) : 1.0, k2 = (g2 != 0.0) ? take_pending(1) : 1.0,
+                     k3 = (g3 != 0.0) ? take_pending(2) : 1.0;
         buoyancy_kernel<<<ew_blocks(N), EW_THREADS, 0, ctx().stream>>>(
             hq[0], hq[1], hq[2], linear ? s[0] : nullptr, bbackground, prm.buoyancy_params[0], prm.buoyancy_params[1],
-            prm.buoyancy_params[0], linear, g1, g2, g3, nx, ny, N);
+            prm.buoyancy_params[0], linear, g1, g2, g3, k1, k2, k3, nx, ny, N);
         launches++;
         return 0;
     }
@@ -312,6 +326,7 @@ struct Dns {
     }
 
     int rhs_overlapped(double dte) {
+        flush_pending();
         cudaStream_t s0 = ctx().stream, s1 = trp().zstream;
         const int b0 = 0;
         int rc = 0;
@@ -411,10 +426,10 @@ struct Dns {
         cudaStream_t st = ctx().stream;
         const int b0 = 0;   // bcs = 0: biased, non-zero (rhs_global_incompressible_1.f90:67)
         int rc = 0;
-        auto B = [&](int dir, int is, const double* sf, const double* vel, double* out) {
+        auto B = [&](int dir, int is, const double* sf, const double* vel, double* out, double acc_scale = 1.0) {
             if (rc) return;
             if (dir == 3) rc = burgers_z(is, sf, vel, out, sf == vel);
-            else rc = run_burgers(dir, is, nx, ny, nz, b0, g[dir - 1], sf, vel, out, +1);
+            else rc = run_burgers(dir, is, nx, ny, nz, b0, g[dir - 1], sf, vel, out, +1, acc_scale);
             launches++;
         };
         double *u = q[0], *v = q[1], *w = q[2];
@@ -428,13 +443,19 @@ struct Dns {
         double* outs[4] = {hq[0], hq[1], hq[2], ns > 0 ? hs[0] : nullptr};
         const int isv[4] = {0, 0, 0, 1};
         const bool fuse_z = (P == 1) && !split;
+        if (ctx().tune_fuse) flush_pending();
         for (int dir = 1; dir <= 3 && !rc; dir++) {
             if (dir == 3 && !fuse_z) break;
+            if (dir == 1 && !ctx().tune_fuse) {
+                // the first accumulation into every hq / hs of this substep: it also applies the pending `h = h*kco`
+                for (int f = 0; f < nfields; f++) B(1, isv[f], sf[f], u, outs[f], take_pending(f));
+                continue;
+            }
             rc = run_burgers_multi(dir, nfields, isv, sf, q[dir - 1], outs, nx, ny, nz, g[dir - 1], &launches);
         }
         if (!fuse_z) { B(3, 0, u, w, hq[0]); B(3, 0, v, w, hq[1]); B(3, 0, w, w, hq[2]); if (ns > 0) B(3, 1, s[0], w, hs[0]); }
         for (int is = 1; is < ns; is++) {              // further scalars: one launch each
-            B(1, is + 1, s[is], u, hs[is]); B(2, is + 1, s[is], v, hs[is]); B(3, is + 1, s[is], w, hs[is]);
+            B(1, is + 1, s[is], u, hs[is], take_pending(3 + is)); B(2, is + 1, s[is], v, hs[is]); B(3, is + 1, s[is], w, hs[is]);
         }
         if (rc) return rc;
         // pressure forcing: div(hq + q/dte), accumulated in the order y, x, z (:177-260)
@@ -495,16 +516,22 @@ struct Dns {
         if (rc) { v_deferred = false; return rc; }
         cudaStream_t st = ctx().stream;
         ProfScope ps(PC_ELEMENTWISE);
+        // `h = h*kco` (time.f90:290-297) waits for the first accumulation of the next substep instead of being written now
+        const bool lazy = scale_h && ctx().tune_lazy_scale;
+        const int sh = lazy ? 0 : scale_h;
         for (int f = 0; f < 3; f++) {
             if (f == 1 && v_deferred)
-                rk_update_sub_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(q[1], hq[1], tmp3, dte, kcoef, scale_h, nx, ny, N);
+                rk_update_sub_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(q[1], hq[1], tmp3, dte, kcoef, sh, nx, ny, N);
             else
-                rk_update_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(q[f], hq[f], dte, kcoef, scale_h, 0, 0.0, 0.0, N);
+                rk_update_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(q[f], hq[f], dte, kcoef, sh, 0, 0.0, 0.0, N);
+            if (lazy) pending[f] = kcoef;
         }
         v_deferred = false;
-        for (int is = 0; is < ns; is++)
-            rk_update_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(s[is], hs[is], dte, kcoef, scale_h, prm.scal_limit,
+        for (int is = 0; is < ns; is++) {
+            rk_update_kernel<<<ew_blocks(N), EW_THREADS, 0, st>>>(s[is], hs[is], dte, kcoef, sh, prm.scal_limit,
                                                                   prm.scal_min[is], prm.scal_max[is], N);
+            if (lazy) pending[3 + is] = kcoef;
+        }
         launches += 3 + ns;
         return cuda_check(cudaGetLastError(), "rk update");
     }
@@ -517,6 +544,7 @@ struct Dns {
             ProfScope ps(PC_ELEMENTWISE);
             for (double* h : hq) cudaMemsetAsync(h, 0, (size_t)N * sizeof(double), st);
             for (double* h : hs) cudaMemsetAsync(h, 0, (size_t)N * sizeof(double), st);
+            for (double& k : pending) k = 1.0;
         }
         const double dte = dtime * kdt[sub];
         const bool last = (sub == nsub - 1);
@@ -628,6 +656,7 @@ int tlab_dns_destroy(tlab_dns_t h) {
 
 int tlab_dns_field(tlab_dns_t h, const char* name, double** dev_ptr) {
     if (!h || !dev_ptr) return fail(TLAB_ERR_OPTION, "tlab_dns_field: null argument");
+    h->d.flush_pending();       // the caller may read or write hq / hs through the pointer
     double* p = field_ptr(h->d, name);
     if (!p) return fail(TLAB_ERR_OPTION, std::string("tlab_dns_field: unknown field ") + (name ? name : "(null)"));
     *dev_ptr = p;
@@ -636,6 +665,7 @@ int tlab_dns_field(tlab_dns_t h, const char* name, double** dev_ptr) {
 
 int tlab_dns_upload_host(tlab_dns_t h, const char* name, const double* src_host) {
     if (!h || !src_host) return fail(TLAB_ERR_OPTION, "tlab_dns_upload_host: null argument");
+    h->d.flush_pending();
     double* p = field_ptr(h->d, name);
     if (!p) return fail(TLAB_ERR_OPTION, "tlab_dns_upload_host: unknown field");
     return tlab_gpu_upload(p, src_host, (size_t)h->d.N * sizeof(double));
@@ -643,6 +673,7 @@ int tlab_dns_upload_host(tlab_dns_t h, const char* name, const double* src_host)
 
 int tlab_dns_download_host(tlab_dns_t h, const char* name, double* dst_host) {
     if (!h || !dst_host) return fail(TLAB_ERR_OPTION, "tlab_dns_download_host: null argument");
+    h->d.flush_pending();
     double* p = field_ptr(h->d, name);
     if (!p) return fail(TLAB_ERR_OPTION, "tlab_dns_download_host: unknown field");
     return tlab_gpu_download(dst_host, p, (size_t)h->d.N * sizeof(double));

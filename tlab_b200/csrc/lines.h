@@ -12,6 +12,7 @@ struct LineArgs {
     int xstride = 0;                  // shared-memory line stride (contiguous-line kernel)
     int accumulate = 0;               // +1: out1 += result, -1: out1 -= result, 0: out1 = result
     double scale = 0.0;               // input is u + scale * u2 when u2 != nullptr
+    double acc_scale = 1.0;           // accumulate != 0: out1 = acc_scale * out1 +|- result (the pending `hq = hq*kco` of the RK scheme)
     long long nlines = 0;
     long long stride = 1;             // distance between consecutive points of a line
     long long inner = 1;              // line index -> offset: (line / inner) * outer_stride + line % inner

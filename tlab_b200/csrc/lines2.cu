@@ -897,7 +897,8 @@ __device__ __forceinline__ void contig_field(const Line2Args& a, const ChunkCtx&
         if (has_acc) {
 #pragma unroll
             for (int k = 0; k < 8; k++) {
-                const double2 o = acc[k];
+                double2 o = acc[k];
+                if (a.acc_scale != 1.0) { o.x = DMUL(a.acc_scale, o.x); o.y = DMUL(a.acc_scale, o.y); }   // hq = hq*kco, then the sum
                 if (a.accumulate > 0) { v[k].x = o.x + v[k].x; v[k].y = o.y + v[k].y; }
                 else { v[k].x = o.x - v[k].x; v[k].y = o.y - v[k].y; }
             }

@@ -18,9 +18,11 @@ struct Line2Args {
     int tma_rb = 0;                   // rows per TMA box
     int march = 0;                    // strided kernel: marching panels of 32 lines (march.cu)
     int march_cfg = 4;                // marching kernel: resident CTAs per SM it is compiled for (+10: velocity requested before the barriers)
+    int march_pf = 0;                 // marching kernel: L2 prefetch of the finishing stage's operands at the start of a step
     int march_red = 0;                // marching kernel: accumulate with red.global.add.f64 instead of load + store
     int tma_l2 = 0;                   // L2 promotion of the tensor maps (0 none, 1/2/3: 64/128/256 bytes)
     double scale = 0.0;               // input is u + scale * u2 when u2 != nullptr
+    double acc_scale = 1.0;           // contiguous kernel: out1 = acc_scale * out1 +|- result (explicitly rounded product first)
     long long stride = 1;             // distance between consecutive points of a line (strided kernel)
     long long inner = 1;              // tile (bx, by) starts at by * outer_stride + bx * L; lines by * inner + bx * L + l
     long long outer_stride = 0;

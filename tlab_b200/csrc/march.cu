@@ -188,6 +188,18 @@ __global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_const
         const int h = s & 1;
         const int t = rf * MW + w, tb = rb * MW + w;
         double ye1 = 0.0, ye2 = 0.0, pt1 = 0.0, pt2 = 0.0, x01 = 0.0, x02 = 0.0;
+        const long long boff = base + (long long)(tb * C) * st;
+        if (a.march_pf && back) {
+            // what the finishing stage of this step will read (velocity, accumulation target) goes to L2 while the new round is swept
+            const double* pv = a.vel + boff;
+            const double* pa = a.out1 + boff;
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                if (TWO) prefetch_l2(pv);
+                if (a.accumulate != 0) prefetch_l2(pa);
+                pv += st; pa += st;
+            }
+        }
         if (front) {
             double u[C + 6], f1[C], f2[C];
             march_load<PER>(u, pu, pu2, a.scale, t, T, n, st);
@@ -220,7 +232,6 @@ __global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_const
         }
         // the advecting velocity of the chunk being finished: in flight across the two barriers
         double vv[C];
-        const long long boff = base + (long long)(tb * C) * st;
         if (TWO && back && VPRE) {
             const double* vp = a.vel + boff;
 #pragma unroll
