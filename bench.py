@@ -589,8 +589,13 @@ def run_gpu(args):
             sim4, g4, grids4, kmax4, koff4 = make_sim(GD, opr, mpi, cx, cy, cz, world, rank)
             fill_fields(torch, tl, L, sim4, dev, grids4, kmax4, koff4)
             k4 = min(args.steps, 5)
+            tl.check(L.tlab_gpu_profile(1))
             ms4 = time_substeps(torch, dist, tl, L, sim4, stream, dev, world, k4, 3)
-            c4 = {"workload": "2048x1024x2048 (BASELINE configs[3]), z-slabs x8", "ms_per_step": ms4, "steps": k4, "warmup": 3,
+            m4, n4 = (ctypes.c_double * 11)(), (ctypes.c_int * 11)()
+            tl.check(L.tlab_gpu_profile_report(m4, n4, 11))
+            tl.check(L.tlab_gpu_profile(0))
+            c4 = {"breakdown_ms": {n_: m4[i] / (k4 + 3) for i, n_ in enumerate(cls_names) if n4[i] > 0},
+                  "workload": "2048x1024x2048 (BASELINE configs[3]), z-slabs x8", "ms_per_step": ms4, "steps": k4, "warmup": 3,
                   "value": cx * cy * cz / (ms4 * 1e-3) / 1e9, "unit": "Gpts/s", "points_per_gpu": cx * cy * kmax4,
                   "roofline_substep_frac": ALG_BYTES_PER_PT_SUBSTEP * cx * cy * kmax4 / (ms4 * 1e-3) / 1e9 / peak,
                   "note": "weak-scaled against C3 on one GPU (same 2^29 points per GPU): efficiency = value / (8 x the N=1 value of "
