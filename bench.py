@@ -125,43 +125,63 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_port_worker(args):
-    """One process = one host core running the oracle RK step on the sample grid."""
-    nx, ny, nz, nsteps, seed = args
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    from oracle import fdm, dns as OD
+# CPU legs.  The reference cannot be built here (Fortran 2008 + FFTW3, no Fortran compiler in the image), so the CPU arm is
+# the C++17/OpenMP restatement of its algorithm (oracle/cpp/tlab_cpu.cpp, checked against the numpy oracle, kind "port"),
+# on all host cores, on a bounded sample of the bench workload: a slab of the C3 grid with the full x and y extents
+# (1024 x 512 points per plane, the same line lengths, schemes, boundary conditions and physics) and CPU_SAMPLE_NZ planes.
+CPU_SAMPLE_NZ = 128
+
+
+def cpu_leg(nx, ny, nz, warm, steps):
+    """Runs in a process of its own (clean OpenMP environment): W + K substeps of the sample, each one timed."""
+    from oracle import fdm, dns as OD, cpu_baseline as CB
+    t0 = time.perf_counter()
     x, z, y = grid_periodic(nx), grid_periodic(nz), grid_tanh(ny)
     g = [fdm.Plan(x, True, True, name="x"), fdm.Plan(y, False, False, name="y"), fdm.Plan(z, True, True, name="z")]
     D, Nn = OD.DNS_BCS_DIRICHLET, OD.DNS_BCS_NEUMANN
-    o = OD.Dns(g, visc=PHYS["visc"], schmidt=PHYS["schmidt"], buoyancy_type="linear", buoyancy_params=(1.0, 0.0),
-               buoyancy_vector=(0.0, 1.0, 0.0), bcs_flow_jmin=(D, D, D), bcs_flow_jmax=(Nn, D, Nn),
-               bcs_scal_jmin=(D,), bcs_scal_jmax=(Nn,))
-    rng = np.random.default_rng(seed)
-    Z, Y, X = np.meshgrid(z, y, x, indexing="ij")
+    c = CB.CpuDns(g, visc=PHYS["visc"], schmidt=PHYS["schmidt"], buoyancy_type="linear", buoyancy_params=(1.0, 0.0),
+                  buoyancy_vector=(0.0, 1.0, 0.0), bcs_flow_jmin=(D, D, D), bcs_flow_jmax=(Nn, D, Nn), bcs_scal_jmin=(D,),
+                  bcs_scal_jmax=(Nn,))
+    init_s = time.perf_counter() - t0
+    Z, Y, X = np.meshgrid(z, y / y[-1], x, indexing="ij", sparse=True)
     wall = np.sin(0.5 * np.pi * Y)
+    rng = np.random.default_rng(20261017)
     for i in range(3):
-        o.q[i][...] = 0.3 * np.sin(rng.integers(1, 5) * X + rng.integers(1, 5) * Z + rng.uniform(0, 6.28)) * wall
-    o.s[0][...] = 0.5 + 0.2 * np.sin(X + 2 * Z) * wall
-    o.runge_kutta(PHYS["dtime"])                    # warm-up step (plans, caches)
-    t0 = time.perf_counter()
-    for _ in range(nsteps):
-        o.runge_kutta(PHYS["dtime"])
-    dt = time.perf_counter() - t0
-    return dt / (nsteps * o.rkm_endstep)            # seconds per substep on this core
+        c.q[i][...] = 0.05 * np.sin(rng.integers(1, 5) * X + rng.integers(1, 5) * Z + rng.uniform(0, 6.28)) * wall
+    c.s[0][...] = 0.5 + 0.05 * np.sin(X + 2 * Z) * wall
+    kdt, _, kco = OD.rk_coefficients(OD.RKM_EXP4)
+    times = []
+    for i in range(warm + steps):
+        sub = i % 5
+        if sub == 0:
+            for a in c.hq + c.hs:
+                a[...] = 0.0
+        t1 = time.perf_counter()
+        c.substep(PHYS["dtime"] * kdt[sub], kco[sub] if sub < 4 else None)
+        times.append(time.perf_counter() - t1)
+    ok = bool(np.isfinite(c.q[0]).all() and np.isfinite(c.s[0]).all())
+    print(json.dumps({"cpu_leg": True, "seconds": times, "init_s": init_s, "threads": c.threads, "finite": ok,
+                      "grid": [nx, ny, nz]}))
 
 
-def cpu_port_rate(sample=(128, 64, 128), rk_steps=1, cores=None):
-    """Aggregate Gpts/s per substep of `cores` independent oracle instances (no communication cost charged)."""
-    import multiprocessing as mp
-    cores = cores or max(1, (os.cpu_count() or 1))
-    cores = min(cores, 64)
-    nx, ny, nz = sample
-    ctx = mp.get_context("spawn")
-    with ctx.Pool(cores) as pool:
-        secs = pool.map(cpu_port_worker, [(nx, ny, nz, rk_steps, 100 + i) for i in range(cores)])
-    pts = nx * ny * nz
-    rate = sum(pts / s for s in secs) / 1e9
-    return rate, cores, "%d independent %dx%dx%d oracle instances, %d RK step(s) each" % (cores, nx, ny, nz, rk_steps)
+def run_cpu_leg(nx, ny, nz, warm, steps):
+    """-> (seconds per substep of the sample [list of the timed ones], threads, description)"""
+    import subprocess
+    env = dict(os.environ)
+    env.pop("OMP_NUM_THREADS", None)            # torchrun pins it to 1; the baseline is meant to use every core
+    env["OMP_PROC_BIND"] = "false"
+    r = subprocess.run([sys.executable, os.path.abspath(__file__), "--cpu-leg", "%d,%d,%d,%d,%d" % (nx, ny, nz, warm, steps)],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=900)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{") and "cpu_leg" in l]
+    if r.returncode != 0 or not lines:
+        raise RuntimeError("cpu leg failed: " + r.stderr[-800:])
+    d = json.loads(lines[-1])
+    if not d["finite"]:
+        raise RuntimeError("cpu leg produced non-finite fields")
+    desc = ("%dx%dx%d slab of the %s grid (full x and y lines, %d of its z planes), %d warm-up + %d timed RK4-5 substeps, "
+            "C++17/OpenMP restatement oracle/cpp/tlab_cpu.cpp, tables initialised in %.0f s (untimed)"
+            % (nx, ny, nz, "1024x512x1024", nz, warm, steps, d["init_s"]))
+    return d["seconds"][warm:], d["threads"], desc
 
 
 def run_reference(args):
@@ -169,26 +189,20 @@ def run_reference(args):
     if rank != 0:
         return
     nx, ny, nz = WORKLOADS[args.workload]
-    sample = (128, 64, 128)
-    per_step = []
-    cores = None
-    desc = ""
-    total = args.warmup + args.steps
-    # each "step" of this arm is one bounded sample (one RK step of every instance = 5 substeps per core)
-    for i in range(min(total, 3)):
-        t0 = time.perf_counter()
-        rate, cores, desc = cpu_port_rate(sample, 1, None)
-        per_step.append((rate, time.perf_counter() - t0))
-    rates = [r for r, _ in per_step[min(args.warmup, len(per_step) - 1):]]
-    value = float(np.median(rates))
+    snz = min(CPU_SAMPLE_NZ, nz)
+    secs, threads, desc = run_cpu_leg(nx, ny, snz, args.warmup, args.steps)
+    sec = float(np.mean(secs))
+    value = nx * ny * snz / sec / 1e9
     out = {"impl": "reference", "metric": "rk_substep_throughput", "value": value, "unit": "Gpts/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * nx * ny * nz / (value * 1e9),
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sec,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": "incompressible Boussinesq CBL %dx%dx%d, RK4-5 substep, 1 scalar, CompactJacobian6 + "
                                   "CompactJacobian6Hyper, tanh-stretched y" % (nx, ny, nz),
-                      "note": "CPU restatement of the reference algorithm (no Fortran compiler in the image); "
-                              "rate measured on a bounded sample and quoted per point"},
-           "cpu_baseline": {"value": value, "unit": "Gpts/s", "cores": cores, "kind": "port", "sample": desc},
+                      "sample": "each step = one substep of a %dx%dx%d slab of that grid (ms_per_step is the measured time of "
+                                "such a step; value = its points / that time)" % (nx, ny, snz),
+                      "note": "CPU restatement of the reference algorithm in C++/OpenMP on all host cores (the image has no "
+                              "Fortran compiler and no FFTW: the reference itself cannot be built)"},
+           "cpu_baseline": {"value": value, "unit": "Gpts/s", "cores": threads, "kind": "port", "sample": desc},
            "e2e": {"value": value, "unit": "Gpts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
@@ -247,20 +261,20 @@ def fill_fields(torch, tl, L, sim, dev, grids, kmax, koff):
 
 def parity_block(torch, dist, tl, L, opr, GD, mpi, dev, world, rank):
     """Correctness record of the multi-GPU paths, taken before anything is timed: one RK step of a small split-eligible grid
-    (32 x 32 x 96 P, slabs of 6 chunks) on the P ranks against the single-domain oracle on rank 0 -- once with the default path
+    (32 x 32 x 128 P: slabs of 8 chunks, the thinnest the marching split-z kernels take) on the P ranks against the single-domain oracle on rank 0 -- once with the default path
     (split-z operators over peer memory + kx-split Poisson stage) and once with splitz = 0 (K-transposes for every z operator).
     The oracle is the checker here, never the thing measured."""
     import ctypes
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from common import smooth_field, rel_l2
-    nx, ny, nz = 32, 32, 96 * world
+    nx, ny, nz = 32, 32, 128 * world
     out = {"grid": [nx, ny, nz], "paths": {}}
     ref = None
     for label, tune in (("default", None), ("splitz=0", ("splitz", 0))):
         if tune:
             tl.check(L.tlab_gpu_set_tuning(tune[0].encode(), tune[1]))
         cnt0 = {}
-        for key in ("p2p_exchanges", "nccl_exchanges", "splitz_ops"):
+        for key in ("p2p_exchanges", "nccl_exchanges", "splitz_ops", "splitz_march_ops"):
             c = ctypes.c_longlong()
             tl.check(L.tlab_gpu_get_counter(key.encode(), ctypes.byref(c)))
             cnt0[key] = c.value
@@ -569,8 +583,14 @@ def run_gpu(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        rate, cores, desc = cpu_port_rate((128, 64, 128), 1, None)
-        cpu = {"value": rate, "unit": "Gpts/s", "cores": cores, "kind": "port", "sample": desc}
+        try:
+            snz = min(CPU_SAMPLE_NZ, nz)
+            secs, cores, desc = run_cpu_leg(nx, ny, snz, 1, 5)
+            sec = float(np.mean(secs))
+            cpu = {"value": nx * ny * snz / sec / 1e9, "unit": "Gpts/s", "cores": cores, "kind": "port", "sample": desc,
+                   "seconds_per_sample_substep": sec}
+        except Exception as ex:
+            cpu = {"value": None, "unit": "Gpts/s", "cores": None, "kind": "port", "sample": "failed: %s" % str(ex)[:300]}
 
     zc = ctypes.c_longlong(0)
     tl.check(L.tlab_gpu_get_counter(b"splitz_ops", ctypes.byref(zc)))
@@ -644,11 +664,15 @@ def main():
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--nz", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-leg", default="", help=argparse.SUPPRESS)     # internal: nx,ny,nz,warm,steps of the CPU sample
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the oracle parity record taken before the timed region")
     ap.add_argument("--no-c4", action="store_true", help="N = 8: skip the additional 2048x1024x2048 timing")
     ap.add_argument("--no-extra", action="store_true", help="N = 1: skip the OPR_Partial 512^3 and OPR_Poisson sweep records")
     ap.add_argument("--tune", default="", help="library tuning knobs, e.g. fuse=0,pf_next=1 (tlab_gpu_set_tuning)")
     args = ap.parse_args()
+    if args.cpu_leg:
+        cpu_leg(*[int(v) for v in args.cpu_leg.split(",")])
+        return
     if args.warmup < 3:
         args.warmup = 3
     if args.impl == "reference":

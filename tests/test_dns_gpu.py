@@ -206,11 +206,15 @@ def test_step_through_the_tma_kernels(cuda, shape, lines):
     assert rel_l2(g.get("s1"), o.s[0]) <= 1e-11
 
 
-@pytest.mark.parametrize("shape,pv", [((32, 32, 256), 2), ((16, 32, 192), 2), ((16, 32, 512), 4), ((64, 16, 384), 3)])
-def test_split_z_operators_on_virtual_slabs(cuda, shape, pv):
+@pytest.mark.parametrize("march", [1, 0])
+@pytest.mark.parametrize("shape,pv", [((32, 32, 256), 2), ((16, 32, 192), 2), ((16, 32, 512), 4), ((64, 16, 384), 3),
+                                      ((32, 16, 512), 2), ((32, 32, 768), 3)])
+def test_split_z_operators_on_virtual_slabs(cuda, shape, pv, march):
     """The split-z kernels of splitz.cu (z operators of a z-split domain without transposes: halo planes and chunk ends
     exchanged between neighbouring slabs) run over pv virtual slabs of one field on one GPU: the RK step must agree with
-    the oracle, and with the whole-line kernels to round-off.  Slab thicknesses 128 / 96 (the minimum: 6 chunks) planes."""
+    the oracle, and with the whole-line kernels to round-off.  Slab thicknesses 96 (the minimum: 6 chunks) to 256 planes; with
+    march = 1 the finishing phase runs as a march over panels of 32 lines (splitz_march_kernel) when the slab holds a multiple
+    of 4 chunks, seeded from the neighbours' chunk ends."""
     import ctypes
     from tlab_b200 import lib as tl
     L = tl.load()
@@ -218,17 +222,24 @@ def test_split_z_operators_on_virtual_slabs(cuda, shape, pv):
     o.runge_kutta(1e-3)
     g.runge_kutta(1e-3)
     whole = [g.get("q%d" % (i + 1)) for i in range(3)] + [g.get("s1")]
-    before = ctypes.c_longlong(0)
+    before, mbefore = ctypes.c_longlong(0), ctypes.c_longlong(0)
     tl.check(L.tlab_gpu_get_counter(b"splitz_ops", ctypes.byref(before)))
+    tl.check(L.tlab_gpu_get_counter(b"splitz_march_ops", ctypes.byref(mbefore)))
     try:
         tl.check(L.tlab_gpu_set_tuning(b"split_emulate", pv))
+        tl.check(L.tlab_gpu_set_tuning(b"march", march))
         _, g2 = _pair(*shape, "tanh")
         g2.runge_kutta(1e-3)
     finally:
         tl.check(L.tlab_gpu_set_tuning(b"split_emulate", 0))
-    after = ctypes.c_longlong(0)
+        tl.check(L.tlab_gpu_set_tuning(b"march", 1))
+    after, mafter = ctypes.c_longlong(0), ctypes.c_longlong(0)
     tl.check(L.tlab_gpu_get_counter(b"splitz_ops", ctypes.byref(after)))
+    tl.check(L.tlab_gpu_get_counter(b"splitz_march_ops", ctypes.byref(mafter)))
     assert after.value - before.value == 5 * 6, "the split-z kernels did not run"
+    chunks = shape[2] // pv // 16
+    eligible = march == 1 and chunks % 4 == 0 and chunks >= 8 and (shape[0] * shape[1]) % 32 == 0
+    assert mafter.value - mbefore.value == (5 * 6 * pv if eligible else 0), (mafter.value - mbefore.value, eligible)
     split = [g2.get("q%d" % (i + 1)) for i in range(3)] + [g2.get("s1")]
     ref = o.q + o.s
     for a, b, c in zip(split, whole, ref):

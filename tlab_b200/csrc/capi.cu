@@ -482,6 +482,7 @@ int tlab_gpu_get_counter(const char* key, long long* value) {
     else if (!std::strcmp(key, "tma_launches")) *value = lines2_tma_launches();
     else if (!std::strcmp(key, "march_launches")) *value = ctx().march_launches;
     else if (!std::strcmp(key, "splitz_ops")) *value = splitz().ops;
+    else if (!std::strcmp(key, "splitz_march_ops")) *value = splitz().march_ops;
     else if (!std::strcmp(key, "p2p_exchanges")) *value = trp().p2p_exchanges;
     else if (!std::strcmp(key, "nccl_exchanges")) *value = trp().nccl_exchanges;
     else return fail(TLAB_ERR_OPTION, std::string("unknown counter ") + key);

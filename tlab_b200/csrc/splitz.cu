@@ -24,7 +24,7 @@
 // next call while a neighbour still reads the previous one.
 #include "../../include/tlab_gpu.h"
 #include "splitz.h"
-#include "lines2_dev.cuh"
+#include "march_dev.cuh"
 #include "trp.h"
 #include <algorithm>
 
@@ -289,6 +289,303 @@ cudaError_t launch_split(int phase, const SplitArgs& a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------
+// PHASE 2 as a march (march.cu): a CTA of MW warps owns a panel of 32 lines of the slab and walks along z in rounds of MW
+// chunks; the corrections of a round are applied one round later from a thread-private stash.  What a whole-line march
+// gets from its own rounds comes from the neighbours here: the ring is seeded with the forward ends of the previous rank's
+// last LBM chunks, the chunk starts beyond the slab are built from the next rank's first chunks, and the two ends of the
+// circulant line trade their closure terms (all of it left in this rank's exchange block by PHASE 1 of the ranks
+// concerned).  No rotation of the rounds is needed: the other end of the line is not ours to wait for.
+// 256-byte rows whatever the slab thickness, four CTAs per SM in different phases: the finishing stage reads the
+// field once, against the whole-slab kernel above that holds the slab line in one CTA (and is bound by its latency).
+__host__ __device__ inline long long e_next(int t, int s, int c) { return (long long)OFF_ENEXT + (long long)(t * 2 + s) * 3 + c; }
+__host__ __device__ inline long long e_prev(int t, int s) { return (long long)OFF_EPREV + (long long)(t * 2 + s); }
+__host__ __device__ inline long long e_tail(int ti, int s, int c) { return (long long)OFF_TAIL + (long long)(ti * 2 + s) * 2 + c; }
+
+template <int MODE>
+__global__ void __launch_bounds__(MW * ML, 4) splitz_march_kernel(const __grid_constant__ SplitArgs a) {
+    constexpr bool TWO = (MODE == MODE_BURGERS);
+    constexpr int NS = TWO ? 2 : 1;
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int Tl = a.Tl, T = a.T, t0 = a.t0, R = Tl / MW;
+    const long long nxy = a.nxy;
+    const long long line = (long long)blockIdx.x * ML + lane;
+    const bool first = (t0 == 0), last = (t0 + Tl == T);
+    const Sys2& S1 = a.s1;
+    const Sys2& S2 = a.s2;
+    const MarchSm m1(sm), m2(sm + M_SYS);
+    for (int i = threadIdx.x; i < NS * M_SYS; i += blockDim.x) sm[i] = 0.0;
+    __syncthreads();
+    const double* __restrict__ mine = a.mine + line;
+    // ---- seeds: forward ends of the previous rank's last LBM chunks -> "previous round" half of the ring (half 1 for step 0)
+    if (w < LBM) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const MarchSm& m = s ? m2 : m1;
+            m.Y[(MW + MW - LBM + w) * ML + lane] = mine[e_prev(LB2 - LBM + w, s) * nxy];
+        }
+    }
+    // ---- closure terms of the other end of the line (lines2.cu: x_N = sum over the first K0 and the last K1 chunks)
+    if (w == 3) {
+#pragma unroll
+        for (int s = 0; s < NS; s++) {
+            const Sys2& S = s ? S2 : S1;
+            const MarchSm& m = s ? m2 : m1;
+            if (first) {
+                for (int k = 0; k < S.K1m; k++) {
+                    const int kk = T - S.K1m + k, ti = kk - (T - TAILC);
+                    const double* cr = S.crec + (size_t)kk * 16;
+                    double A = __ldg(cr + 0) * mine[e_tail(ti - 1, s, 0) * nxy];
+                    A = fma(__ldg(cr + 1), mine[e_tail(ti - 2, s, 0) * nxy], A);
+                    A = fma(__ldg(cr + 2), mine[e_tail(ti - 3, s, 0) * nxy], A);
+                    m.Wc[(MW + k) * ML + lane] = fma(__ldg(cr + 13), A, mine[e_tail(ti, s, 1) * nxy]);
+                }
+            }
+            if (last) {
+                // the next rank is the first one: its chunks 0 .. K0-1 open the line (no inflow before chunk 0: weights vanish)
+                for (int k = 0; k < S.K0m; k++) {
+                    const double* cr = S.crec + (size_t)k * 16;
+                    double A = 0.0;
+                    if (k >= 1) A = __ldg(cr + 0) * mine[e_next(k - 1, s, 0) * nxy];
+                    if (k >= 2) A = fma(__ldg(cr + 1), mine[e_next(k - 2, s, 0) * nxy], A);
+                    if (k >= 3) A = fma(__ldg(cr + 2), mine[e_next(k - 3, s, 0) * nxy], A);
+                    m.Wc[k * ML + lane] = fma(__ldg(cr + 13), A, mine[e_next(k, s, 2) * nxy]);
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    const double* __restrict__ pu = a.u + line;
+    const double* __restrict__ pu2 = (a.u2 != nullptr) ? a.u2 + line : nullptr;
+    const int slot = w * ML + lane;
+    double o1[C], o2[C];
+    double A1p = 0.0, A2p = 0.0;
+    for (int s = 0; s <= R; s++) {
+        const bool front = s < R, back = s > 0;
+        const int h = s & 1;
+        const int t = s * MW + w, tb = (s - 1) * MW + w;
+        const int tg = t0 + t, tbg = t0 + tb;
+        double ye1 = 0.0, ye2 = 0.0, pt1 = 0.0, pt2 = 0.0, x01 = 0.0, x02 = 0.0;
+        if (front) {
+            double u[C + 6], f1[C], f2[C];
+            {
+                // chunk + halos: from the slab, or from the planes the neighbours pushed
+                const double* q = pu + (long long)(t * C) * nxy;
+                const double* ql = (t > 0) ? q - 3 * nxy : mine + (long long)OFF_HLO * nxy;
+                const double* qr = (t < Tl - 1) ? q + (long long)C * nxy : mine + (long long)OFF_HHI * nxy;
+#pragma unroll
+                for (int j = 0; j < C; j++) { u[j + 3] = __ldcs(q); q += nxy; }
+#pragma unroll
+                for (int k = 0; k < 3; k++) { u[k] = __ldcs(ql); u[C + 3 + k] = __ldcs(qr); ql += nxy; qr += nxy; }
+                if (pu2 != nullptr) {
+                    // (the pushed halo planes already hold u + scale*u2)
+                    const double* p2 = pu2 + (long long)(t * C) * nxy;
+                    const double* pl = p2 - 3 * nxy;
+                    const double* pr = p2 + (long long)C * nxy;
+#pragma unroll
+                    for (int j = 0; j < C; j++) { u[j + 3] = fma(__ldcs(p2), a.scale, u[j + 3]); p2 += nxy; }
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        if (t > 0) u[k] = fma(__ldcs(pl), a.scale, u[k]);
+                        if (t < Tl - 1) u[C + 3 + k] = fma(__ldcs(pr), a.scale, u[C + 3 + k]);
+                        pl += nxy; pr += nxy;
+                    }
+                }
+            }
+            rhs_interior<false>(u, f1, a.rhs1);
+            if (TWO) rhs_interior<true>(u, f2, a.rhs2);
+            march_local<true>(f1, S1, tg, ye1, pt1);
+            if (TWO) march_local<true>(f2, S2, tg, ye2, pt2);
+            x01 = f1[0];
+            if (TWO) x02 = f2[0];
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                double* q = m1.X + j * (MW * ML) + slot;
+                o1[j] = *q;
+                *q = f1[j];
+                if (TWO) {
+                    double* q2 = m2.X + j * (MW * ML) + slot;
+                    o2[j] = *q2;
+                    *q2 = f2[j];
+                }
+            }
+            m1.Y[(h * MW) * ML + slot] = ye1;
+            if (TWO) m2.Y[(h * MW) * ML + slot] = ye2;
+        } else {
+#pragma unroll
+            for (int j = 0; j < C; j++) {
+                o1[j] = m1.X[j * (MW * ML) + slot];
+                if (TWO) o2[j] = m2.X[j * (MW * ML) + slot];
+            }
+        }
+        __syncthreads();
+        double A1 = 0.0, A2 = 0.0;
+        if (front) {
+#pragma unroll
+            for (int q = 0; q < NS; q++) {
+                const Sys2& S = q ? S2 : S1;
+                const MarchSm& m = q ? m2 : m1;
+                const double* cr = S.crec + (size_t)tg * 16;
+                const double A = march_look_back(m.Y, cr, h, w, lane);
+                m.Z[(h * MW) * ML + slot] = fma(__ldg(cr + 12), A, q ? x02 : x01);
+                if (tg < S.K0m) m.Wc[tg * ML + lane] = fma(__ldg(cr + 13), A, q ? pt2 : pt1);
+                if (tg >= T - S.K1m) m.Wc[(MW + tg - (T - S.K1m)) * ML + lane] = fma(__ldg(cr + 13), A, q ? pt2 : pt1);
+                if (q) A2 = A; else A1 = A;
+            }
+            if (s == R - 1 && w < LBM) {
+                // chunk starts beyond the slab (the next rank's chunks 0 .. LBM-1): z = Q0 A + x^_0 with A from the ends before them,
+                // this rank's last chunks (ring) and the next rank's first ones (exchange block)
+                const int tgn = t0 + Tl + w;
+#pragma unroll
+                for (int q = 0; q < NS; q++) {
+                    const Sys2& S = q ? S2 : S1;
+                    const MarchSm& m = q ? m2 : m1;
+                    double z = 0.0;
+                    if (tgn < T) {
+                        const double* cr = S.crec + (size_t)tgn * 16;
+                        auto yof = [&](int k) {            // forward end of slab chunk Tl + w - k
+                            const int j = w - k;           // >= 0: the next rank's chunk j; < 0: this rank's chunk Tl + j (last round, half h)
+                            return (j >= 0) ? mine[e_next(j, q, 0) * nxy] : m.Y[(h * MW + MW + j) * ML + lane];
+                        };
+                        double A = __ldg(cr + 0) * yof(1);
+                        A = fma(__ldg(cr + 1), yof(2), A);
+                        A = fma(__ldg(cr + 2), yof(3), A);
+                        z = fma(__ldg(cr + 12), A, mine[e_next(w, q, 1) * nxy]);
+                    }
+                    m.Zk[w * ML + lane] = z;
+                }
+            }
+        }
+        __syncthreads();
+        if (back) {
+            double vv[C];
+            const long long boff = line + (long long)(tb * C) * nxy;
+            if (TWO) {
+                const double* vp = a.vel + boff;
+#pragma unroll
+                for (int j = 0; j < C; j++) { vv[j] = __ldcs(vp); vp += nxy; }
+            }
+            const bool endr = (s == R);
+            const double B1 = march_look_ahead(m1.Z + ((h ^ 1) * MW) * ML, endr ? m1.Zk : m1.Z + (h * MW) * ML,
+                                               S1.crec + (size_t)tbg * 16, w, lane);
+            march_finish<true>(o1, S1, m1, tbg, T, A1p, B1, lane);
+            if (TWO) {
+                const double B2 = march_look_ahead(m2.Z + ((h ^ 1) * MW) * ML, endr ? m2.Zk : m2.Z + (h * MW) * ML,
+                                                   S2.crec + (size_t)tbg * 16, w, lane);
+                march_finish<true>(o2, S2, m2, tbg, T, A2p, B2, lane);
+#pragma unroll
+                for (int j = 0; j < C; j++) o1[j] = o2[j] - vv[j] * o1[j];
+            }
+            double* po = a.out + boff;
+            if (a.accumulate == 0) {
+#pragma unroll
+                for (int j = 0; j < C; j++) { __stcs(po, o1[j]); po += nxy; }
+            } else {
+                double oo[C];
+                const double* pi = po;
+#pragma unroll
+                for (int j = 0; j < C; j++) { oo[j] = __ldcs(pi); pi += nxy; }
+#pragma unroll
+                for (int j = 0; j < C; j++) { __stcs(po, (a.accumulate > 0) ? oo[j] + o1[j] : oo[j] - o1[j]); po += nxy; }
+            }
+        }
+        A1p = A1;
+        A2p = A2;
+    }
+}
+
+// PHASE 1 for the march: only the chunks whose ends somebody reads -- the first MW of the slab (chunk starts and closure terms
+// for the previous rank), the last LBM (forward ends for the next rank) and, on the last rank, the last LBM + MW (closure terms
+// for the first rank) -- in the geometry of the march (lane = line, warp = chunk): a fraction (MW + LBM) / Tl of the field is
+// read instead of all of it.
+template <int MODE>
+__global__ void __launch_bounds__(MW * ML, 4) splitz_ends_kernel(const __grid_constant__ SplitArgs a, int nfirst, int nlist) {
+    constexpr bool TWO = (MODE == MODE_BURGERS);
+    constexpr int NS = TWO ? 2 : 1;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int e = blockIdx.y * MW + w;
+    if (e >= nlist) return;
+    const int Tl = a.Tl, T = a.T;
+    const int t = (e < nfirst) ? e : Tl - (nlist - e);
+    const int tg = a.t0 + t;
+    const long long nxy = a.nxy;
+    const long long line = (long long)blockIdx.x * ML + lane;
+    const double* __restrict__ mine = a.mine + line;
+    double u[C + 6];
+    {
+        const double* q = a.u + line + (long long)(t * C) * nxy;
+        const double* ql = (t > 0) ? q - 3 * nxy : mine + (long long)OFF_HLO * nxy;
+        const double* qr = (t < Tl - 1) ? q + (long long)C * nxy : mine + (long long)OFF_HHI * nxy;
+#pragma unroll
+        for (int j = 0; j < C; j++) { u[j + 3] = __ldcs(q); q += nxy; }
+#pragma unroll
+        for (int k = 0; k < 3; k++) { u[k] = __ldcs(ql); u[C + 3 + k] = __ldcs(qr); ql += nxy; qr += nxy; }
+        if (a.u2 != nullptr) {
+            const double* p2 = a.u2 + line + (long long)(t * C) * nxy;
+            const double* pl = p2 - 3 * nxy;
+            const double* pr = p2 + (long long)C * nxy;
+#pragma unroll
+            for (int j = 0; j < C; j++) { u[j + 3] = fma(__ldcs(p2), a.scale, u[j + 3]); p2 += nxy; }
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                if (t > 0) u[k] = fma(__ldcs(pl), a.scale, u[k]);
+                if (t < Tl - 1) u[C + 3 + k] = fma(__ldcs(pr), a.scale, u[C + 3 + k]);
+                pl += nxy; pr += nxy;
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; s++) {
+        const Sys2& S = s ? a.s2 : a.s1;
+        double f[C], yend, part;
+        if (s) rhs_interior<true>(u, f, a.rhs2);
+        else rhs_interior<false>(u, f, a.rhs1);
+        march_local<true>(f, S, tg, yend, part);
+        if (t < LB2) {
+            double* d = a.to_prev + e_next(t, s, 0) * nxy + line;
+            d[0] = yend; d[nxy] = f[0]; d[2 * nxy] = part;
+        }
+        if (t >= Tl - LB2) a.to_next[e_prev(t - (Tl - LB2), s) * nxy + line] = yend;
+        if (tg >= T - TAILC) {
+            double* d = a.to_first + e_tail(tg - (T - TAILC), s, 0) * nxy + line;
+            d[0] = yend; d[nxy] = part;
+        }
+    }
+}
+
+template <int MODE>
+cudaError_t launch_split_ends(const SplitArgs& a, cudaStream_t st) {
+    const bool last = (a.t0 + a.Tl == a.T);
+    int nfirst = MW, nlast = last ? LBM + MW : LBM;
+    int nlist = nfirst + nlast;
+    if (nlist >= a.Tl) { nfirst = a.Tl; nlist = a.Tl; }        // the two sets meet: every chunk once
+    const dim3 grid((unsigned)(a.nxy / ML), (unsigned)((nlist + MW - 1) / MW), 1);
+    splitz_ends_kernel<MODE><<<grid, MW * ML, 0, st>>>(a, nfirst, nlist);
+    return cudaGetLastError();
+}
+
+bool split_march_ok(const SplitArgs& a, int mode) {
+    if (a.Tl % MW != 0 || a.Tl < 2 * MW || a.nxy % ML != 0) return false;
+    if (!a.s1.march_ok || a.s1.K0m > MW || a.s1.K1m > MW) return false;
+    if (mode == MODE_BURGERS && (!a.s2.march_ok || a.s2.K0m > MW || a.s2.K1m > MW)) return false;
+    return true;
+}
+
+template <int MODE>
+cudaError_t launch_split_march(const SplitArgs& a, cudaStream_t st) {
+    const size_t smem = (size_t)((MODE == MODE_BURGERS) ? 2 : 1) * M_SYS * sizeof(double);
+    static bool set = false;
+    if (!set) {
+        cudaError_t e = cudaFuncSetAttribute(splitz_march_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        set = true;
+    }
+    splitz_march_kernel<MODE><<<(unsigned)(a.nxy / ML), MW * ML, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 int pick_L(int Tl, long long nxy) {
     int L = 32;
     while (L > 4 && (L * Tl > 512 || nxy % L != 0)) L >>= 1;
@@ -397,7 +694,17 @@ int run_split(SplitZ& z, int mode, tlab_plan_s* g, int is, const double* u, cons
             a.t0 = r * a.Tl;
             a.u = u + fo; a.u2 = u2 ? u2 + fo : nullptr; a.vel = vel ? vel + fo : nullptr; a.out = out + fo;
             a.mine = blk(r); a.to_prev = blk(prev); a.to_next = blk(next); a.to_first = blk(0);
-            cudaError_t e = (mode == MODE_BURGERS) ? launch_split<MODE_BURGERS>(phase, a, st) : launch_split<MODE_P1>(phase, a, st);
+            cudaError_t e;
+            if (ctx().tune_march && split_march_ok(a, mode)) {
+                if (phase == 1) {
+                    e = (mode == MODE_BURGERS) ? launch_split_ends<MODE_BURGERS>(a, st) : launch_split_ends<MODE_P1>(a, st);
+                } else {
+                    z.march_ops++;
+                    e = (mode == MODE_BURGERS) ? launch_split_march<MODE_BURGERS>(a, st) : launch_split_march<MODE_P1>(a, st);
+                }
+            } else {
+                e = (mode == MODE_BURGERS) ? launch_split<MODE_BURGERS>(phase, a, st) : launch_split<MODE_P1>(phase, a, st);
+            }
             if (e != cudaSuccess) return cuda_check(e, "split-z kernel");
         }
         if (phase == 1 && z.emulate <= 1) { if (int rc = trp().barrier()) return rc; }

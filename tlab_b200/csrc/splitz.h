@@ -15,6 +15,7 @@ struct SplitZ {
     bool ready = false;
     long long calls = 0;     // operator calls so far (parity of the exchange buffers)
     long long ops = 0;
+    long long march_ops = 0; // ... of which the finishing phase ran as a march (splitz_march_kernel)
     std::vector<double*> block[2];   // exchange buffers per parity: [0] of this rank (P > 1) or one per virtual rank
     int init(long long nxy, int kmax, int nzg, int P, int rank, int emulate);
     bool eligible(const tlab_plan_s* g, int is) const;      // is < 0: first derivative only
