@@ -9,7 +9,7 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("tune", ["", "p2p=0", "overlap=0,kxsplit=0", "p2p_dma=1"])
+@pytest.mark.parametrize("tune", ["", "p2p=0", "overlap=0,kxsplit=0", "p2p_dma=1", "pull_overlap=0"])
 def test_two_gpu_rk_steps(cuda, tune):
     """Two RK steps on 2 z slabs against the single-domain oracle: peer-memory transposes with overlapped z operators
     and the kx-split Poisson stage (default), the NCCL send/recv fallback, the plain schedule, the copy-engine variant."""
@@ -32,18 +32,20 @@ def test_two_gpu_rk_steps(cuda, tune):
     assert p2p + nccl > 0
 
 
-@pytest.mark.parametrize("shape", ["32,32,256", "16,32,192"])
-def test_two_gpu_split_z_operators(cuda, shape):
+@pytest.mark.parametrize("march", [1, 0])
+@pytest.mark.parametrize("shape", ["32,32,256", "16,32,192", "32,16,512"])
+def test_two_gpu_split_z_operators(cuda, shape, march):
     """Slabs thick enough for the split-z operators (>= 6 chunks of 16 planes): the z derivatives and Burgers operators
     run on the slabs with halo / chunk-end exchange through peer memory instead of transposes (splitz.cu); two RK steps
-    against the single-domain oracle, and the split kernels must actually have run (6 operators per substep)."""
+    against the single-domain oracle, and the split kernels must actually have run (6 operators per substep).  march = 1: slabs
+    of a multiple of 4 chunks (128 and 256 planes here) finish as a march seeded from the neighbours' chunk ends."""
     import re
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", "29519", os.path.join(ROOT, "tests", "dist_gpu_worker.py")]
-    env = dict(os.environ, TLAB_TUNE="splitz=1", TLAB_SHAPE=shape)
+    env = dict(os.environ, TLAB_TUNE="splitz=1,march=%d" % march, TLAB_SHAPE=shape)
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-3000:]
     assert "DIST_ERRS" in r.stdout

@@ -454,6 +454,7 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "split_emulate")) ctx().tune_split_emulate = value;
     else if (!std::strcmp(key, "pf_l1")) ctx().tune_pf_l1 = value;
     else if (!std::strcmp(key, "march")) ctx().tune_march = value;
+    else if (!std::strcmp(key, "pull_overlap")) ctx().tune_pull_overlap = value;
     else if (!std::strcmp(key, "lazy_scale")) ctx().tune_lazy_scale = value;
     else if (!std::strcmp(key, "march_red")) ctx().tune_march_red = value;
     else if (!std::strcmp(key, "march_cfg")) ctx().tune_march_cfg = value;

@@ -49,6 +49,7 @@ struct Context {
                               // rows of 32-128 bytes (profiles/ncu_full_tma_r01.json)
     int tune_lazy_scale = 1;  // RK substep: `hq = hq*kco` is not written by the update but folded into the first accumulation of the next
                               // substep (buoyancy source, OPR_Burgers_X): 8 B/pt less per field and substep, same bits
+    int tune_pull_overlap = 1; // kx-split Poisson stage: pulls of p^ and dp^/dy on a second stream, beside the inverse transforms
     int tune_march = 1;       // strided fast kernels: marching panels of 32 lines (march.cu) for OPR_Partial P1 and OPR_Burgers
     int tune_march_cfg = 4;   // marching kernels: CTAs per SM they are compiled for (3 / 4; +10: velocity requested before the barriers)
     int tune_march_pf = 0;

@@ -1448,6 +1448,54 @@ int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const do
             launch_modes(D, cpa, cpb, st);
             if (int rc = cuda_check(cudaGetLastError(), "poisson mode kernels")) return rc;
         }
+        if (ctx().tune_pull_overlap && T.zstream) {
+            // The way back on two streams: the pull of p^ (second stream) runs beside the inverse z transform of dp^/dy, the pull of
+            // dp^/dy beside the inverse x transform of p.  All NCCL barriers of this section are issued on the second stream.
+            cudaStream_t s0 = st, s1 = T.zstream;
+            for (cudaEvent_t& e : ev) if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+            {
+                ProfScope ps(PC_FFT);
+                if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)cpa, (cufftDoubleComplex*)cpa, CUFFT_INVERSE), "cufftExecZ2Z")) return rc;
+                cudaEventRecord(ev[0], s0);
+                if (dpdy) {
+                    if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)cpb, (cufftDoubleComplex*)cpb, CUFFT_INVERSE), "cufftExecZ2Z")) return rc;
+                    cudaEventRecord(ev[1], s0);
+                }
+            }
+            int rc = 0;
+            ctx().stream = s1;
+            cudaStreamWaitEvent(s1, ev[0], 0);
+            {
+                ProfScope ps(PC_TRANSPOSE);
+                rc = T.barrier();
+                if (!rc) kx_pull_kernel<<<ctas, 256, 0, s1>>>((double2*)c1, ta, nxh, ny, nz, T.rank, P);
+                cudaEventRecord(ev[2], s1);
+            }
+            if (!rc && dpdy) {
+                cudaStreamWaitEvent(s1, ev[1], 0);
+                ProfScope ps(PC_TRANSPOSE);
+                rc = T.barrier();
+                if (!rc) kx_pull_kernel<<<ctas, 256, 0, s1>>>((double2*)c2, tb, nxh, ny, nz, T.rank, P);
+                cudaEventRecord(ev[3], s1);
+            }
+            if (!rc) rc = T.barrier();
+            cudaEventRecord(ev[4], s1);
+            T.launches += dpdy ? 2 : 1; T.p2p_exchanges += dpdy ? 2 : 1;
+            ctx().stream = s0;
+            if (rc) return rc;
+            cudaStreamWaitEvent(s0, ev[2], 0);
+            {
+                ProfScope ps(PC_FFT);
+                if (int r2 = cufft_check(cufftExecZ2D(plan_bx, (cufftDoubleComplex*)c1, p), "cufftExecZ2D")) return r2;
+            }
+            if (dpdy) {
+                cudaStreamWaitEvent(s0, ev[3], 0);
+                ProfScope ps(PC_FFT);
+                if (int r2 = cufft_check(cufftExecZ2D(plan_bx, (cufftDoubleComplex*)c2, dpdy), "cufftExecZ2D")) return r2;
+            }
+            cudaStreamWaitEvent(s0, ev[4], 0);      // the peers have read this rank's pencils: they may be overwritten again
+            return 0;
+        }
         {
             ProfScope ps(PC_FFT);
             if (int rc = cufft_check(cufftExecZ2Z(plan_z, (cufftDoubleComplex*)cpa, (cufftDoubleComplex*)cpa, CUFFT_INVERSE), "cufftExecZ2Z")) return rc;

@@ -61,6 +61,7 @@ struct Poisson {
     int kx0[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
     PoissonDev D;
     cufftHandle plan_fx = 0, plan_bx = 0, plan_z = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // two-stream way back of the kx-split stage
     std::vector<void*> allocs;
     int init(tlab_plan_s* gx, tlab_plan_s* gy, tlab_plan_s* gz, int nz_local);
     int solve(double* p, double* c1, double* c2, const double* hb, const double* ht, double* dpdy);

@@ -3,7 +3,7 @@
 one RK substep of bench.py into DRAM bytes per point and launch for each line-kernel class (profiles/ncu_dram_bench_r01.json).
 
   ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
-      -k regex:lines2_ --launch-skip 60 --launch-count 20 --log-file gpurun_out/dram_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu
+      -k regex:lines2_|poisson_team --launch-skip 60 --launch-count 20 --log-file gpurun_out/dram_bench.csv python bench.py --steps 2 --warmup 3 --no-cpu
   python tools/ncu_dram_summary.py gpurun_out/dram_bench.csv 1024 512 1024
 """
 import collections
@@ -16,11 +16,13 @@ import sys
 def classify(name):
     # lines2_contig / lines2_strided <MODE, periodic, need_1der>; in the C3 bench y is the only non-periodic direction
     import re
-    m = re.search(r"lines2_(contig|strided)\w*<(?:\(int\))?(\d+), (?:\(bool\))?(\d), (?:\(bool\))?(\d)>", name)
+    if "poisson_team_kernel" in name or "poisson_modes_kernel" in name:
+        return "poisson_y"
+    m = re.search(r"lines2_(contig|strided|march)\w*<(?:\(int\))?(\d+), (?:\(bool\))?(\d), (?:\(bool\))?(\d)", name)
     if not m:
         return None
     kind, mode, per = m.group(1), int(m.group(2)), int(m.group(3))
-    d = "x" if kind == "contig" else ("z" if per else "y")
+    d = "x" if kind == "contig" else ("z" if per else "y")      # (march: the second template argument is PER as well)
     return {1: "partial_", 2: "partial_", 3: "partial_", 4: "burgers_", 5: "neumann_"}[mode] + d
 
 
@@ -54,7 +56,8 @@ def main():
            "launches": {k: v["launches"] for k, v in agg.items()},
            "ms_per_launch_under_ncu": {k: v["ms"] / v["launches"] for k, v in agg.items()}}
     print(json.dumps(out, indent=1))
-    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "ncu_dram_bench_r01.json"), "w"), indent=1)
+    name = sys.argv[5] if len(sys.argv) > 5 else "ncu_dram_bench_r02.json"
+    json.dump(out, open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", name), "w"), indent=1)
 
 
 if __name__ == "__main__":
