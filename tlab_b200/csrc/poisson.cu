@@ -511,23 +511,17 @@ __global__ void __launch_bounds__(128, MINB) poisson_modes_kernel(PoissonDev D, 
 
 // per call: the (up to four) singular modes, OPR_ODE2_Factorize_NN_Sing -> _DN_Sing
 // `slot` selects the per-mode planes (the mode index for the full planes, 0..3 for the small planes of the warp path)
-__device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ cf, double* __restrict__ cv, int i, int k, long long slot) {
-    const double lam = sqrt(D.lambda[(long long)i + (long long)D.nxh * k]);
-    const long long m = slot;
-    const long long NM = D.nmodes;
-    const long long plane_sz = D.plane_sz;
+// the lines a singular mode works on: forcing / p^ (in place), dp^/dy, and nine scratch lines
+struct SingLines { LineRef fre, fim, vre, vim, ysc0, ysc1, csc, dsc, esc, v1, u1; };
+
+__device__ void poisson_singular_solve(const PoissonDev& D, double lam, const SingLines& Ln) {
     const int n = D.ny;
-    const long long off = 2 * ((long long)i + (long long)D.nxh * D.ny * k);
-    const long long js = 2LL * D.nxh;
-    LineRef fre = {cf + off, js}, fim = {cf + off + 1, js};
-    LineRef vre = {cv + off, js}, vim = {cv + off + 1, js};
+    const LineRef fre = Ln.fre, fim = Ln.fim, vre = Ln.vre, vim = Ln.vim;
     const double norm = D.norm;
     const double bct[2] = {fre.get(n) * norm, fim.get(n) * norm};
-    LineRef ysc[2] = {plane(D, P_SCR, 0, m), plane(D, P_SCR, 1, m)};
-    LineRef csc = plane(D, P_SCR, 2, m), dsc = plane(D, P_SCR, 3, m),
-            esc = plane(D, P_SCR, 4, m);
-    // fundamental lines of this mode live in the (otherwise unused) fund planes of the mode
-    LineRef v1 = plane(D, P_FUND, 0, m), u1 = plane(D, P_FUND, 2, m);
+    LineRef ysc[2] = {Ln.ysc0, Ln.ysc1};
+    LineRef csc = Ln.csc, dsc = Ln.dsc, esc = Ln.esc;
+    LineRef v1 = Ln.v1, u1 = Ln.u1;
     const double zero2[2] = {0.0, 0.0};
     // v^(0): v' = f with f(1) = 0, v(n) = bcs(:,2)
     {
@@ -562,6 +556,69 @@ __device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ 
             vl[l].set(r, vl[l].get(r) + cdu * v1.get(r));
         }
     }
+}
+
+// Singular mode on lines in shared memory with everything that depends on lambda only kept from the first call (`cache`, global:
+// ten lines of n doubles -- lower and upper LU factors of both systems, the fundamental lines v^(1), u^(1) -- and three scalars):
+// later calls run two factor-free solves (no divisions, no table rows) instead of four factorising ones.  Leaves v^(0) and u^(0)
+// in the lines and returns the weights of v^(1), u^(1); the caller adds them (in parallel).
+__device__ void poisson_singular_cached(const PoissonDev& D, double lam, const SingLines& Ln, double* __restrict__ cache, double (&cdu)[2]) {
+    const int n = D.ny;
+    const LineRef famax = {cache, 1}, fbmax = {cache + n, 1}, cmax = {cache + 2 * n, 1}, dmax = {cache + 3 * n, 1};
+    const LineRef famin = {cache + 4 * n, 1}, fbmin = {cache + 5 * n, 1}, cmin = {cache + 6 * n, 1}, dmin = {cache + 7 * n, 1};
+    const LineRef v1 = {cache + 8 * n, 1}, u1 = {cache + 9 * n, 1};
+    double* sc = cache + 10 * n;                  // [0] filled flag, [1] du1, [2] v1(1)
+    const LineRef fre = Ln.fre, fim = Ln.fim, vre = Ln.vre, vim = Ln.vim;
+    LineRef ysc[2] = {Ln.ysc0, Ln.ysc1};
+    const double norm = D.norm;
+    const double bct[2] = {fre.get(n) * norm, fim.get(n) * norm};
+    const double zero2[2] = {0.0, 0.0};
+    if (sc[0] == 0.0) {
+        {   // v^(1): forcing delta at row 1, v1(n) = 0; keeps the factors of the BCS_MAX system
+            LineRef f[1] = {{nullptr, 0}}, res[1] = {v1}, ys[1] = {ysc[0]};
+            const double fend[1] = {1.0}, bc[1] = {0.0};
+            int1_solve<1, 1>(D.smax, -lam, f, 1.0, fend, bc, res, ys, cmax, dmax, Ln.esc, nullptr, famax, fbmax);
+        }
+        {   // u^(1): u' = v1, u1(1) = 0; keeps the factors of the BCS_MIN system
+            LineRef f[1] = {v1}, res[1] = {u1}, ys[1] = {ysc[0]};
+            const double fend[1] = {v1.get(n)}, bc[1] = {0.0};
+            double du1[1];
+            int1_solve<1, 1>(D.smin, lam, f, 1.0, fend, bc, res, ys, cmin, dmin, Ln.esc, du1, famin, fbmin);
+            sc[1] = du1[0];
+            sc[2] = v1.get(1);
+        }
+        __threadfence();
+        sc[0] = 1.0;
+    }
+    {   // v^(0): v' = f with f(1) = 0, v(n) = bcs(:,2)
+        LineRef f[2] = {fre, fim}, res[2] = {vre, vim};
+        int1_solve<2, 2>(D.smax, -lam, f, norm, zero2, bct, res, ysc, cmax, dmax, Ln.esc, nullptr, famax, fbmax);
+    }
+    double du0[2];
+    {   // u^(0): u' = v, u(1) = 0
+        LineRef f[2] = {vre, vim}, res[2] = {fre, fim};
+        const double fend[2] = {vre.get(n), vim.get(n)};
+        int1_solve<2, 2>(D.smin, lam, f, 1.0, fend, zero2, res, ysc, cmin, dmin, Ln.esc, du0, famin, fbmin);
+    }
+    const double ff = 1.0 / (sc[1] - sc[2]);
+    cdu[0] = (vre.get(1) - du0[0]) * ff;
+    cdu[1] = (vim.get(1) - du0[1]) * ff;
+}
+
+// the same on the mode's lines in global memory (thread-per-mode kernels)
+__device__ void poisson_singular_mode(const PoissonDev& D, double* __restrict__ cf, double* __restrict__ cv, int i, int k, long long slot) {
+    const double lam = sqrt(D.lambda[(long long)i + (long long)D.nxh * k]);
+    const long long m = slot;
+    const long long off = 2 * ((long long)i + (long long)D.nxh * D.ny * k);
+    const long long js = 2LL * D.nxh;
+    SingLines Ln;
+    Ln.fre = {cf + off, js}; Ln.fim = {cf + off + 1, js};
+    Ln.vre = {cv + off, js}; Ln.vim = {cv + off + 1, js};
+    Ln.ysc0 = plane(D, P_SCR, 0, m); Ln.ysc1 = plane(D, P_SCR, 1, m);
+    Ln.csc = plane(D, P_SCR, 2, m); Ln.dsc = plane(D, P_SCR, 3, m); Ln.esc = plane(D, P_SCR, 4, m);
+    // fundamental lines of this mode live in the (otherwise unused) fund planes of the mode
+    Ln.v1 = plane(D, P_FUND, 0, m); Ln.u1 = plane(D, P_FUND, 2, m);
+    poisson_singular_solve(D, lam, Ln);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -896,14 +953,48 @@ poisson_team_kernel(PoissonDev D, double* __restrict__ cf, double* __restrict__ 
         // The (up to four) singular modes are marched by one thread each (OPR_ODE2_Factorize_NN_Sing: a different, rank-deficient
         // problem) on small planes of their own.  They take as long as ~1000 dependent loads; the first CTA of the grid starts
         // them so that they run beside the regular modes instead of behind them.
-        if (blockIdx.x == 0 && threadIdx.x < 4) {
-            const int t = threadIdx.x;
+        // one CTA per singular mode; its lines live in shared memory while the thread marches (a march through global memory
+        // waits for a loaded memory system at every row: 3.7 ms for four modes against 1.4 ms for the 66 560 regular modes of the
+        // per-GPU share at 8 GPUs, i.e. the critical path of the stage)
+        if (blockIdx.x < 4) {
+            const int t = blockIdx.x;
             const int is = (t & 1) ? D.i_sing1 : D.i_sing0, ks = (t & 2) ? D.k_sing1 : D.k_sing0;
             const bool dup = ((t & 2) && D.k_sing1 == D.k_sing0) || ((t & 1) && D.i_sing1 == D.i_sing0);
             if (!dup && is >= 0 && is < D.nxh && ks >= 0 && ks < D.nz) {
-                PoissonDev Ds = D;
-                Ds.fund = D.sing; Ds.scr = D.sing + (size_t)5 * 32 * n; Ds.fac = nullptr; Ds.plane_sz = 32LL * n; Ds.il = 0;
-                poisson_singular_mode(Ds, cf, cv, is, ks, t);
+                double* sl = reinterpret_cast<double*>(wtile);               // 11 n doubles
+                double2* cf2s = reinterpret_cast<double2*>(cf) + ((size_t)is + (size_t)D.nxh * n * ks);
+                double2* cv2s = reinterpret_cast<double2*>(cv) + ((size_t)is + (size_t)D.nxh * n * ks);
+                for (int row = threadIdx.x; row < n; row += NT) reinterpret_cast<double2*>(sl)[row] = cf2s[(size_t)D.nxh * row];
+                __syncthreads();
+                double* cache = D.sing + (size_t)t * (10 * (size_t)n + 8);
+                if (threadIdx.x == 0) {
+                    SingLines Ln;
+                    Ln.fre = {sl, 2}; Ln.fim = {sl + 1, 2};
+                    Ln.vre = {sl + 2 * n, 2}; Ln.vim = {sl + 2 * n + 1, 2};
+                    Ln.ysc0 = {sl + 4 * n, 1}; Ln.ysc1 = {sl + 5 * n, 1};
+                    Ln.csc = {sl + 6 * n, 1}; Ln.dsc = {sl + 7 * n, 1}; Ln.esc = {sl + 8 * n, 1};
+                    Ln.v1 = {sl + 9 * n, 1}; Ln.u1 = {sl + 10 * n, 1};
+                    double cdu[2];
+                    poisson_singular_cached(D, sqrt(D.lambda[(long long)is + (long long)D.nxh * ks]), Ln, cache, cdu);
+                    sl[6 * n] = cdu[0]; sl[6 * n + 1] = cdu[1];
+                }
+                __syncthreads();
+                {
+                    // u = u^(0) + cdu u^(1), v = v^(0) + cdu v^(1) (opr_odes.f90:90-95), all rows at once
+                    const double c0 = sl[6 * n], c1 = sl[6 * n + 1];
+                    const double* v1 = cache + 8 * (size_t)n;
+                    const double* u1 = cache + 9 * (size_t)n;
+                    for (int row = threadIdx.x; row < n; row += NT) {
+                        const double a = u1[row], b = v1[row];
+                        sl[2 * row] = sl[2 * row] + c0 * a; sl[2 * row + 1] = sl[2 * row + 1] + c1 * a;
+                        sl[2 * n + 2 * row] = sl[2 * n + 2 * row] + c0 * b; sl[2 * n + 2 * row + 1] = sl[2 * n + 2 * row + 1] + c1 * b;
+                    }
+                }
+                __syncthreads();
+                for (int row = threadIdx.x; row < n; row += NT) {
+                    cf2s[(size_t)D.nxh * row] = reinterpret_cast<double2*>(sl)[row];
+                    cv2s[(size_t)D.nxh * row] = reinterpret_cast<double2*>(sl + 2 * n)[row];
+                }
             }
         }
         return;
@@ -1196,8 +1287,8 @@ static void launch_modes(const PoissonDev& D, double* cf, double* cv, cudaStream
         if (MW != 2 && MW != 4 && MW != 8) MW = 4;
         if (NW * MW > 16) MW = 16 / NW;
         const int TP = (D.T * 9) | 1;
-        const size_t smem = (size_t)MW * TP * sizeof(double2) + (size_t)MW * sizeof(TeamShared);
-        const dim3 grid((unsigned)((D.nxh + MW - 1) / MW), (unsigned)D.nz + 1);      // row 0: singular modes
+        const size_t smem = std::max((size_t)MW * TP * sizeof(double2) + (size_t)MW * sizeof(TeamShared), (size_t)11 * D.ny * sizeof(double));
+        const dim3 grid((unsigned)std::max((D.nxh + MW - 1) / MW, 4), (unsigned)D.nz + 1);      // row 0: singular modes, one CTA each
         PoissonDev Dl = D;
         Dl.pf_dist = ctx().tune_poisson_pf < 0 ? 2 * 148 : ctx().tune_poisson_pf;
         auto go = [&](auto kern) {
