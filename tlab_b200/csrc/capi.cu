@@ -125,6 +125,8 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
         if (nb + nt > 0 && nb + nt < b.T) {
             int Lc = 64;
             while (Lc > 1 && (Lc * (nb + nt) > 512 || a.inner % Lc != 0)) Lc >>= 1;
+            // the exchange area is sized for the whole line (absent chunks read as zero): long lines take fewer lines per CTA
+            while (Lc > 8 && (size_t)8 * b.T * Lc * sizeof(double) > 100 * 1024) Lc >>= 1;
             if ((size_t)8 * b.T * Lc * sizeof(double) <= 200 * 1024) {
                 b.neu_nb = nb; b.neu_nt = nt; b.L = Lc;
                 b.lshift = 0;
