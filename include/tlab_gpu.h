@@ -45,6 +45,7 @@ extern "C" {
 #define TLAB_FDM_COM4_JACOBIAN 4
 #define TLAB_FDM_COM6_JACOBIAN 6
 #define TLAB_FDM_COM6_JACOBIAN_HYPER 7
+#define TLAB_FDM_COM6_DIRECT 16      /* second derivative only (SpaceOrder2 = CompactDirect6, src/fdm/fdm_comx_direct.f90:305-412) */
 /* DNS_BCS_* of src/tools/dns/boundary_bcs.f90:42-46 */
 #define TLAB_DNS_BCS_DIRICHLET 3
 #define TLAB_DNS_BCS_NEUMANN 4

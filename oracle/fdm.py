@@ -33,6 +33,7 @@ FDM_COM4_JACOBIAN = 4
 FDM_COM6_JACOBIAN_PENTA = 5
 FDM_COM6_JACOBIAN = 6
 FDM_COM6_JACOBIAN_HYPER = 7
+FDM_COM6_DIRECT = 16          # fdm_derivative.f90:57
 
 
 def _cshift(a1, s):
@@ -1004,9 +1005,16 @@ def der2_create_system(x, dx1, dx2, g, periodic, uniform):
         g.lhs, g.rhs, g.nb_diag, g.coef = c2n6_jacobian(dx1, dx2, periodic)
     elif g.mode_fdm == FDM_COM6_JACOBIAN_HYPER:
         g.lhs, g.rhs, g.nb_diag, g.coef = c2n6_hyper_jacobian(dx1, dx2, periodic)
+    elif g.mode_fdm == FDM_COM6_DIRECT:
+        # FDM_C2N6_Direct(g%size, x, g%lhs, g%rhs, g%nb_diag); g%need_1der = .false.  (fdm_derivative.f90:381-383)
+        from .fdm_direct import c2n6_direct
+        g.lhs, g.rhs, g.nb_diag = c2n6_direct(x)
+        g.coef = np.zeros(5)
     else:
-        raise NotImplementedError("direct schemes are outside the oracle's scope")
-    if not uniform:
+        raise NotImplementedError("CompactDirect4 is outside the oracle's scope")
+    if g.mode_fdm == FDM_COM6_DIRECT:
+        g.need_1der = False
+    elif not uniform:
         g.need_1der = True
     if periodic:
         wn = _wavenumbers(g.size)
@@ -1038,8 +1046,11 @@ def der2_solve(g, lu, u, du):
     ndl, ndr = g.nb_diag
     result = np.zeros_like(u)
     ibc = BCS_PERIODIC if g.periodic else BCS_DD
-    mm = {5: matmul_5d_sym, 7: matmul_7d_sym}[ndr]
-    mm(g.rhs[:, :ndr + 1], u, result, ibc)
+    if g.mode_fdm == FDM_COM6_DIRECT:
+        matmul_5d(g.rhs[:, :ndr + 1], u, result, ibc)           # g%matmul => MatMul_5d (fdm_derivative.f90:318-323)
+    else:
+        mm = {5: matmul_5d_sym, 7: matmul_7d_sym}[ndr]
+        mm(g.rhs[:, :ndr + 1], u, result, ibc)
     if g.need_1der:
         ip = ndr
         sub = np.zeros((g.size + 1, 4))
@@ -1076,6 +1087,8 @@ def create_plan(g):
     """FDM_CreatePlan, fdm.f90:143-252."""
     x = g.x_nodes
     nx = g.size
+    if g.periodic and g.der2.mode_fdm == FDM_COM6_DIRECT:
+        g.der2.mode_fdm = FDM_COM6_JACOBIAN_HYPER                  # they are the same for uniform grids (fdm.f90:158)
     if nx > 1:
         g.scale = x[nx - 1] - x[0]
         if g.periodic:

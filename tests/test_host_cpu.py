@@ -118,3 +118,26 @@ def test_oracle_is_not_imported_by_the_product():
             if f.endswith((".py", ".cu", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), f
+
+
+@pytest.mark.parametrize("n", [17, 65, 128])
+def test_host_plan_direct_second_derivative_matches_oracle(L, n):
+    """SpaceOrder2 = CompactDirect6 (src/fdm/fdm_comx_direct.f90:305-412): per-row lhs/rhs from the node positions."""
+    from oracle import fdm
+    from tlab_b200 import opr
+    nodes = grid_tanh(n)
+    g = fdm.Plan(nodes, False, False, mode2=fdm.FDM_COM6_DIRECT)
+    p = opr.FdmPlan(nodes, False, False, der2="compactdirect6", host_only=True)
+    assert not g.der2.need_1der
+    assert rel_l2(p.table("lhs2").reshape(3, n).T, g.der2.lhs[1:, 1:4]) < 1e-13
+    assert rel_l2(p.table("rhs2").reshape(-1, n).T[:, :5], g.der2.rhs[1:, 1:6]) < 1e-12
+    nc = g.der2.lu.shape[1] - 1
+    assert rel_l2(p.table("lu2").reshape(nc, n).T, g.der2.lu[1:, 1:]) < 1e-12
+    # the first derivative is untouched by the choice of the second
+    assert rel_l2(p.table("lhs1").reshape(3, n).T, g.der1.lhs[1:, 1:4]) < 1e-13
+    # a periodic direction falls back to the hyper scheme (fdm.f90:158)
+    x = grid_periodic(32)
+    gp = fdm.Plan(x, True, True, mode2=fdm.FDM_COM6_DIRECT)
+    pp = opr.FdmPlan(x, True, True, der2="compactdirect6", host_only=True)
+    assert rel_l2(pp.table("rhs2").reshape(-1, 32).T, gp.der2.rhs[1:, 1:11]) < 1e-13
+    assert rel_l2(pp.table("mwn2"), gp.der2.mwn) < 1e-14

@@ -179,3 +179,59 @@ def test_fast_and_general_kernels_agree(cuda, shape):
     assert cnt[1] == cnt[0] and c.value == cnt[1] + 9, "the fast kernels did not run"
     for a, b in zip(out[0], out[1]):
         assert float(torch.linalg.vector_norm(a - b) / torch.linalg.vector_norm(a)) <= (1e-13 if max(shape) <= 128 else 5e-13)
+
+
+DIRECT_CASES = [(32, 65, 16, "tanh", True, True),        # the usual use: stretched wall-normal direction, periodic x/z fall back to the hyper scheme
+                (48, 40, 33, "stretched", False, False),  # per-row coefficients in all three directions, ragged chunks
+                (16, 17, 16, "tanh", True, True),         # a single chunk (n = 17: the boundary and interior row classes all touch)
+                (32, 256, 32, "tanh", True, True)]        # 16 chunks: lines the fast kernels would have taken
+
+
+@pytest.mark.parametrize("case", DIRECT_CASES)
+def test_compact_direct6_second_derivative(cuda, case):
+    """SpaceOrder2 = CompactDirect6 (src/fdm/fdm_comx_direct.f90:305-412, MatMul_5d fdm_matmul.f90:266-320):
+    OPR_Partial P2 / P2_P1 and OPR_Burgers against the oracle; the first derivative keeps CompactJacobian6."""
+    import torch
+    from oracle import fdm, operators as O
+    from tlab_b200 import opr
+    nx, ny, nz, ykind, xper, zper = case
+    x = grid_periodic(nx) if xper else grid_stretched(nx, 2.0)
+    z = grid_periodic(nz) if zper else grid_stretched(nz, 3.0)
+    y = grid_tanh(ny) if ykind == "tanh" else grid_stretched(ny)
+    grids = (x, y, z)
+    go = [fdm.Plan(x, xper, xper, name="x", mode2=fdm.FDM_COM6_DIRECT), fdm.Plan(y, False, False, name="y", mode2=fdm.FDM_COM6_DIRECT),
+          fdm.Plan(z, zper, zper, name="z", mode2=fdm.FDM_COM6_DIRECT)]
+    gg = [opr.FdmPlan(x, xper, xper, name="x", der2="compactdirect6"), opr.FdmPlan(y, False, False, name="y", der2="compactdirect6"),
+          opr.FdmPlan(z, zper, zper, name="z", der2="compactdirect6")]
+    a = smooth_field((nz, ny, nx), grids)
+    u = torch.from_numpy(a).to(cuda)
+    fns = [opr.OPR_Partial_X, opr.OPR_Partial_Y, opr.OPR_Partial_Z]
+    bcs = [[0, 0], [0, 0]]
+    for idir in range(3):
+        for type_ in (O.OPR_P1, O.OPR_P2, O.OPR_P2_P1):
+            res = torch.full_like(u, float("nan"))
+            tmp = torch.full_like(u, float("nan"))
+            fns[idir](type_, nx, ny, nz, bcs, gg[idir], u, res, tmp if type_ == O.OPR_P2_P1 else None)
+            ref = O.opr_partial(idir, type_, bcs, go[idir], a)
+            if type_ == O.OPR_P2_P1:
+                assert rel_l2(res.cpu().numpy(), ref[0]) <= TOL, (idir, type_)
+                assert rel_l2(tmp.cpu().numpy(), ref[1]) <= TOL, (idir, type_)
+            else:
+                assert rel_l2(res.cpu().numpy(), ref) <= TOL, (idir, type_)
+    # the scheme really is a different one from the Jacobian form on a stretched grid
+    gj = fdm.Plan(y, False, False, name="y")
+    d2j = O.opr_partial(1, O.OPR_P2, bcs, gj, a)
+    d2d = O.opr_partial(1, O.OPR_P2, bcs, go[1], a)
+    assert 1e-10 < rel_l2(d2d, d2j) < 0.5
+    visc, schmidt = 1.0 / 5000.0, [1.0]
+    B = O.Burgers(go, visc, schmidt)
+    opr.OPR_Burgers_Initialize(gg, visc, schmidt)
+    s_np = smooth_field((nz, ny, nx), grids, seed=1)
+    v_np = smooth_field((nz, ny, nx), grids, seed=2)
+    s, v = torch.from_numpy(s_np).to(cuda), torch.from_numpy(v_np).to(cuda)
+    bfn = [opr.OPR_Burgers_X, opr.OPR_Burgers_Y, opr.OPR_Burgers_Z]
+    for idir in range(3):
+        for is_ in range(2):
+            res = torch.full_like(s, float("nan"))
+            bfn[idir](opr.OPR_B_U_IN, is_, nx, ny, nz, bcs, s, v, res)
+            assert rel_l2(res.cpu().numpy(), B.apply(idir, is_, bcs, s_np, v_np)) <= TOL, ("u_in", idir, is_)

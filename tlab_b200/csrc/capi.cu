@@ -63,6 +63,7 @@ static int need_ready() {
 static void fill_common(LineArgs& a, const DevPlan& p) {
     a.n = p.n; a.T = p.T; a.cbase = p.cbase; a.crem = p.crem;
     a.rhs_d1 = p.rhs_d1;
+    a.rhs2_rows = p.rhs2_rows;
     a.rhs2 = p.rhs2;
 }
 
@@ -92,6 +93,8 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
         fast = al(a.u) && al(a.u2) && al(a.vel) && al(a.out1) && al(a.out2);
     }
     if (fast && p.need_1der && !p.cjac2) fast = false;
+    // per-row rhs of the CompactDirect6 second derivative: general kernels (the first derivative alone keeps the fast path)
+    if (fast && p.rhs2_rows && (mode == MODE_P2 || mode == MODE_P2_P1 || mode == MODE_BURGERS)) fast = false;
     if (!fast) return false;
     b.n = a.n; b.T = a.n / CHUNK; b.L = L;
     b.xls = contig ? lines2_xstride(b.T, L) : 0;

@@ -236,6 +236,20 @@ void matmul_line(const HostDer& g, bool second, int ibc, const double* u, double
     auto U = [&](int i) { return u[i - 1]; };
     auto Up = [&](int i) { return u[((i - 1) % n + n) % n]; };
     const bool per = (ibc == BCS_PERIODIC);
+    if (second && g.mode_fdm == FDM_COM6_DIRECT) {
+        // MatMul_5d with per-row coefficients (fdm_matmul.f90:266-320)
+        for (int i = 1; i <= n; i++) {
+            double s = 0.0;
+            if (i == 1) s = U(1) * r(1, 3) + U(2) * r(1, 4) + U(3) * r(1, 5) + U(4) * r(1, 1);
+            else if (i == 2) s = U(1) * r(2, 2) + U(2) * r(2, 3) + U(3) * r(2, 4) + U(4) * r(2, 5);
+            else if (i == n - 1) s = U(n - 3) * r(i, 1) + U(n - 2) * r(i, 2) + U(n - 1) * r(i, 3) + U(n) * r(i, 4);
+            else if (i == n) s = U(n - 3) * r(n, 5) + U(n - 2) * r(n, 1) + U(n - 1) * r(n, 2) + U(n) * r(n, 3);
+            else if (i <= 4 || i >= n - 3) s = U(i - 2) * r(i, 1) + U(i - 1) * r(i, 2) + U(i) * r(i, 3) + U(i + 1) * r(i, 4) + U(i + 2) * r(i, 5);
+            else s = U(i - 2) * r(i, 1) + U(i - 1) * r(i, 2) + U(i) * r(i, 3) + U(i + 1) + U(i + 2) * r(i, 5);
+            f[i - 1] = s;
+        }
+        return;
+    }
     // rows with constant interior stencil: nb+1 .. n-nb (nb = idr-1 special rows for antisym/sym kernels)
     const int nb = per ? 0 : h;
     const int ref_row = h + 2;      // a row guaranteed to hold interior coefficients
@@ -412,6 +426,199 @@ void der2_initialize(const std::vector<double>& dx1, const std::vector<double>& 
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CompactDirect6 second derivative: the compact scheme derived on the actual (non-uniform) nodes instead of on a uniform
+// computational grid (reference src/fdm/fdm_comx_direct.f90:305-412 FDM_C2N6_Direct with its coefficient functions :468-783 and
+// the Lagrange helpers of src/fdm/fdm_base.f90:31-143).  Tridiagonal lhs, pentadiagonal rhs with per-row coefficients, no
+// Jacobian term.  x is 1-based here, as in the formulas.
+struct DirectC2N6 {
+    const double* x;      // x[i], i = 1..n
+    double Pi(int j, std::initializer_list<int> idx) const { double f = 1.0; for (int k : idx) f *= (x[j] - x[k]); return f; }
+    double Pi_p(int j, std::initializer_list<int> idx) const {
+        double f = 0.0;
+        int kk = 0;
+        for (int k : idx) {
+            (void)k;
+            double d = 1.0;
+            int mm = 0;
+            for (int m : idx) { if (mm != kk) d *= (x[j] - x[m]); mm++; }
+            f += d;
+            kk++;
+        }
+        return f;
+    }
+    double Pi_pp_3(int j, int a, int b, int c) const { return 2.0 * (x[j] - x[a] + x[j] - x[b] + x[j] - x[c]); }
+    double Lag(int j, int i, std::initializer_list<int> idx) const {
+        double f = 1.0;
+        for (int k : idx) if (k != i) f = f * (x[j] - x[k]) / (x[i] - x[k]);
+        return f;
+    }
+    double Lag_p(int j, int i, std::initializer_list<int> idx) const {
+        double den = 1.0, f = 0.0;
+        int kk = 0;
+        for (int k : idx) {
+            if (k != i) {
+                double d = 1.0;
+                int mm = 0;
+                for (int m : idx) { if (m != i && mm != kk) d *= (x[j] - x[m]); mm++; }
+                f += d;
+                den *= (x[i] - x[k]);
+            }
+            kk++;
+        }
+        return f / den;
+    }
+    double Lag_pp_3(int j, int i, std::initializer_list<int> idx) const {
+        (void)j;
+        double f = 2.0;
+        for (int k : idx) if (k != i) f = f / (x[i] - x[k]);
+        return f;
+    }
+    double PIp_o_PI(int j, int i) const {
+        double f = (x[j] - x[i + 2]) * (x[j] - x[i - 2]) + (x[j] - x[i]) * (x[j] - x[i - 2]) + (x[j] - x[i]) * (x[j] - x[i + 2]);
+        return f / Pi(j, {i - 2, i, i + 2});
+    }
+    double PIpp_o_PI(int j, int i) const {
+        const double f = x[j] - x[i + 2] + x[j] - x[i - 2] + x[j] - x[i];
+        return 2.0 * f / Pi(j, {i - 2, i, i + 2});
+    }
+    double D_coef(int i) const {
+        const double dx = x[i + 1] - x[i - 1];
+        return 6.0 + 4.0 * dx * (PIp_o_PI(i + 1, i) - PIp_o_PI(i - 1, i)) - 2.0 * dx * dx * PIp_o_PI(i + 1, i) * PIp_o_PI(i - 1, i);
+    }
+    double A1D(int im, int ip, int i) const {
+        const double dx = x[ip] - x[im];
+        return -4.0 * PIp_o_PI(ip, i) - 2.0 * PIp_o_PI(im, i) + 2.0 * dx * (PIp_o_PI(ip, i) * PIp_o_PI(im, i) - PIpp_o_PI(ip, i)) +
+               dx * dx * PIpp_o_PI(ip, i) * PIp_o_PI(im, i);
+    }
+    double A2D(int im, int ip, int i) const {
+        const double dx = x[ip] - x[im];
+        return 4.0 * PIp_o_PI(ip, i) * PIp_o_PI(im, i) - PIpp_o_PI(ip, i) - 2.0 / dx * (PIp_o_PI(ip, i) - PIp_o_PI(im, i)) +
+               dx * PIpp_o_PI(ip, i) * PIp_o_PI(im, i);
+    }
+    double B1D(int im, int ip, int i) const { const double dx = x[ip] - x[im]; return -(2.0 / dx + PIp_o_PI(ip, i)) * dx * dx; }
+    double B2D(int im, int ip, int i) const { const double dx = x[ip] - x[im]; return 1.0 - dx * PIp_o_PI(im, i); }
+    double C1D(int j, int i) const {
+        const double dx = x[i + 1] - x[i - 1], dxp = x[i + 1] - x[j], dxm = x[j] - x[i - 1];
+        return (dxp - dxm) / (dxp * dxm) * (6.0 - 4.0 * dx * dx / (dxp * dxm)) +
+               2.0 * dx * (dxm / dxp - dxp / dxm) * PIp_o_PI(i - 1, i) * PIp_o_PI(i + 1, i) +
+               PIp_o_PI(i - 1, i) * (4.0 * dx / dxp - 4.0 * dx / dxm - 2.0 * dx * dx / (dxp * dxp)) -
+               PIp_o_PI(i + 1, i) * (4.0 * dx / dxp - 4.0 * dx / dxm + 2.0 * dx * dx / (dxm * dxm));
+    }
+    double C2D(int j, int i) const {
+        const double dx = x[i + 1] - x[i - 1], dxp = x[i + 1] - x[j], dxm = x[j] - x[i - 1];
+        return 2.0 * (1.0 / (dxp * dxp) + 1.0 / (dxm * dxm) - 1.0 / (dxp * dxm)) +
+               2.0 * dx * dx / (dxp * dxm) * PIp_o_PI(i + 1, i) * PIp_o_PI(i - 1, i) -
+               2.0 * PIp_o_PI(i + 1, i) * dx / dxm * (1.0 / dxp - 1.0 / dxm) - 2.0 * PIp_o_PI(i - 1, i) * dx / dxp * (1.0 / dxp - 1.0 / dxm);
+    }
+    double a2n6(int im, int ip, int i) const {
+        const double dx = x[ip] - x[im], dxp = x[i] - x[ip], dxm = x[i] - x[im];
+        double f1 = B1D(ip, im, i) * (dxm + dxp) + B2D(im, ip, i) * dxp * (dxp + 2.0 * dxm);
+        f1 = f1 * 2.0 * Pi_p(i, {i - 2, i, i + 2});
+        double f2 = B1D(ip, im, i) + B2D(im, ip, i) * dxp;
+        f2 = f2 * Pi_pp_3(i, i - 2, i, i + 2) * dxp * dxm;
+        return -(f1 + f2) / dx / Pi(ip, {i - 2, i, i + 2});
+    }
+    double b2n6(int im, int ip, int i) const {
+        const double dx = x[ip] - x[im], dxp = x[i] - x[ip], dxm = x[i] - x[im];
+        const double D = D_coef(i);
+        double f1 = 1.0 + A1D(im, ip, i) / D * (dxm + dxp) + A2D(im, ip, i) / D * dxp * (dxp + 2.0 * dxm);
+        f1 = f1 * 2.0 * Pi_p(i, {i - 2, i, i + 2});
+        double f2 = 1.0 + A1D(im, ip, i) / D * dxp + A2D(im, ip, i) / D * dxp * dxp;
+        f2 = f2 * Pi_pp_3(i, i - 2, i, i + 2) * dxm;
+        return (f1 + f2) / dx / Pi(ip, {i - 2, i, i + 2});
+    }
+    double c2n6(int j, int i) const {
+        const double dx = x[i] - x[j], dxp = x[i] - x[i + 1], dxm = x[i] - x[i - 1], dxp2 = x[j] - x[i + 1], dxm2 = x[j] - x[i - 1];
+        const double D = D_coef(i);
+        double f1 = C1D(j, i) / D * (1.0 + dx / dxp + dx / dxm) + C2D(j, i) / D * (2.0 + dx / dxp + dx / dxm) * dx + 1.0 / dxp + 1.0 / dxm;
+        f1 = f1 * 2.0 * Lag_p(i, j, {i - 2, i, i + 2}) * dxp * dxm / (dxp2 * dxm2);
+        double f2 = 1.0 + C1D(j, i) / D * dx + C2D(j, i) / D * dx * dx;
+        f2 = f2 * Lag_pp_3(j, j, {i - 2, i, i + 2}) * dxp * dxm / (dxp2 * dxm2);
+        return f1 + f2;
+    }
+    void c2n4(int i, double (&c)[6]) const {
+        const double dx = x[i + 1] - x[i - 1], dxp = x[i + 1] - x[i], dxm = x[i] - x[i - 1];
+        const double D = dxp * dxm + dx * dx;
+        c[0] = (dxm * dxm - dxp * dxp + dxp * dxm) * dxp / dx / D;
+        c[1] = 1.0;
+        c[2] = (dxp * dxp - dxm * dxm + dxp * dxm) * dxm / dx / D;
+        c[3] = dxp / dx * 12.0 / D;
+        c[4] = -12.0 / D;
+        c[5] = dxm / dx * 12.0 / D;
+    }
+    void c2n3_biased(int i, bool backwards, double (&c)[6]) const {
+        const int i1 = i, i2 = backwards ? i - 1 : i + 1, i3 = backwards ? i - 2 : i + 2, i4 = backwards ? i - 3 : i + 3;
+        const double dx1 = x[i2] - x[i1], dx3 = x[i2] - x[i3], dx4 = x[i2] - x[i4];
+        auto M = std::initializer_list<int>{i1, i3, i4};
+        const double a1 = 1.0;
+        const double a2 = (0.5 * dx1 * Pi_pp_3(i1, i1, i3, i4) - Pi_p(i1, M)) / Pi_p(i2, M);
+        double b2 = Pi_pp_3(i1, i1, i3, i4) + 0.5 * dx1 * Pi_pp_3(i1, i1, i3, i4) * Pi_pp_3(i2, i1, i3, i4) / Pi_p(i2, M) -
+                    Pi_p(i1, M) / Pi_p(i2, M) * Pi_pp_3(i2, i1, i3, i4);
+        b2 = b2 / Pi(i2, M);
+        double D = Lag(i2, i1, M) + dx1 * Lag_p(i2, i1, M);
+        double b1 = -2.0 * Lag_p(i1, i1, M) * (Lag(i2, i1, M) + 2.0 * dx1 * Lag_p(i2, i1, M)) + 2.0 * Lag_p(i2, i1, M);
+        b1 = b1 / D / dx1 + Lag_pp_3(i1, i1, M);
+        D = Lag(i2, i3, M) + dx3 * Lag_p(i2, i3, M);
+        double b3 = (Lag(i2, i3, M) + dx1 * Lag_p(i2, i3, M)) * dx1 * Lag_pp_3(i1, i3, M) -
+                    2.0 * (Lag(i2, i3, M) + 2.0 * dx1 * Lag_p(i2, i3, M)) * Lag_p(i1, i3, M);
+        b3 = b3 / D / dx3;
+        D = Lag(i2, i4, M) + dx4 * Lag_p(i2, i4, M);
+        double b4 = (Lag(i2, i4, M) + dx1 * Lag_p(i2, i4, M)) * dx1 * Lag_pp_3(i1, i4, M) -
+                    2.0 * (Lag(i2, i4, M) + 2.0 * dx1 * Lag_p(i2, i4, M)) * Lag_p(i1, i4, M);
+        b4 = b4 / D / dx4;
+        c[0] = a1; c[1] = a2; c[2] = b1; c[3] = b2; c[4] = b3; c[5] = b4;
+    }
+};
+
+// lhs(1..n, 1..3), rhs(1..n, 1..5); the fourth coefficient of the first / last row sits in rhs(1, 1) / rhs(n, 5)
+void c2n6_direct(const std::vector<double>& nodes0, int n, Mat& lhs, Mat& rhs) {
+    std::vector<double> xp(n + 1, 0.0);
+    for (int i = 1; i <= n; i++) xp[i] = nodes0[i - 1];
+    DirectC2N6 d{xp.data()};
+    double c[6];
+    d.c2n3_biased(1, false, c);
+    double dummy = 1.0 / c[2];
+    lhs(1, 2) = c[0] * dummy; lhs(1, 3) = c[1] * dummy;
+    rhs(1, 3) = c[2] * dummy; rhs(1, 4) = c[3] * dummy; rhs(1, 5) = c[4] * dummy; rhs(1, 1) = c[5] * dummy;
+    d.c2n3_biased(n, true, c);
+    dummy = 1.0 / c[2];
+    lhs(n, 2) = c[0] * dummy; lhs(n, 1) = c[1] * dummy;
+    rhs(n, 3) = c[2] * dummy; rhs(n, 2) = c[3] * dummy; rhs(n, 1) = c[4] * dummy; rhs(n, 5) = c[5] * dummy;
+    for (int i : {2, n - 1}) {
+        d.c2n4(i, c);
+        dummy = 1.0 / c[4];
+        for (int j = 0; j < 3; j++) { lhs(i, 1 + j) = c[j] * dummy; rhs(i, 2 + j) = c[3 + j] * dummy; }
+    }
+    for (int i = 3; i <= n - 2; i++) {
+        const double D = d.D_coef(i);
+        const double a = 1.0, ap1 = d.a2n6(i - 1, i + 1, i) / D, am1 = d.a2n6(i + 1, i - 1, i) / D;
+        const double bp1 = d.b2n6(i - 1, i + 1, i), bm1 = d.b2n6(i + 1, i - 1, i);
+        const double dxp = xp[i] - xp[i + 1], dxm = xp[i] - xp[i - 1];
+        const double lp = d.Lag_p(i, i, {i - 2, i, i + 2});
+        const double b = 2.0 * d.C2D(i, i) / D + 2.0 * d.C1D(i, i) / D * ((dxm + dxp) / (dxp * dxm) + lp) +
+                         (2.0 + 2.0 * lp * (dxm + dxp)) / (dxp * dxm) + d.Lag_pp_3(i, i, {i - 2, i, i + 2});
+        const double bp2 = d.c2n6(i + 2, i), bm2 = d.c2n6(i - 2, i);
+        dummy = 1.0 / bp1;
+        lhs(i, 1) = am1 * dummy; lhs(i, 2) = a * dummy; lhs(i, 3) = ap1 * dummy;
+        rhs(i, 1) = bm2 * dummy; rhs(i, 2) = bm1 * dummy; rhs(i, 3) = b * dummy; rhs(i, 4) = bp1 * dummy; rhs(i, 5) = bp2 * dummy;
+    }
+}
+
+void der2_initialize_direct(const std::vector<double>& nodes0, int n, HostDer& g) {
+    g.size = n; g.periodic = false; g.ndl = 3; g.ndr = 5;
+    for (double& c : g.coef) c = 0.0;
+    g.lhs = Mat(1, n, 1, 5);
+    g.rhs = Mat(1, n, 1, 12);
+    c2n6_direct(nodes0, n, g.lhs, g.rhs);
+    g.need_1der = false;
+    g.mwn.assign(n, 0.0);
+    g.lu = Mat(1, n, 1, 3);
+    for (int i = 1; i <= n; i++) for (int j = 1; j <= 3; j++) g.lu(i, j) = g.lhs(i, j);
+    tridfs(n, {&g.lu, 1, 1}, {&g.lu, 2, 1}, {&g.lu, 3, 1});
+}
+
 }  // namespace
 
 void der1_solve_line(const HostDer& g, int ibc, const double* u, double* result) {
@@ -442,7 +649,8 @@ void der2_solve_line(const HostDer& g, const double* u, const double* du, double
 int create_plan(const double* nodes, int n, bool periodic, bool uniform, int mode1, int mode2, HostPlan& g) {
     if (periodic && !uniform) return 85;   // DNS_ERROR_OPTION: grid must be uniform in a periodic direction
     if (mode1 != FDM_COM4_JACOBIAN && mode1 != FDM_COM6_JACOBIAN) return 104;   // DNS_ERROR_UNDEVELOP
-    if (mode2 != FDM_COM4_JACOBIAN && mode2 != FDM_COM6_JACOBIAN && mode2 != FDM_COM6_JACOBIAN_HYPER) return 104;
+    if (periodic && mode2 == FDM_COM6_DIRECT) mode2 = FDM_COM6_JACOBIAN_HYPER;      // the same on uniform grids (fdm.f90:158)
+    if (mode2 != FDM_COM4_JACOBIAN && mode2 != FDM_COM6_JACOBIAN && mode2 != FDM_COM6_JACOBIAN_HYPER && mode2 != FDM_COM6_DIRECT) return 104;
     g.size = n; g.periodic = periodic; g.uniform = uniform;
     g.der1 = HostDer(); g.der2 = HostDer();
     g.der1.mode_fdm = mode1; g.der2.mode_fdm = mode2;
@@ -466,11 +674,18 @@ int create_plan(const double* nodes, int n, bool periodic, bool uniform, int mod
     der1_initialize(j1, n, g.der1, periodic, {BCS_DD, BCS_ND, BCS_DN, BCS_NN});
     if (periodic) for (double& w : g.der1.mwn) w = w / g.jac(1, 1);
     // d2x/ds2 from the second-derivative scheme on the unit grid
-    der2_initialize(one, zero, n, g.der2, false, true);
+    if (mode2 == FDM_COM6_DIRECT) {
+        std::vector<double> unit(n);
+        for (int i = 0; i < n; i++) unit[i] = double(i);
+        der2_initialize_direct(unit, n, g.der2);
+    } else {
+        der2_initialize(one, zero, n, g.der2, false, true);
+    }
     der2_solve_line(g.der2, nodes, nodes, tmp.data());
     for (int i = 1; i <= n; i++) { g.jac(i, 3) = tmp[i - 1]; j2[i] = tmp[i - 1]; g.jac(i, 2) = g.jac(i, 1); }
     g.der2.need_1der = false;
-    der2_initialize(j1, j2, n, g.der2, periodic, uniform);
+    if (mode2 == FDM_COM6_DIRECT) der2_initialize_direct(g.nodes, n, g.der2);
+    else der2_initialize(j1, j2, n, g.der2, periodic, uniform);
     if (periodic) for (double& w : g.der2.mwn) w = w / (g.jac(1, 1) * g.jac(1, 1));
     return 0;
 }

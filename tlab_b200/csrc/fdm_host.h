@@ -36,7 +36,7 @@ struct Mat {
 enum { BCS_PERIODIC = -1, BCS_DD = 0, BCS_ND = 1, BCS_DN = 2, BCS_NN = 3 };
 enum { BCS_NONE = 0, BCS_MIN = 1, BCS_MAX = 2, BCS_BOTH = 3 };
 // scheme codes (reference fdm_derivative.f90:51-58)
-enum { FDM_COM4_JACOBIAN = 4, FDM_COM6_JACOBIAN_PENTA = 5, FDM_COM6_JACOBIAN = 6, FDM_COM6_JACOBIAN_HYPER = 7 };
+enum { FDM_COM4_JACOBIAN = 4, FDM_COM6_JACOBIAN_PENTA = 5, FDM_COM6_JACOBIAN = 6, FDM_COM6_JACOBIAN_HYPER = 7, FDM_COM6_DIRECT = 16 };
 
 struct HostDer {
     int mode_fdm = 0;

@@ -271,6 +271,30 @@ __device__ __forceinline__ void rhs_top(const double (&wt)[BROW_W], double (&f)[
     }
 }
 
+// CompactDirect6 second derivative (fdm_comx_direct.f90:305-412): pentadiagonal rhs with per-row coefficients, MatMul_5d
+// (fdm_matmul.f90:266-320) term by term -- ascending columns, the first upper diagonal of the interior rows (5 .. n-4) is 1
+// by normalisation and not multiplied, the fourth coefficient of the first / last row sits in column 1 / 5 of its row.
+__device__ __forceinline__ void rhs_direct(const double (&u)[CHUNK + 6], double (&f)[CHUNK], const double* __restrict__ rows,
+                                           const Chunk& c, int n) {
+    const int base = c.s0 - c.j0;
+#pragma unroll
+    for (int j = 0; j < CHUNK; j++) {
+        const int i = base + j;
+        if (j < c.j0 || j >= c.j0 + c.cnt) continue;
+        const double* r = rows + 5 * (size_t)i;
+        const double r1 = ldro(r), r2 = ldro(r + 1), r3 = ldro(r + 2), r4 = ldro(r + 3), r5 = ldro(r + 4);
+        const double um3 = u[j], um2 = u[j + 1], um1 = u[j + 2], u0 = u[j + 3], up1 = u[j + 4], up2 = u[j + 5], up3 = u[j + 6];
+        double s;
+        if (i == 0) s = DADD(DADD(DADD(DMUL(u0, r3), DMUL(up1, r4)), DMUL(up2, r5)), DMUL(up3, r1));
+        else if (i == 1) s = DADD(DADD(DADD(DMUL(um1, r2), DMUL(u0, r3)), DMUL(up1, r4)), DMUL(up2, r5));
+        else if (i == n - 1) s = DADD(DADD(DADD(DMUL(um3, r5), DMUL(um2, r1)), DMUL(um1, r2)), DMUL(u0, r3));
+        else if (i == n - 2) s = DADD(DADD(DADD(DMUL(um2, r1), DMUL(um1, r2)), DMUL(u0, r3)), DMUL(up1, r4));
+        else if (i < 4 || i > n - 5) s = DADD(DADD(DADD(DADD(DMUL(um2, r1), DMUL(um1, r2)), DMUL(u0, r3)), DMUL(up1, r4)), DMUL(up2, r5));
+        else s = DADD(DADD(DADD(DADD(DMUL(um2, r1), DMUL(um1, r2)), DMUL(u0, r3)), up1), DMUL(up2, r5));
+        f[j] = s;
+    }
+}
+
 // Jacobian correction of the second derivative on non-uniform grids:  f2 += A2*jac2 * du  (tridiagonal,
 // extended stencil in the first and last row)
 __device__ __forceinline__ void add_jacobian_term(double (&f2)[CHUNK], const double (&d1)[CHUNK], const Chunk& c,
@@ -326,10 +350,14 @@ __device__ __forceinline__ void line_core(double (&u)[CHUNK + 6], const double (
         }
     }
     if (WANT2) {
-        rhs_interior<true>(u, d[1], a.rhs2);
-        if (!PER) {
-            if (c.t == 0) rhs_bottom(wb, d[1], a.rhs2);
-            if (c.t == c.T - 1) rhs_top(wt, d[1], a.rhs2);
+        if (!PER && a.rhs2_rows != nullptr) {
+            rhs_direct(u, d[1], a.rhs2_rows, c, a.n);
+        } else {
+            rhs_interior<true>(u, d[1], a.rhs2);
+            if (!PER) {
+                if (c.t == 0) rhs_bottom(wb, d[1], a.rhs2);
+                if (c.t == c.T - 1) rhs_top(wt, d[1], a.rhs2);
+            }
         }
     }
     if (WANT1 && WANT2 && !NEED1) {

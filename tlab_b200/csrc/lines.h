@@ -25,6 +25,7 @@ struct LineArgs {
     double* bcs_hb = nullptr;         // NEUMANN: boundary planes
     double* bcs_ht = nullptr;
     const double* rhs_d1 = nullptr;
+    const double* rhs2_rows = nullptr; // CompactDirect6 second derivative: per-row coefficients [n][5] of the pentadiagonal rhs (MatMul_5d)
     RhsTab rhs1, rhs2;
     SolveTab lu1, lu2;
     double neu_bot[BROW_W], neu_top[BROW_W];

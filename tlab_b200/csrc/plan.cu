@@ -329,6 +329,13 @@ int devplan_build(DevPlan& p) {
     }
     // second derivative
     make_rhs(h.der2, true, BCS_DD, p.rhs2);
+    if (h.der2.mode_fdm == FDM_COM6_DIRECT) {
+        // per-row coefficients: no constant interior stencil, no dense special rows (the kernels branch on rhs2_rows)
+        std::memset(&p.rhs2, 0, sizeof(p.rhs2));
+        std::vector<double> rows(5 * (size_t)n);
+        for (int i = 1; i <= n; i++) for (int j = 1; j <= 5; j++) rows[5 * (size_t)(i - 1) + (j - 1)] = h.der2.rhs(i, j);
+        p.rhs2_rows = upload(p, rows);
+    }
     p.lu2.clear();
     p.lu2.emplace_back();
     p.sys2.clear();

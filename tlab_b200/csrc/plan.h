@@ -87,6 +87,7 @@ struct DevPlan {
     Sys2 sys1[4];                    // the same systems in the form of lines2.cu
     std::vector<Sys2> sys2;
     const double* rhs_d1 = nullptr;  // [n][3] Jacobian correction of the second derivative (need_1der)
+    const double* rhs2_rows = nullptr;  // [n][5] per-row rhs of a CompactDirect6 second derivative (general kernels only)
     const double* cjac2 = nullptr;   // lines2.cu: c_j = dx2_j / dx1_j^2, item (t, j) at ((t>>3)*CHUNK + j)*8 + (t&7).  The Jacobian term of
                                      // the second derivative is a diagonal correction of the solution: with lhs = A0 diag(dx1^2) and
                                      // rhs_d1 = -A0 diag(dx2) (fdm_com2_jacobian.f90:263-274; the extended-stencil entry of a tridiagonal

@@ -18,7 +18,7 @@ OPR_P1, OPR_P2, OPR_P2_P1 = 1, 2, 3
 OPR_B_SELF, OPR_B_U_IN = 0, 1
 BCS_DD, BCS_ND, BCS_DN, BCS_NN = 0, 1, 2, 3
 
-_SCHEMES = {"compactjacobian4": 4, "compactjacobian6": 6, "compactjacobian6hyper": 7}
+_SCHEMES = {"compactjacobian4": 4, "compactjacobian6": 6, "compactjacobian6hyper": 7, "compactdirect6": 16}
 
 
 def _ptr(t):
