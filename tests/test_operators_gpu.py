@@ -235,3 +235,41 @@ def test_compact_direct6_second_derivative(cuda, case):
             res = torch.full_like(s, float("nan"))
             bfn[idir](opr.OPR_B_U_IN, is_, nx, ny, nz, bcs, s, v, res)
             assert rel_l2(res.cpu().numpy(), B.apply(idir, is_, bcs, s_np, v_np)) <= TOL, ("u_in", idir, is_)
+
+
+@pytest.mark.parametrize("shape", [(256, 32, 128), (1024, 16, 32), (128, 16, 512)])
+def test_circulant_form_and_closure_form_agree_with_the_oracle(cuda, shape):
+    """Periodic directions: the fast kernels solve the circulant systems either with the reference's rank-one closure
+    (TRIDPFS / TRIDPSS, linear3.f90:321-442: per-point tables in the chunks at the two ends of a line) or in circulant form
+    (constant chunks everywhere, windows wrapping around the line; the default).  Both against the oracle."""
+    import torch
+    from oracle import operators as O
+    from tlab_b200 import lib as tl, opr
+    nx, ny, nz = shape
+    grids, go, gg = _plans(nx, ny, nz, "tanh")
+    visc = 1.0 / 5000.0
+    Bo = O.Burgers(go, visc, [1.0])
+    opr.OPR_Burgers_Initialize(gg, visc, [1.0])
+    a = smooth_field((nz, ny, nx), grids, seed=7)
+    b = smooth_field((nz, ny, nx), grids, seed=8)
+    u, v = torch.from_numpy(a).to(cuda), torch.from_numpy(b).to(cuda)
+    P = [opr.OPR_Partial_X, None, opr.OPR_Partial_Z]
+    B = [opr.OPR_Burgers_X, None, opr.OPR_Burgers_Z]
+    bcs = [[0, 0], [0, 0]]
+    L = tl.load()
+    try:
+        for circ in (0, 1):
+            tl.check(L.tlab_gpu_set_tuning(b"circ", circ))
+            tl.check(L.tlab_gpu_set_tuning(b"march", 0))          # the line kernels of lines2.cu in both directions
+            for d in (0, 2):
+                r1, r2, r3, r4 = (torch.full_like(u, float("nan")) for _ in range(4))
+                P[d](opr.OPR_P2_P1, nx, ny, nz, bcs, gg[d], u, r1, r2)
+                ref = O.opr_partial(d, O.OPR_P2_P1, bcs, go[d], a)
+                assert rel_l2(r1.cpu().numpy(), ref[0]) <= TOL and rel_l2(r2.cpu().numpy(), ref[1]) <= TOL, (circ, d)
+                P[d](opr.OPR_P1, nx, ny, nz, bcs, gg[d], u, r4)
+                assert rel_l2(r4.cpu().numpy(), O.opr_partial(d, O.OPR_P1, bcs, go[d], a)) <= TOL, (circ, d)
+                B[d](opr.OPR_B_U_IN, 1, nx, ny, nz, bcs, u, v, r3)
+                assert rel_l2(r3.cpu().numpy(), Bo.apply(d, 1, bcs, a, b)) <= TOL, (circ, d)
+    finally:
+        tl.check(L.tlab_gpu_set_tuning(b"circ", 1))
+        tl.check(L.tlab_gpu_set_tuning(b"march", 1))

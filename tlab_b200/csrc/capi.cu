@@ -114,6 +114,7 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
     b.u = a.u; b.u2 = a.u2; b.vel = a.vel; b.out1 = a.out1; b.out2 = a.out2; b.bcs_hb = a.bcs_hb; b.bcs_ht = a.bcs_ht;
     b.cjac = p.cjac2;
     b.rhs1 = a.rhs1; b.rhs2 = a.rhs2; b.s1 = s1; b.s2 = s2;
+    if (!ctx().tune_circ) b.s1.circ = b.s2.circ = 0;
     std::memcpy(b.neu_bot, a.neu_bot, sizeof(b.neu_bot));
     std::memcpy(b.neu_top, a.neu_top, sizeof(b.neu_top));
     b.neu_lu_bot = a.neu_lu_bot; b.neu_lu_top = a.neu_lu_top;
@@ -459,6 +460,9 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "split_emulate")) ctx().tune_split_emulate = value;
     else if (!std::strcmp(key, "pf_l1")) ctx().tune_pf_l1 = value;
     else if (!std::strcmp(key, "march")) ctx().tune_march = value;
+    else if (!std::strcmp(key, "circ")) ctx().tune_circ = value;
+    else if (!std::strcmp(key, "split_trim")) ctx().tune_split_trim = value;
+    else if (!std::strcmp(key, "split_local")) ctx().tune_split_local = value;
     else if (!std::strcmp(key, "pull_overlap")) ctx().tune_pull_overlap = value;
     else if (!std::strcmp(key, "lazy_scale")) ctx().tune_lazy_scale = value;
     else if (!std::strcmp(key, "march_red")) ctx().tune_march_red = value;

@@ -60,6 +60,27 @@ __device__ __forceinline__ double look_ahead(const double* __restrict__ z, const
     B = fma(w45.y, z[min(c.t + 6, last) * c.L + c.l], B);
     return B;
 }
+// circulant form: constant weights, windows wrapping around the line (T >= LB2)
+__device__ __forceinline__ double look_back_circ(const double* __restrict__ y, const Sys2& S, const ChunkCtx& c) {
+    double A = 0.0;
+#pragma unroll
+    for (int k = LB2 - 1; k >= 0; k--) {
+        int tm = c.t - 1 - k;
+        tm += (tm < 0) ? c.T : 0;
+        A = fma(S.cwf[k], y[tm * c.L + c.l], A);
+    }
+    return A;
+}
+__device__ __forceinline__ double look_ahead_circ(const double* __restrict__ z, const Sys2& S, const ChunkCtx& c) {
+    double B = 0.0;
+#pragma unroll
+    for (int k = LB2 - 1; k >= 0; k--) {
+        int tp = c.t + 1 + k;
+        tp -= (tp >= c.T) ? c.T : 0;
+        B = fma(S.cwb[k], z[tp * c.L + c.l], B);
+    }
+    return B;
+}
 __device__ __forceinline__ double closure(const double* __restrict__ w, const Sys2& S, const ChunkCtx& c) {
     double xN = 0.0;
     for (int k = 0; k < S.K0; k++) xN += w[k * c.L + c.l];
@@ -74,6 +95,17 @@ __device__ __forceinline__ void solve_one(double (&f)[C], const Sys2& S, const C
     double* y = sm;
     double* z = sm + TL;
     double* w = sm + 2 * TL;
+    if (PER && S.circ) {
+        double ye;
+        local_const(f, S, ye);
+        publish(&y[c.t * c.L + c.l], ye, c);
+        exchange_barrier(c);
+        const double A = look_back_circ(y, S, c);
+        publish(&z[c.t * c.L + c.l], fma(S.cQ[0], A, f[0]), c);
+        exchange_barrier(c);
+        finish_const(f, S, A, look_ahead_circ(z, S, c));
+        return;
+    }
     const double2* cr = reinterpret_cast<const double2*>(S.crec) + c.t * 8;
     const double2 q0pp = ldg2(cr + 6);
     const bool isc = ldg2(cr + 7).x != 0.0;
@@ -106,6 +138,25 @@ __device__ __forceinline__ void solve_two(double (&f0)[C], double (&f1)[C], cons
     double* y1 = sm + 3 * TL;
     double* z1 = sm + 4 * TL;
     double* w1 = sm + 5 * TL;
+    if (PER && S0.circ && S1.circ) {
+        const int me = c.t * c.L + c.l;
+        double ye0, ye1;
+        local_const2(f0, f1, S0, S1, ye0, ye1);
+        publish(&y0[me], ye0, c);
+        publish(&y1[me], ye1, c);
+        exchange_barrier(c);
+        const double A0 = look_back_circ(y0, S0, c), A1 = look_back_circ(y1, S1, c);
+        publish(&z0[me], fma(S0.cQ[0], A0, f0[0]), c);
+        publish(&z1[me], fma(S1.cQ[0], A1, f1[0]), c);
+        exchange_barrier(c);
+        const double B0 = look_ahead_circ(z0, S0, c), B1 = look_ahead_circ(z1, S1, c);
+#pragma unroll
+        for (int j = 0; j < C; j++) {
+            f0[j] = fma(S0.cQ[j], A0, fma(S0.cR[j], B0, f0[j]));
+            f1[j] = fma(S1.cQ[j], A1, fma(S1.cR[j], B1, f1[j]));
+        }
+        return;
+    }
     const double2* cr0 = reinterpret_cast<const double2*>(S0.crec) + c.t * 8;
     const double2* cr1 = reinterpret_cast<const double2*>(S1.crec) + c.t * 8;
     const double2 q0 = ldg2(cr0 + 6), q1 = ldg2(cr1 + 6);

@@ -196,6 +196,18 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
         for (int t = m0; t < T - m1; t++) if (carries56(t)) { m0 = T; m1 = 0; break; }
         s2.K0m = m0; s2.K1m = m1;
     }
+    // circulant form: the factors are flat to 2^-41 over the middle half of the line (then the mean is their fixed point, the
+    // spectral factorisation of the circulant matrix) and the line has room for the window
+    if (periodic && T >= 8) {
+        bool flat = true;
+        for (int i = n / 4; i < n - n / 4 && flat; i++) flat = close(a[i], s2.ca) && close(d[i], s2.cd) && close(g[i], s2.cg);
+        if (flat) {
+            const double af = std::pow(s2.ca, CHUNK), rb = std::pow(s2.cg, CHUNK);
+            double wa = 1.0, wb = 1.0;
+            for (int k = 0; k < LB2; k++) { s2.cwf[k] = wa; s2.cwb[k] = wb; wa *= af; wb *= rb; }
+            s2.circ = (std::fabs(wa) <= std::ldexp(1.0, -80) && std::fabs(wb) <= std::ldexp(1.0, -80)) ? 1 : 0;
+        }
+    }
     const int Tp = (T + 7) / 8 * 8;
     std::vector<double2> tab((size_t)Tp * CHUNK * 4, make_double2(0.0, 0.0));
     std::vector<double> crec((size_t)T * 16, 0.0);
