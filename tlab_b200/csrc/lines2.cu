@@ -104,6 +104,7 @@ __device__ __forceinline__ void solve_one(double (&f)[C], const Sys2& S, const C
         publish(&z[c.t * c.L + c.l], fma(S.cQ[0], A, f[0]), c);
         exchange_barrier(c);
         finish_const(f, S, A, look_ahead_circ(z, S, c));
+        scale_rho(f, S, c.t);
         return;
     }
     const double2* cr = reinterpret_cast<const double2*>(S.crec) + c.t * 8;
@@ -155,6 +156,8 @@ __device__ __forceinline__ void solve_two(double (&f0)[C], double (&f1)[C], cons
             f0[j] = fma(S0.cQ[j], A0, fma(S0.cR[j], B0, f0[j]));
             f1[j] = fma(S1.cQ[j], A1, fma(S1.cR[j], B1, f1[j]));
         }
+        scale_rho(f0, S0, c.t);
+        scale_rho(f1, S1, c.t);
         return;
     }
     const double2* cr0 = reinterpret_cast<const double2*>(S0.crec) + c.t * 8;

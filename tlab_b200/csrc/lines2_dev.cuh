@@ -154,6 +154,12 @@ __device__ __forceinline__ void finish_tab(double (&f)[C], const double2* __rest
         f[j] = v;
     }
 }
+// circulant form: x_j *= rho_j (the column scaling of the reference's matrix, plan.h)
+__device__ __forceinline__ void scale_rho(double (&x)[C], const Sys2& S, int t) {
+    const double* rp = S.rho + ((size_t)(t >> 3) * C) * 8 + (t & 7);
+#pragma unroll
+    for (int j = 0; j < C; j++) x[j] = x[j] * __ldg(rp + j * 8);
+}
 __device__ __forceinline__ void finish_const(double (&f)[C], const Sys2& S, double A, double B) {
 #pragma unroll
     for (int j = 0; j < C; j++) f[j] = fma(S.cQ[j], A, fma(S.cR[j], B, f[j]));

@@ -17,10 +17,12 @@
 // shared memory and 128 threads, four CTAs are resident per SM and are in different phases at any time: loads of one overlap
 // the sweeps and barriers of the others.
 //
-// Circulant systems (periodic directions): the rank-one closure x_N is a sum over the first K0m and last K1m <= MW chunks and
-// is needed by exactly those chunks, so the rounds are visited in the order 1, 2, ..., R-1, 0: x_N is complete when the last
-// round and round 0 are finished.  The look-back of round 1 needs the forward ends of the last LBM chunks of round 0, which a
-// short pre-step computes (re-reading 3 chunks of the line).
+// Circulant systems (periodic directions) are solved in circulant form (plan.h, Sys2::circ: two cyclic first-order recurrences
+// with the converged LU constants -- every chunk is a constant chunk, the windows wrap around the line, no rank-one closure).
+// The rounds are visited in the order 1, 2, ..., R-1, 0, so that round 0 finds its predecessors (round R-1) and round R-1 its
+// successors (round 0) in the rings like any other round; the look-back of round 1 needs the forward ends of the last LBM chunks
+// of round 0, which a short pre-step computes (re-reading 3 chunks of the line), and the chunk starts of round 1 are kept (Zk)
+// for the look-ahead of round 0 at the end.
 //
 // Non-uniform grids: the Jacobian term of the second derivative is a diagonal correction of the solution (see lines2.cu,
 // jacobian_correction), applied when a chunk is finished.
@@ -58,10 +60,10 @@ __global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_const
         double u[C + 6], f[C];
         march_load<PER>(u, pu, pu2, a.scale, w, T, n, st);
         march_rhs<PER, false>(u, f, a.rhs1, w, T);
-        m1.Y[MW * ML + slot] = march_forward_end(f, S1, w);
+        m1.Y[MW * ML + slot] = march_forward_end_const(f, S1);
         if (TWO) {
             march_rhs<PER, true>(u, f, a.rhs2, w, T);
-            m2.Y[MW * ML + slot] = march_forward_end(f, S2, w);
+            m2.Y[MW * ML + slot] = march_forward_end_const(f, S2);
         }
     }
 
@@ -91,8 +93,14 @@ __global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_const
             march_load<PER>(u, pu, pu2, a.scale, t, T, n, st);
             march_rhs<PER, false>(u, f1, a.rhs1, t, T);
             if (TWO) march_rhs<PER, true>(u, f2, a.rhs2, t, T);
-            march_local<PER>(f1, S1, t, ye1, pt1);
-            if (TWO) march_local<PER>(f2, S2, t, ye2, pt2);
+            if (PER) {
+                // circulant form: every chunk is a constant chunk
+                if (TWO) local_const2(f1, f2, S1, S2, ye1, ye2);
+                else local_const(f1, S1, ye1);
+            } else {
+                march_local<PER>(f1, S1, t, ye1, pt1);
+                if (TWO) march_local<PER>(f2, S2, t, ye2, pt2);
+            }
             x01 = f1[0];
             if (TWO) x02 = f2[0];
             // swap with the stash: the previous chunk's solutions come out, this chunk's go in (thread-private slots)
@@ -127,20 +135,16 @@ __global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_const
         double A1 = 0.0, A2 = 0.0;
         if (front) {
             const double* cr1 = S1.crec + (size_t)t * 16;
-            A1 = march_look_back(m1.Y, cr1, h, w, lane);
-            const double z1 = fma(__ldg(cr1 + 12), A1, x01);
+            A1 = PER ? march_look_back_w(m1.Y, S1.cwf[0], S1.cwf[1], S1.cwf[2], h, w, lane) : march_look_back(m1.Y, cr1, h, w, lane);
+            const double z1 = fma(PER ? S1.cQ[0] : __ldg(cr1 + 12), A1, x01);
             m1.Z[(h * MW) * ML + slot] = z1;
             if (PER && rf == 1 && w < LBM) m1.Zk[slot] = z1;
-            if (PER && (t < S1.K0m || t >= T - S1.K1m))
-                m1.Wc[((t < S1.K0m) ? t : MW + t - (T - S1.K1m)) * ML + lane] = fma(__ldg(cr1 + 13), A1, pt1);
             if (TWO) {
                 const double* cr2 = S2.crec + (size_t)t * 16;
-                A2 = march_look_back(m2.Y, cr2, h, w, lane);
-                const double z2 = fma(__ldg(cr2 + 12), A2, x02);
+                A2 = PER ? march_look_back_w(m2.Y, S2.cwf[0], S2.cwf[1], S2.cwf[2], h, w, lane) : march_look_back(m2.Y, cr2, h, w, lane);
+                const double z2 = fma(PER ? S2.cQ[0] : __ldg(cr2 + 12), A2, x02);
                 m2.Z[(h * MW) * ML + slot] = z2;
                 if (PER && rf == 1 && w < LBM) m2.Zk[slot] = z2;
-                if (PER && (t < S2.K0m || t >= T - S2.K1m))
-                    m2.Wc[((t < S2.K0m) ? t : MW + t - (T - S2.K1m)) * ML + lane] = fma(__ldg(cr2 + 13), A2, pt2);
             }
         }
         __syncthreads();
@@ -151,13 +155,17 @@ __global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_const
                 for (int j = 0; j < C; j++) { vv[j] = __ldcs(vp); vp += st; }
             }
             const bool wrap = PER && s == R;       // round 0 of a circulant line is finished last: its successors are the kept z
-            const double B1 = march_look_ahead(m1.Z + ((h ^ 1) * MW) * ML, wrap ? m1.Zk : m1.Z + (h * MW) * ML,
-                                               S1.crec + (size_t)tb * 16, w, lane);
-            march_finish<PER>(o1, S1, m1, tb, T, A1p, B1, lane);
+            const double B1 = PER ? march_look_ahead_w(m1.Z + ((h ^ 1) * MW) * ML, wrap ? m1.Zk : m1.Z + (h * MW) * ML,
+                                                       S1.cwb[0], S1.cwb[1], S1.cwb[2], w, lane)
+                                  : march_look_ahead(m1.Z + ((h ^ 1) * MW) * ML, m1.Z + (h * MW) * ML, S1.crec + (size_t)tb * 16, w, lane);
+            if (PER) { finish_const(o1, S1, A1p, B1); scale_rho(o1, S1, tb); }
+            else march_finish<PER>(o1, S1, m1, tb, T, A1p, B1, lane);
             if (TWO) {
-                const double B2 = march_look_ahead(m2.Z + ((h ^ 1) * MW) * ML, wrap ? m2.Zk : m2.Z + (h * MW) * ML,
-                                                   S2.crec + (size_t)tb * 16, w, lane);
-                march_finish<PER>(o2, S2, m2, tb, T, A2p, B2, lane);
+                const double B2 = PER ? march_look_ahead_w(m2.Z + ((h ^ 1) * MW) * ML, wrap ? m2.Zk : m2.Z + (h * MW) * ML,
+                                                           S2.cwb[0], S2.cwb[1], S2.cwb[2], w, lane)
+                                      : march_look_ahead(m2.Z + ((h ^ 1) * MW) * ML, m2.Z + (h * MW) * ML, S2.crec + (size_t)tb * 16, w, lane);
+                if (PER) { finish_const(o2, S2, A2p, B2); scale_rho(o2, S2, tb); }
+                else march_finish<PER>(o2, S2, m2, tb, T, A2p, B2, lane);
                 if (JAC) {
                     const double* cp = a.cjac + ((size_t)(tb >> 3) * C) * 8 + (tb & 7);
 #pragma unroll
@@ -240,7 +248,8 @@ bool march_eligible(int mode, const Line2Args& a, bool periodic, bool need1, lon
     if (mode == MODE_BURGERS && a.u2 != nullptr) return false;
     if (need1 && mode == MODE_BURGERS && a.cjac == nullptr) return false;
     if (a.nf > 0) return false;
-    (void)periodic;
+    // periodic lines march in circulant form only (constant chunks, wrapping windows; lines2.cu / plan.h, Sys2::circ)
+    if (periodic && (!a.s1.circ || (mode == MODE_BURGERS && !a.s2.circ))) return false;
     return true;
 }
 

@@ -87,6 +87,29 @@ __device__ __forceinline__ double march_forward_end(const double (&f)[C], const 
     return e;
 }
 
+__device__ __forceinline__ double march_forward_end_const(const double (&f)[C], const Sys2& S) {
+    double e = 0.0;
+#pragma unroll
+    for (int j = 0; j < C; j++) e = fma(S.ca, e, f[j]);
+    return e;
+}
+// the same look-back / look-ahead with the constant weights of the circulant form
+__device__ __forceinline__ double march_look_back_w(const double* __restrict__ Y, double w0, double w1, double w2, int h, int w, int lane) {
+    const double* cur = Y + (h * MW) * ML + lane;
+    const double* prv = Y + ((h ^ 1) * MW) * ML + lane;
+    double A = w0 * ((w >= 1) ? cur[(w - 1) * ML] : prv[(MW + w - 1) * ML]);
+    A = fma(w1, (w >= 2) ? cur[(w - 2) * ML] : prv[(MW + w - 2) * ML], A);
+    A = fma(w2, (w >= 3) ? cur[(w - 3) * ML] : prv[(MW + w - 3) * ML], A);
+    return A;
+}
+__device__ __forceinline__ double march_look_ahead_w(const double* __restrict__ own, const double* __restrict__ nxt,
+                                                     double w0, double w1, double w2, int w, int lane) {
+    double B = w0 * ((w + 1 < MW) ? own[(w + 1) * ML + lane] : nxt[(w + 1 - MW) * ML + lane]);
+    B = fma(w1, (w + 2 < MW) ? own[(w + 2) * ML + lane] : nxt[(w + 2 - MW) * ML + lane], B);
+    B = fma(w2, (w + 3 < MW) ? own[(w + 3) * ML + lane] : nxt[(w + 3 - MW) * ML + lane], B);
+    return B;
+}
+
 // A of chunk t = round * MW + w from the forward ends of the LBM chunks before it (this round: half h, previous round: other half)
 __device__ __forceinline__ double march_look_back(const double* __restrict__ Y, const double* __restrict__ cr, int h, int w, int lane) {
     const double* cur = Y + (h * MW) * ML + lane;

@@ -106,7 +106,7 @@ void finish_solve(DevPlan& p, SolveTab& s, std::vector<double>& alpha, std::vect
 // ---- the same system for lines2.cu (see plan.h, Sys2) ------------------------------------------
 void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const std::vector<double>& beta,
                 const std::vector<double>& gamma, const std::vector<double>& delta, const std::vector<double>& pd,
-                const std::vector<double>& pe, double bN, bool periodic) {
+                const std::vector<double>& pe, double bN, bool periodic, const std::vector<double>* sdiag = nullptr) {
     s2 = Sys2();
     const int n = p.n, T = p.T;
     if (p.crem != 0 || p.cbase != CHUNK) return;            // fast kernels need full chunks
@@ -142,10 +142,12 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
     // ~eps*n in its LU factors; the constants are the mean over the middle half of the line and a chunk counts as
     // constant if it deviates by less than 2^-41 (4.5e-13) from them -- far inside the 1e-12 parity tolerance.
     {
+        // means as reference value + mean deviation: a plain running sum of 512 equal numbers is already off by ~1e-14
+        const double ra = a[n / 2], rd = d[n / 2], rg = g[n / 2];
         double sa = 0.0, sd = 0.0, sg = 0.0;
         int cnt = 0;
-        for (int i = n / 4; i < n - n / 4; i++) { sa += a[i]; sd += d[i]; sg += g[i]; cnt++; }
-        s2.ca = sa / cnt; s2.cd = sd / cnt; s2.cg = sg / cnt;
+        for (int i = n / 4; i < n - n / 4; i++) { sa += a[i] - ra; sd += d[i] - rd; sg += g[i] - rg; cnt++; }
+        s2.ca = ra + sa / cnt; s2.cd = rd + sd / cnt; s2.cg = rg + sg / cnt;
     }
     {
         double w = 1.0, q = 0.0;
@@ -196,16 +198,45 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
         for (int t = m0; t < T - m1; t++) if (carries56(t)) { m0 = T; m1 = 0; break; }
         s2.K0m = m0; s2.K1m = m1;
     }
-    // circulant form: the factors are flat to 2^-41 over the middle half of the line (then the mean is their fixed point, the
-    // spectral factorisation of the circulant matrix) and the line has room for the window
-    if (periodic && T >= 8) {
+    // circulant form.  The reference scales the COLUMNS of the constant-coefficient matrix A0 by the Jacobian s_j (dx_j or
+    // dx_j^2, computed from the node positions and therefore carrying round-off noise of relative size eps*j: 5e-13 at the
+    // end of a line of 1024 points, 3.5e-12 at 2048), i.e. x = diag(1/s) A0^-1 f: the forward multipliers of its LU are the
+    // clean constant, d_j = d0 / s_j and g_j = g0 s_{j+1} / s_j.  So the constant-coefficient solution is multiplied point by
+    // point by rho_j = (1/s_j) / mean(1/s) and equals the reference's to round-off for any line length.  Checked here: with
+    // the noise divided out the factors must be flat to 2^-48 over the middle half of the line.
+    if (periodic && T >= 8 && sdiag != nullptr) {
+        const std::vector<double>& sd = *sdiag;
+        const double rm = 1.0 / sd[n / 2];
+        double m = 0.0;
+        int cnt = 0;
+        for (int i = n / 4; i < n - n / 4; i++) { m += 1.0 / sd[i] - rm; cnt++; }
+        m = rm + m / cnt;
+        std::vector<double> rho(n);
+        for (int i = 0; i < n; i++) rho[i] = (1.0 / sd[i]) / m;
+        auto close48 = [](double v, double ref) { return std::fabs(v - ref) <= std::ldexp(std::fabs(ref), -48); };
         bool flat = true;
-        for (int i = n / 4; i < n - n / 4 && flat; i++) flat = close(a[i], s2.ca) && close(d[i], s2.cd) && close(g[i], s2.cg);
+        for (int i = n / 4; i < n - n / 4 && flat; i++)
+            flat = close48(a[i], s2.ca) && close48(d[i] / rho[i], s2.cd) && close48(g[i] * sd[i] / sd[i + 1], s2.cg);
+        if (getenv("TLAB_DEBUG_PLAN")) {
+            double ea = 0, ed = 0, eg = 0;
+            for (int i = n / 4; i < n - n / 4; i++) {
+                ea = std::max(ea, std::fabs(a[i] / s2.ca - 1)); ed = std::max(ed, std::fabs(d[i] / rho[i] / s2.cd - 1));
+                eg = std::max(eg, std::fabs(g[i] * sd[i] / sd[i + 1] / s2.cg - 1));
+            }
+            fprintf(stderr, "[circ] n=%d flat=%d dev a=%g d=%g g=%g (2^-48=%g) sd[mid]=%g\n", n, (int)flat, ea, ed, eg, std::ldexp(1.0, -48), sd[n / 2]);
+        }
         if (flat) {
             const double af = std::pow(s2.ca, CHUNK), rb = std::pow(s2.cg, CHUNK);
             double wa = 1.0, wb = 1.0;
             for (int k = 0; k < LB2; k++) { s2.cwf[k] = wa; s2.cwb[k] = wb; wa *= af; wb *= rb; }
-            s2.circ = (std::fabs(wa) <= std::ldexp(1.0, -80) && std::fabs(wb) <= std::ldexp(1.0, -80)) ? 1 : 0;
+            if (std::fabs(wa) <= std::ldexp(1.0, -80) && std::fabs(wb) <= std::ldexp(1.0, -80)) {
+                const int Tq = (T + 7) / 8 * 8;
+                std::vector<double> rt((size_t)Tq * CHUNK, 1.0);
+                for (int t = 0; t < T; t++)
+                    for (int j = 0; j < CHUNK; j++) rt[((size_t)(t >> 3) * CHUNK + j) * 8 + (t & 7)] = rho[t * CHUNK + j];
+                s2.rho = upload(p, rt);
+                s2.circ = s2.rho ? 1 : 0;
+            }
         }
     }
     const int Tp = (T + 7) / 8 * 8;
@@ -249,7 +280,7 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
 
 // lu columns c0+1..c0+3 (c0+1..c0+5 periodic); rows nmin..nmax active; scale = diffusivity (1 = none)
 void make_solve(DevPlan& p, SolveTab& s, Sys2& s2, const Mat& lu, int c0, int nmin, int nmax, bool periodic, double diff,
-                bool scaled) {
+                bool scaled, const Mat* lhs = nullptr) {
     const int n = p.n;
     std::vector<double> alpha(n, 0.0), beta(n, 1.0), gamma(n, 0.0), delta(n, 1.0), pd(n, 0.0), pe(n, 0.0);
     if (periodic) {
@@ -273,7 +304,12 @@ void make_solve(DevPlan& p, SolveTab& s, Sys2& s2, const Mat& lu, int c0, int nm
             delta[i] = b;
         }
     }
-    build_sys2(p, s2, alpha, beta, gamma, delta, pd, pe, s.bN, periodic);
+    std::vector<double> sdiag;
+    if (periodic && lhs != nullptr) {
+        sdiag.resize(n);
+        for (int r = 1; r <= n; r++) sdiag[r - 1] = (*lhs)(r, 2);      // centre column of the tridiagonal lhs: 1 * s_j
+    }
+    build_sys2(p, s2, alpha, beta, gamma, delta, pd, pe, s.bN, periodic, sdiag.empty() ? nullptr : &sdiag);
     s2.jscale = scaled ? diff : 1.0;
     finish_solve(p, s, alpha, beta, gamma, delta, pd, pe, periodic);
 }
@@ -328,7 +364,7 @@ int devplan_build(DevPlan& p) {
     // first derivative
     if (h.periodic) {
         make_rhs(h.der1, false, BCS_PERIODIC, p.rhs1[0]);
-        make_solve(p, p.lu1[0], p.sys1[0], h.der1.lu, 0, 1, n, true, 1.0, false);
+        make_solve(p, p.lu1[0], p.sys1[0], h.der1.lu, 0, 1, n, true, 1.0, false, &h.der1.lhs);
         for (int b = 1; b < 4; b++) { p.rhs1[b] = p.rhs1[0]; p.lu1[b] = p.lu1[0]; p.sys1[b] = p.sys1[0]; }
     } else {
         for (int ibc = 0; ibc < 4; ibc++) {
@@ -352,7 +388,7 @@ int devplan_build(DevPlan& p) {
     p.lu2.emplace_back();
     p.sys2.clear();
     p.sys2.emplace_back();
-    make_solve(p, p.lu2[0], p.sys2[0], h.der2.lu, 0, 1, n, h.periodic, 1.0, false);
+    make_solve(p, p.lu2[0], p.sys2[0], h.der2.lu, 0, 1, n, h.periodic, 1.0, false, &h.der2.lhs);
     if (p.need_1der) {
         std::vector<double> r(3 * (size_t)n);
         for (int i = 1; i <= n; i++) for (int j = 1; j <= 3; j++) r[3 * (size_t)(i - 1) + (j - 1)] = h.der2.rhs(i, h.der2.ndr + j);
@@ -404,7 +440,7 @@ int devplan_add_diffusion(DevPlan& p, double diff) {
     if (p.n <= 1) return 0;
     p.lu2.emplace_back();
     p.sys2.emplace_back();
-    make_solve(p, p.lu2.back(), p.sys2.back(), p.h.der2.lu, 0, 1, p.n, p.h.periodic, diff, true);
+    make_solve(p, p.lu2.back(), p.sys2.back(), p.h.der2.lu, 0, 1, p.n, p.h.periodic, diff, true, &p.h.der2.lhs);
     return (int)p.lu2.size() - 1;
 }
 

@@ -58,11 +58,14 @@ struct Sys2 {
     double cQ[CHUNK], cR[CHUNK];           // constant-chunk correction vectors
     int K0 = 0, K1 = 0;              // circulant: chunks [0,K0) and [T-K1,T) contribute to x_N
     int K0m = 0, K1m = 0;            // the same with a threshold of 2^-56 instead of 2^-80 (march.cu)
-    // circulant form (periodic, hence uniform, direction with converged LU factors): the circulant matrix is EXACTLY
-    // (I - ca P) diag(1/cd)^-1 (I - cg P^T) with P the cyclic shift, so every chunk is a constant chunk, the windows wrap
-    // around the line and there is no rank-one closure (no tables, no x_N): wf[k] = (ca^16)^k, wb[k] = (cg^16)^k
+    // circulant form (periodic, hence uniform, direction): the reference's matrix is A0 diag(s) with A0 the constant-coefficient
+    // circulant matrix and s_j the Jacobian factor of column j, and A0 factorises EXACTLY into two cyclic first-order recurrences
+    // with the converged LU constants (ca, cd, cg).  So every chunk is a constant chunk, the windows wrap around the line, there
+    // is no rank-one closure (no tables, no x_N), and the solution is multiplied point by point by rho_j = (1/s_j) / mean(1/s)
+    // (the round-off noise of the reference's Jacobian, see plan.cu): wf[k] = (ca^16)^k, wb[k] = (cg^16)^k
     int circ = 0;
     double cwf[LB2], cwb[LB2];
+    const double* rho = nullptr;     // item (t, j) at ((t>>3)*CHUNK + j)*8 + (t&7)
     double jscale = 1.0;             // factor of the solution (the diffusivity of a Burgers system): scales the Jacobian correction
     int ok = 0;                      // 0: look-back window too long for the fast kernels
     int march_ok = 0;                // 1: a window of 3 chunks suffices (dropped weights < 2^-64) and the closure chunks fit one round
