@@ -109,7 +109,11 @@ __device__ __forceinline__ void solve_one(double (&f)[C], const Sys2& S, const C
     }
     const double2* cr = reinterpret_cast<const double2*>(S.crec) + c.t * 8;
     const double2 q0pp = ldg2(cr + 6);
-    const bool isc = ldg2(cr + 7).x != 0.0;
+    const double2 fl = ldg2(cr + 7);
+    const bool isc = fl.x != 0.0;
+    // non-periodic constant chunk in the unscaled variable w = x / rho (plan.cu): its chunk start goes out as x, the inflow B
+    // comes back as w, the solution is scaled at the end
+    const bool unsc = !PER && isc && S.rho != nullptr;
     const double2* tp = tab_ptr(S, c.t);
     double yend, part = 0.0;
     if (isc) local_const(f, S, yend);
@@ -117,12 +121,14 @@ __device__ __forceinline__ void solve_one(double (&f)[C], const Sys2& S, const C
     publish(&y[c.t * c.L + c.l], yend, c);
     exchange_barrier(c);
     const double A = look_back(y, cr, c);
-    publish(&z[c.t * c.L + c.l], fma(q0pp.x, A, f[0]), c);
+    publish(&z[c.t * c.L + c.l], fma(q0pp.x, A, unsc ? f[0] * rho_first(S, c.t) : f[0]), c);
     if (PER) publish(&w[c.t * c.L + c.l], fma(q0pp.y, A, part), c);
     exchange_barrier(c);
     const double B = look_ahead(z, cr, c);
-    if (isc) finish_const(f, S, A, B);
-    else {
+    if (isc) {
+        finish_const(f, S, A, unsc ? B * fl.y : B);
+        if (unsc) scale_rho(f, S, c.t);
+    } else {
         const double xN = PER ? closure(w, S, c) : 0.0;
         finish_tab<PER>(f, tp, A, B, xN);
     }
@@ -163,7 +169,9 @@ __device__ __forceinline__ void solve_two(double (&f0)[C], double (&f1)[C], cons
     const double2* cr0 = reinterpret_cast<const double2*>(S0.crec) + c.t * 8;
     const double2* cr1 = reinterpret_cast<const double2*>(S1.crec) + c.t * 8;
     const double2 q0 = ldg2(cr0 + 6), q1 = ldg2(cr1 + 6);
-    const bool c0 = ldg2(cr0 + 7).x != 0.0, c1 = ldg2(cr1 + 7).x != 0.0;
+    const double2 fl0 = ldg2(cr0 + 7), fl1 = ldg2(cr1 + 7);
+    const bool c0 = fl0.x != 0.0, c1 = fl1.x != 0.0;
+    const bool u0 = !PER && c0 && S0.rho != nullptr, u1 = !PER && c1 && S1.rho != nullptr;      // see solve_one
     const double2* tp0 = tab_ptr(S0, c.t);
     const double2* tp1 = tab_ptr(S1, c.t);
     double ye0, ye1, p0 = 0.0, p1 = 0.0;
@@ -177,11 +185,13 @@ __device__ __forceinline__ void solve_two(double (&f0)[C], double (&f1)[C], cons
     publish(&y1[me], ye1, c);
     exchange_barrier(c);
     const double A0 = look_back(y0, cr0, c), A1 = look_back(y1, cr1, c);
-    publish(&z0[me], fma(q0.x, A0, f0[0]), c);
-    publish(&z1[me], fma(q1.x, A1, f1[0]), c);
+    publish(&z0[me], fma(q0.x, A0, u0 ? f0[0] * rho_first(S0, c.t) : f0[0]), c);
+    publish(&z1[me], fma(q1.x, A1, u1 ? f1[0] * rho_first(S1, c.t) : f1[0]), c);
     if (PER) { publish(&w0[me], fma(q0.y, A0, p0), c); publish(&w1[me], fma(q1.y, A1, p1), c); }
     exchange_barrier(c);
-    const double B0 = look_ahead(z0, cr0, c), B1 = look_ahead(z1, cr1, c);
+    double B0 = look_ahead(z0, cr0, c), B1 = look_ahead(z1, cr1, c);
+    if (u0) B0 *= fl0.y;
+    if (u1) B1 *= fl1.y;
     if (c0 && c1) {
 #pragma unroll
         for (int j = 0; j < C; j++) {
@@ -194,6 +204,8 @@ __device__ __forceinline__ void solve_two(double (&f0)[C], double (&f1)[C], cons
         if (c1) finish_const(f1, S1, A1, B1);
         else finish_tab<PER>(f1, tp1, A1, B1, PER ? closure(w1, S1, c) : 0.0);
     }
+    if (u0) scale_rho(f0, S0, c.t);
+    if (u1) scale_rho(f1, S1, c.t);
 }
 
 // Jacobian term of the second derivative on non-uniform grids (fdm_derivative.f90:437-440, `f2 += rhs_d1 * du` before the

@@ -160,6 +160,7 @@ __device__ __forceinline__ void scale_rho(double (&x)[C], const Sys2& S, int t) 
 #pragma unroll
     for (int j = 0; j < C; j++) x[j] = x[j] * __ldg(rp + j * 8);
 }
+__device__ __forceinline__ double rho_first(const Sys2& S, int t) { return __ldg(S.rho + ((size_t)(t >> 3) * C) * 8 + (t & 7)); }
 __device__ __forceinline__ void finish_const(double (&f)[C], const Sys2& S, double A, double B) {
 #pragma unroll
     for (int j = 0; j < C; j++) f[j] = fma(S.cQ[j], A, fma(S.cR[j], B, f[j]));

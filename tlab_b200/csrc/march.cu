@@ -103,6 +103,11 @@ __global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_const
             }
             x01 = f1[0];
             if (TWO) x02 = f2[0];
+            if (!PER) {
+                // constant chunks of a non-periodic direction work in the unscaled variable (plan.cu): the chunk start goes out as x
+                if (S1.rho != nullptr && __ldg(S1.crec + (size_t)t * 16 + 14) != 0.0) x01 *= rho_first(S1, t);
+                if (TWO && S2.rho != nullptr && __ldg(S2.crec + (size_t)t * 16 + 14) != 0.0) x02 *= rho_first(S2, t);
+            }
             // swap with the stash: the previous chunk's solutions come out, this chunk's go in (thread-private slots)
 #pragma unroll
             for (int j = 0; j < C; j++) {

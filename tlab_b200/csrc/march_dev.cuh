@@ -132,7 +132,13 @@ __device__ __forceinline__ double march_look_ahead(const double* __restrict__ ow
 template <bool PER>
 __device__ __forceinline__ void march_finish(double (&x)[C], const Sys2& S, const MarchSm& m, int t, int T, double A, double B, int lane) {
     if (__ldg(S.crec + (size_t)t * 16 + 14) != 0.0) {
-        finish_const(x, S, A, B);
+        if (!PER && S.rho != nullptr) {
+            // unscaled constant chunk of a non-periodic direction (plan.cu): B as w, the solution scaled by rho
+            finish_const(x, S, A, B * __ldg(S.crec + (size_t)t * 16 + 15));
+            scale_rho(x, S, t);
+        } else {
+            finish_const(x, S, A, B);
+        }
     } else {
         double xN = 0.0;
         if (PER) {

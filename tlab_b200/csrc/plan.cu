@@ -141,7 +141,19 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
     // builds the Jacobian by differentiating the node positions, which leaves round-off noise of relative size
     // ~eps*n in its LU factors; the constants are the mean over the middle half of the line and a chunk counts as
     // constant if it deviates by less than 2^-41 (4.5e-13) from them -- far inside the 1e-12 parity tolerance.
-    {
+    // Non-periodic directions, any grid: the reference's matrix is A0 diag(s) with A0 the constant-coefficient matrix of the scheme
+    // (boundary closures in its first and last rows) and s_j the Jacobian factor of column j (dx_j or dx_j^2: stretched grids,
+    // or the round-off noise of a uniform one).  Its LU therefore has the CLEAN forward multipliers of A0, d_j = d0_j / s_j and
+    // g_j = g0_j s_{j+1} / s_j: away from the walls the factors of A0 have converged, and a chunk is a constant chunk in the
+    // variable w_j = x_j / rho_j, rho_j = s_m / s_j (m = n/2 the reference row).  Only the chunks next to the walls keep tables.
+    const bool unscaled = !periodic && sdiag != nullptr && n >= 4 * CHUNK;
+    std::vector<double> rho(n, 1.0);
+    if (unscaled) {
+        const std::vector<double>& sd = *sdiag;
+        const int m = n / 2;
+        s2.ca = a[m]; s2.cd = d[m]; s2.cg = g[m] * sd[m] / sd[m + 1];
+        for (int i = 0; i < n; i++) rho[i] = sd[m] / sd[i];
+    } else {
         // means as reference value + mean deviation: a plain running sum of 512 equal numbers is already off by ~1e-14
         const double ra = a[n / 2], rd = d[n / 2], rg = g[n / 2];
         double sa = 0.0, sd = 0.0, sg = 0.0;
@@ -159,11 +171,17 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
     double pmax = 0.0, smax = 0.0;
     for (int i = 0; i < n; i++) { pmax = std::max(pmax, std::fabs(pp[i])); smax = std::max(smax, std::fabs(S[i])); }
     auto close = [](double v, double ref) { return std::fabs(v - ref) <= std::ldexp(std::fabs(ref), -41); };
+    auto close48 = [](double v, double ref) { return std::fabs(v - ref) <= std::ldexp(std::fabs(ref), -48); };
     std::vector<int> isc(T, 0);
     for (int t = 0; t < T; t++) {
         bool c = true;
         for (int j = 0; j < CHUNK && c; j++) {
             const int i = t * CHUNK + j;
+            if (unscaled) {
+                const std::vector<double>& sd = *sdiag;
+                c = i + 1 < n && close48(a[i], s2.ca) && close48(d[i] / rho[i], s2.cd) && close48(g[i] * sd[i] / sd[i + 1], s2.cg);
+                continue;
+            }
             c = close(a[i], s2.ca) && close(d[i], s2.cd) && close(g[i], s2.cg);
             if (periodic && c) c = std::fabs(pp[i]) <= std::ldexp(pmax, -80) && std::fabs(S[i]) <= std::ldexp(smax, -80);
         }
@@ -211,9 +229,7 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
         int cnt = 0;
         for (int i = n / 4; i < n - n / 4; i++) { m += 1.0 / sd[i] - rm; cnt++; }
         m = rm + m / cnt;
-        std::vector<double> rho(n);
         for (int i = 0; i < n; i++) rho[i] = (1.0 / sd[i]) / m;
-        auto close48 = [](double v, double ref) { return std::fabs(v - ref) <= std::ldexp(std::fabs(ref), -48); };
         bool flat = true;
         for (int i = n / 4; i < n - n / 4 && flat; i++)
             flat = close48(a[i], s2.ca) && close48(d[i] / rho[i], s2.cd) && close48(g[i] * sd[i] / sd[i + 1], s2.cg);
@@ -262,7 +278,8 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
             c[LB2 + k - 1] = (t + k <= T - 1) ? w : 0.0;
             if (t + k <= T - 1) w *= Rb[t + k];
         }
-        c[12] = Q0[t]; c[13] = PP[t]; c[14] = isc[t] ? 1.0 : 0.0; c[15] = 0.0;
+        c[12] = Q0[t]; c[13] = PP[t]; c[14] = isc[t] ? 1.0 : 0.0;
+        c[15] = (unscaled && t < T - 1) ? 1.0 / rho[(t + 1) * CHUNK] : 1.0;      // B in the variable w of a constant chunk
     }
     if (getenv("TLAB_DEBUG_PLAN")) {
         for (int i : {0, 1, 2, 16, 40, 80, n / 2, n / 2 + 1, n - 80, n - 40, n - 3, n - 2, n - 1})
@@ -271,6 +288,20 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
         for (int t = 0; t < T; t++) nc += isc[t];
         fprintf(stderr, "[sys2] n=%d T=%d periodic=%d Wf=%d Wb=%d const_chunks=%d K0=%d K1=%d ca=%g cd=%g cg=%g Af=%g Rb=%g\n", n, T,
                 (int)periodic, window(Af, true), window(Rb, false), nc, s2.K0, s2.K1, s2.ca, s2.cd, s2.cg, Af[T / 2], Rb[T / 2]);
+    }
+    if (unscaled) {
+        int nc = 0;
+        for (int t = 0; t < T; t++) nc += isc[t];
+        if (nc > 0) {
+            const int Tq = (T + 7) / 8 * 8;
+            std::vector<double> rt((size_t)Tq * CHUNK, 1.0);
+            for (int t = 0; t < T; t++)
+                for (int j = 0; j < CHUNK; j++) rt[((size_t)(t >> 3) * CHUNK + j) * 8 + (t & 7)] = rho[t * CHUNK + j];
+            s2.rho = upload(p, rt);
+            if (!s2.rho) return;
+        } else {
+            for (int t = 0; t < T; t++) crec[(size_t)t * 16 + 15] = 1.0;
+        }
     }
     s2.march_ok = march_sys_ok(crec, T, s2.K0m, s2.K1m, periodic) ? 1 : 0;
     s2.tab = upload_t(p, tab);
@@ -305,7 +336,7 @@ void make_solve(DevPlan& p, SolveTab& s, Sys2& s2, const Mat& lu, int c0, int nm
         }
     }
     std::vector<double> sdiag;
-    if (periodic && lhs != nullptr) {
+    if (lhs != nullptr) {
         sdiag.resize(n);
         for (int r = 1; r <= n; r++) sdiag[r - 1] = (*lhs)(r, 2);      // centre column of the tridiagonal lhs: 1 * s_j
     }
@@ -372,7 +403,7 @@ int devplan_build(DevPlan& p) {
             int nmin = 1, nmax = n;
             if (ibc == BCS_ND || ibc == BCS_NN) nmin++;
             if (ibc == BCS_DN || ibc == BCS_NN) nmax--;
-            make_solve(p, p.lu1[ibc], p.sys1[ibc], h.der1.lu, ibc * 5, nmin, nmax, false, 1.0, false);
+            make_solve(p, p.lu1[ibc], p.sys1[ibc], h.der1.lu, ibc * 5, nmin, nmax, false, 1.0, false, &h.der1.lhs);
         }
     }
     // second derivative
