@@ -206,15 +206,17 @@ def test_step_through_the_tma_kernels(cuda, shape, lines):
     assert rel_l2(g.get("s1"), o.s[0]) <= 1e-11
 
 
-@pytest.mark.parametrize("march", [1, 0])
+@pytest.mark.parametrize("march,circ", [(1, 1), (0, 1), (1, 0)])
 @pytest.mark.parametrize("shape,pv", [((32, 32, 256), 2), ((16, 32, 192), 2), ((16, 32, 512), 4), ((64, 16, 384), 3),
                                       ((32, 16, 512), 2), ((32, 32, 768), 3)])
-def test_split_z_operators_on_virtual_slabs(cuda, shape, pv, march):
+def test_split_z_operators_on_virtual_slabs(cuda, shape, pv, march, circ):
     """The split-z kernels of splitz.cu (z operators of a z-split domain without transposes: halo planes and chunk ends
     exchanged between neighbouring slabs) run over pv virtual slabs of one field on one GPU: the RK step must agree with
     the oracle, and with the whole-line kernels to round-off.  Slab thicknesses 96 (the minimum: 6 chunks) to 256 planes; with
     march = 1 the finishing phase runs as a march over panels of 32 lines (splitz_march_kernel) when the slab holds a multiple
-    of 4 chunks, seeded from the neighbours' chunk ends."""
+    of 4 chunks, seeded from the neighbours' chunk ends -- in circulant form (circ = 1: constant chunks, windows wrapping from rank
+    to rank, every rank the same work) or with the rank-one closure of the reference's periodic solver (circ = 0: closure terms
+    traded between the first and the last rank)."""
     import ctypes
     from tlab_b200 import lib as tl
     L = tl.load()
@@ -228,11 +230,13 @@ def test_split_z_operators_on_virtual_slabs(cuda, shape, pv, march):
     try:
         tl.check(L.tlab_gpu_set_tuning(b"split_emulate", pv))
         tl.check(L.tlab_gpu_set_tuning(b"march", march))
+        tl.check(L.tlab_gpu_set_tuning(b"circ", circ))
         _, g2 = _pair(*shape, "tanh")
         g2.runge_kutta(1e-3)
     finally:
         tl.check(L.tlab_gpu_set_tuning(b"split_emulate", 0))
         tl.check(L.tlab_gpu_set_tuning(b"march", 1))
+        tl.check(L.tlab_gpu_set_tuning(b"circ", 1))
     after, mafter = ctypes.c_longlong(0), ctypes.c_longlong(0)
     tl.check(L.tlab_gpu_get_counter(b"splitz_ops", ctypes.byref(after)))
     tl.check(L.tlab_gpu_get_counter(b"splitz_march_ops", ctypes.byref(mafter)))

@@ -36,40 +36,20 @@ namespace {
 // MODE_P1: out = d/ds (u [+ scale u2]), MODE_BURGERS: out = d2 - vel * d1 (d2 from the diffusivity-scaled system a.s2);
 // accumulate = +1 / -1 adds to / subtracts from out.  JAC: non-uniform direction (Jacobian correction of d2).
 // RED: the accumulation is a fire-and-forget red.global.add.f64 (one IEEE addition per element either way: same bits).
-template <int MODE, bool PER, bool JAC, bool RED, int MINB, bool VPRE>
-__global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_constant__ Line2Args a) {
+// One step of the march: the chunks of round rf enter (loads, right-hand sides, zero-inflow sweeps, ends into the rings) and
+// the chunks of the round that entered one step earlier are finished.  GF / GB = false: peeled variants for a non-periodic
+// direction whose entering / finishing round holds interior constant chunks only (no wall rows, no tables, no dispatch on the
+// chunk records: what keeps the generic body above 128 registers).
+template <int MODE, bool PER, bool JAC, bool RED, bool VPRE, bool GF, bool GB>
+__device__ __forceinline__ void march_step(const Line2Args& a, const MarchSm& m1, const MarchSm& m2, const double* __restrict__ pu,
+                                           const double* __restrict__ pu2, long long base, int lane, int w, int slot, int s,
+                                           double (&o1)[C], double (&o2)[C], double& A1p, double& A2p) {
     constexpr bool TWO = (MODE == MODE_BURGERS);
-    extern __shared__ double sm[];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int T = a.T, n = a.n, R = T / MW;
     const long long st = a.stride;
-    const long long base = (long long)blockIdx.y * a.outer_stride + (long long)blockIdx.x * ML + lane;
     const Sys2& S1 = a.s1;
     const Sys2& S2 = a.s2;
-    const MarchSm m1(sm), m2(sm + M_SYS);
-    // stale ring slots are read with zero weights: they must hold finite numbers
-    for (int i = threadIdx.x; i < (TWO ? 2 : 1) * M_SYS; i += blockDim.x) sm[i] = 0.0;
-    __syncthreads();
-
-    const double* __restrict__ pu = a.u + base;
-    const double* __restrict__ pu2 = (a.u2 != nullptr) ? a.u2 + base : nullptr;
-    const int slot = w * ML + lane;                // this thread's place in a ring half / its stash column
-
-    if (PER && w >= MW - LBM) {
-        // pre-step: forward ends of chunks MW-LBM .. MW-1 of round 0, as seen by the look-back of round 1 (half 1 = "previous")
-        double u[C + 6], f[C];
-        march_load<PER>(u, pu, pu2, a.scale, w, T, n, st);
-        march_rhs<PER, false>(u, f, a.rhs1, w, T);
-        m1.Y[MW * ML + slot] = march_forward_end_const(f, S1);
-        if (TWO) {
-            march_rhs<PER, true>(u, f, a.rhs2, w, T);
-            m2.Y[MW * ML + slot] = march_forward_end_const(f, S2);
-        }
-    }
-
-    double o1[C], o2[C];                           // zero-inflow solutions of the chunk this thread handled one step earlier
-    double A1p = 0.0, A2p = 0.0;                   // and its A
-    for (int s = 0; s <= R; s++) {
+    {
         const bool front = s < R, back = s > 0;
         const int rf = PER ? ((s + 1 == R) ? 0 : s + 1) : s;          // chunk-order round entering the pipeline
         const int rb = PER ? ((s == R) ? 0 : s) : s - 1;              // round being finished (entered one step earlier)
@@ -90,10 +70,17 @@ __global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_const
         }
         if (front) {
             double u[C + 6], f1[C], f2[C];
-            march_load<PER>(u, pu, pu2, a.scale, t, T, n, st);
-            march_rhs<PER, false>(u, f1, a.rhs1, t, T);
-            if (TWO) march_rhs<PER, true>(u, f2, a.rhs2, t, T);
-            if (PER) {
+            if (!PER && !GF) {
+                // peeled interior round of a non-periodic direction: halos on both sides, no wall rows, constant chunks
+                march_load<true>(u, pu, pu2, a.scale, t, T, n, st);
+                rhs_interior<false>(u, f1, a.rhs1);
+                if (TWO) rhs_interior<true>(u, f2, a.rhs2);
+            } else {
+                march_load<PER>(u, pu, pu2, a.scale, t, T, n, st);
+                march_rhs<PER, false>(u, f1, a.rhs1, t, T);
+                if (TWO) march_rhs<PER, true>(u, f2, a.rhs2, t, T);
+            }
+            if (PER || !GF) {
                 // circulant form: every chunk is a constant chunk
                 if (TWO) local_const2(f1, f2, S1, S2, ye1, ye2);
                 else local_const(f1, S1, ye1);
@@ -103,7 +90,10 @@ __global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_const
             }
             x01 = f1[0];
             if (TWO) x02 = f2[0];
-            if (!PER) {
+            if (!PER && !GF) {
+                x01 *= rho_first(S1, t);
+                if (TWO) x02 *= rho_first(S2, t);
+            } else if (!PER) {
                 // constant chunks of a non-periodic direction work in the unscaled variable (plan.cu): the chunk start goes out as x
                 if (S1.rho != nullptr && __ldg(S1.crec + (size_t)t * 16 + 14) != 0.0) x01 *= rho_first(S1, t);
                 if (TWO && S2.rho != nullptr && __ldg(S2.crec + (size_t)t * 16 + 14) != 0.0) x02 *= rho_first(S2, t);
@@ -164,12 +154,14 @@ __global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_const
                                                        S1.cwb[0], S1.cwb[1], S1.cwb[2], w, lane)
                                   : march_look_ahead(m1.Z + ((h ^ 1) * MW) * ML, m1.Z + (h * MW) * ML, S1.crec + (size_t)tb * 16, w, lane);
             if (PER) { finish_const(o1, S1, A1p, B1); scale_rho(o1, S1, tb); }
+            else if (!GB) { finish_const(o1, S1, A1p, B1 * __ldg(S1.crec + (size_t)tb * 16 + 15)); scale_rho(o1, S1, tb); }
             else march_finish<PER>(o1, S1, m1, tb, T, A1p, B1, lane);
             if (TWO) {
                 const double B2 = PER ? march_look_ahead_w(m2.Z + ((h ^ 1) * MW) * ML, wrap ? m2.Zk : m2.Z + (h * MW) * ML,
                                                            S2.cwb[0], S2.cwb[1], S2.cwb[2], w, lane)
                                       : march_look_ahead(m2.Z + ((h ^ 1) * MW) * ML, m2.Z + (h * MW) * ML, S2.crec + (size_t)tb * 16, w, lane);
                 if (PER) { finish_const(o2, S2, A2p, B2); scale_rho(o2, S2, tb); }
+                else if (!GB) { finish_const(o2, S2, A2p, B2 * __ldg(S2.crec + (size_t)tb * 16 + 15)); scale_rho(o2, S2, tb); }
                 else march_finish<PER>(o2, S2, m2, tb, T, A2p, B2, lane);
                 if (JAC) {
                     const double* cp = a.cjac + ((size_t)(tb >> 3) * C) * 8 + (tb & 7);
@@ -197,6 +189,53 @@ __global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_const
         }
         A1p = A1;
         A2p = A2;
+    }
+}
+
+template <int MODE, bool PER, bool JAC, bool RED, int MINB, bool VPRE>
+__global__ void __launch_bounds__(MW * ML, MINB) lines2_march(const __grid_constant__ Line2Args a) {
+    constexpr bool TWO = (MODE == MODE_BURGERS);
+    extern __shared__ double sm[];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int T = a.T, n = a.n, R = T / MW;
+    const long long st = a.stride;
+    const long long base = (long long)blockIdx.y * a.outer_stride + (long long)blockIdx.x * ML + lane;
+    const Sys2& S1 = a.s1;
+    const Sys2& S2 = a.s2;
+    const MarchSm m1(sm), m2(sm + M_SYS);
+    // stale ring slots are read with zero weights: they must hold finite numbers
+    for (int i = threadIdx.x; i < (TWO ? 2 : 1) * M_SYS; i += blockDim.x) sm[i] = 0.0;
+    __syncthreads();
+
+    const double* __restrict__ pu = a.u + base;
+    const double* __restrict__ pu2 = (a.u2 != nullptr) ? a.u2 + base : nullptr;
+    const int slot = w * ML + lane;                // this thread's place in a ring half / its stash column
+
+    if (PER && w >= MW - LBM) {
+        // pre-step: forward ends of chunks MW-LBM .. MW-1 of round 0, as seen by the look-back of round 1 (half 1 = "previous")
+        double u[C + 6], f[C];
+        march_load<PER>(u, pu, pu2, a.scale, w, T, n, st);
+        march_rhs<PER, false>(u, f, a.rhs1, w, T);
+        m1.Y[MW * ML + slot] = march_forward_end_const(f, S1);
+        if (TWO) {
+            march_rhs<PER, true>(u, f, a.rhs2, w, T);
+            m2.Y[MW * ML + slot] = march_forward_end_const(f, S2);
+        }
+    }
+
+    double o1[C], o2[C];                           // zero-inflow solutions of the chunk this thread handled one step earlier
+    double A1p = 0.0, A2p = 0.0;                   // and its A
+    if (!PER && a.march_peel) {
+        // rounds 1 .. R-2 hold interior constant chunks only (checked on the host, R >= 3)
+        march_step<MODE, PER, JAC, RED, VPRE, true, true>(a, m1, m2, pu, pu2, base, lane, w, slot, 0, o1, o2, A1p, A2p);
+        march_step<MODE, PER, JAC, RED, VPRE, false, true>(a, m1, m2, pu, pu2, base, lane, w, slot, 1, o1, o2, A1p, A2p);
+        for (int s = 2; s <= R - 2; s++)
+            march_step<MODE, PER, JAC, RED, VPRE, false, false>(a, m1, m2, pu, pu2, base, lane, w, slot, s, o1, o2, A1p, A2p);
+        march_step<MODE, PER, JAC, RED, VPRE, true, false>(a, m1, m2, pu, pu2, base, lane, w, slot, R - 1, o1, o2, A1p, A2p);
+        march_step<MODE, PER, JAC, RED, VPRE, true, true>(a, m1, m2, pu, pu2, base, lane, w, slot, R, o1, o2, A1p, A2p);
+    } else {
+        for (int s = 0; s <= R; s++)
+            march_step<MODE, PER, JAC, RED, VPRE, true, true>(a, m1, m2, pu, pu2, base, lane, w, slot, s, o1, o2, A1p, A2p);
     }
 }
 

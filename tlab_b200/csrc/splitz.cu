@@ -302,7 +302,9 @@ __host__ __device__ inline long long e_next(int t, int s, int c) { return (long 
 __host__ __device__ inline long long e_prev(int t, int s) { return (long long)OFF_EPREV + (long long)(t * 2 + s); }
 __host__ __device__ inline long long e_tail(int ti, int s, int c) { return (long long)OFF_TAIL + (long long)(ti * 2 + s) * 2 + c; }
 
-template <int MODE>
+// CIRC: circulant form (plan.h, Sys2::circ): constant chunks everywhere, constant window weights wrapping from rank to rank, no
+// closure terms (every rank does the same work), the solution scaled by rho at the end.
+template <int MODE, bool CIRC>
 __global__ void __launch_bounds__(MW * ML, 4) splitz_march_kernel(const __grid_constant__ SplitArgs a) {
     constexpr bool TWO = (MODE == MODE_BURGERS);
     constexpr int NS = TWO ? 2 : 1;
@@ -327,7 +329,7 @@ __global__ void __launch_bounds__(MW * ML, 4) splitz_march_kernel(const __grid_c
         }
     }
     // ---- closure terms of the other end of the line (lines2.cu: x_N = sum over the first K0 and the last K1 chunks)
-    if (w == 3) {
+    if (!CIRC && w == 3) {
 #pragma unroll
         for (int s = 0; s < NS; s++) {
             const Sys2& S = s ? S2 : S1;
@@ -396,8 +398,13 @@ __global__ void __launch_bounds__(MW * ML, 4) splitz_march_kernel(const __grid_c
             }
             rhs_interior<false>(u, f1, a.rhs1);
             if (TWO) rhs_interior<true>(u, f2, a.rhs2);
-            march_local<true>(f1, S1, tg, ye1, pt1);
-            if (TWO) march_local<true>(f2, S2, tg, ye2, pt2);
+            if (CIRC) {
+                if (TWO) local_const2(f1, f2, S1, S2, ye1, ye2);
+                else local_const(f1, S1, ye1);
+            } else {
+                march_local<true>(f1, S1, tg, ye1, pt1);
+                if (TWO) march_local<true>(f2, S2, tg, ye2, pt2);
+            }
             x01 = f1[0];
             if (TWO) x02 = f2[0];
 #pragma unroll
@@ -428,10 +435,12 @@ __global__ void __launch_bounds__(MW * ML, 4) splitz_march_kernel(const __grid_c
                 const Sys2& S = q ? S2 : S1;
                 const MarchSm& m = q ? m2 : m1;
                 const double* cr = S.crec + (size_t)tg * 16;
-                const double A = march_look_back(m.Y, cr, h, w, lane);
-                m.Z[(h * MW) * ML + slot] = fma(__ldg(cr + 12), A, q ? x02 : x01);
-                if (tg < S.K0m) m.Wc[tg * ML + lane] = fma(__ldg(cr + 13), A, q ? pt2 : pt1);
-                if (tg >= T - S.K1m) m.Wc[(MW + tg - (T - S.K1m)) * ML + lane] = fma(__ldg(cr + 13), A, q ? pt2 : pt1);
+                const double A = CIRC ? march_look_back_w(m.Y, S.cwf[0], S.cwf[1], S.cwf[2], h, w, lane) : march_look_back(m.Y, cr, h, w, lane);
+                m.Z[(h * MW) * ML + slot] = fma(CIRC ? S.cQ[0] : __ldg(cr + 12), A, q ? x02 : x01);
+                if (!CIRC) {
+                    if (tg < S.K0m) m.Wc[tg * ML + lane] = fma(__ldg(cr + 13), A, q ? pt2 : pt1);
+                    if (tg >= T - S.K1m) m.Wc[(MW + tg - (T - S.K1m)) * ML + lane] = fma(__ldg(cr + 13), A, q ? pt2 : pt1);
+                }
                 if (q) A2 = A; else A1 = A;
             }
             if (s == R - 1 && w < LBM) {
@@ -443,16 +452,16 @@ __global__ void __launch_bounds__(MW * ML, 4) splitz_march_kernel(const __grid_c
                     const Sys2& S = q ? S2 : S1;
                     const MarchSm& m = q ? m2 : m1;
                     double z = 0.0;
-                    if (tgn < T) {
-                        const double* cr = S.crec + (size_t)tgn * 16;
+                    if (CIRC || tgn < T) {
+                        const double* cr = S.crec + (size_t)(CIRC ? 0 : tgn) * 16;
                         auto yof = [&](int k) {            // forward end of slab chunk Tl + w - k
                             const int j = w - k;           // >= 0: the next rank's chunk j; < 0: this rank's chunk Tl + j (last round, half h)
                             return (j >= 0) ? mine[e_next(j, q, 0) * nxy] : m.Y[(h * MW + MW + j) * ML + lane];
                         };
-                        double A = __ldg(cr + 0) * yof(1);
-                        A = fma(__ldg(cr + 1), yof(2), A);
-                        A = fma(__ldg(cr + 2), yof(3), A);
-                        z = fma(__ldg(cr + 12), A, mine[e_next(w, q, 1) * nxy]);
+                        double A = (CIRC ? S.cwf[0] : __ldg(cr + 0)) * yof(1);
+                        A = fma(CIRC ? S.cwf[1] : __ldg(cr + 1), yof(2), A);
+                        A = fma(CIRC ? S.cwf[2] : __ldg(cr + 2), yof(3), A);
+                        z = fma(CIRC ? S.cQ[0] : __ldg(cr + 12), A, mine[e_next(w, q, 1) * nxy]);
                     }
                     m.Zk[w * ML + lane] = z;
                 }
@@ -468,13 +477,19 @@ __global__ void __launch_bounds__(MW * ML, 4) splitz_march_kernel(const __grid_c
                 for (int j = 0; j < C; j++) { vv[j] = __ldcs(vp); vp += nxy; }
             }
             const bool endr = (s == R);
-            const double B1 = march_look_ahead(m1.Z + ((h ^ 1) * MW) * ML, endr ? m1.Zk : m1.Z + (h * MW) * ML,
-                                               S1.crec + (size_t)tbg * 16, w, lane);
-            march_finish<true>(o1, S1, m1, tbg, T, A1p, B1, lane);
+            const double B1 = CIRC ? march_look_ahead_w(m1.Z + ((h ^ 1) * MW) * ML, endr ? m1.Zk : m1.Z + (h * MW) * ML,
+                                                        S1.cwb[0], S1.cwb[1], S1.cwb[2], w, lane)
+                                   : march_look_ahead(m1.Z + ((h ^ 1) * MW) * ML, endr ? m1.Zk : m1.Z + (h * MW) * ML,
+                                                      S1.crec + (size_t)tbg * 16, w, lane);
+            if (CIRC) { finish_const(o1, S1, A1p, B1); scale_rho(o1, S1, tbg); }
+            else march_finish<true>(o1, S1, m1, tbg, T, A1p, B1, lane);
             if (TWO) {
-                const double B2 = march_look_ahead(m2.Z + ((h ^ 1) * MW) * ML, endr ? m2.Zk : m2.Z + (h * MW) * ML,
-                                                   S2.crec + (size_t)tbg * 16, w, lane);
-                march_finish<true>(o2, S2, m2, tbg, T, A2p, B2, lane);
+                const double B2 = CIRC ? march_look_ahead_w(m2.Z + ((h ^ 1) * MW) * ML, endr ? m2.Zk : m2.Z + (h * MW) * ML,
+                                                            S2.cwb[0], S2.cwb[1], S2.cwb[2], w, lane)
+                                       : march_look_ahead(m2.Z + ((h ^ 1) * MW) * ML, endr ? m2.Zk : m2.Z + (h * MW) * ML,
+                                                          S2.crec + (size_t)tbg * 16, w, lane);
+                if (CIRC) { finish_const(o2, S2, A2p, B2); scale_rho(o2, S2, tbg); }
+                else march_finish<true>(o2, S2, m2, tbg, T, A2p, B2, lane);
 #pragma unroll
                 for (int j = 0; j < C; j++) o1[j] = o2[j] - vv[j] * o1[j];
             }
@@ -501,7 +516,7 @@ __global__ void __launch_bounds__(MW * ML, 4) splitz_march_kernel(const __grid_c
 // for the first rank) -- in the geometry of the march (lane = line, warp = chunk): a fraction (MW + LBM) / Tl of the field is
 // read instead of all of it.
 template <int MODE>
-__global__ void __launch_bounds__(MW * ML, 4) splitz_ends_kernel(const __grid_constant__ SplitArgs a, int nfirst, int nlist, bool trim) {
+__global__ void __launch_bounds__(MW * ML, 4) splitz_ends_kernel(const __grid_constant__ SplitArgs a, int nfirst, int nlist, bool trim, bool circ) {
     constexpr bool TWO = (MODE == MODE_BURGERS);
     constexpr int NS = TWO ? 2 : 1;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -542,6 +557,16 @@ __global__ void __launch_bounds__(MW * ML, 4) splitz_ends_kernel(const __grid_co
         double f[C], yend, part;
         if (s) rhs_interior<true>(u, f, a.rhs2);
         else rhs_interior<false>(u, f, a.rhs1);
+        if (circ) {
+            // circulant form: constant chunk; (y, x^_0) of the first LBM chunks for the previous rank, y of the last LBM for the next
+            local_const(f, S, yend);
+            if (t < LBM) {
+                double* d = a.to_prev + e_next(t, s, 0) * nxy + line;
+                d[0] = yend; d[nxy] = f[0];
+            }
+            if (t >= Tl - LBM) a.to_next[e_prev(t - (Tl - LB2), s) * nxy + line] = yend;
+            continue;
+        }
         march_local<true>(f, S, tg, yend, part);
         // only what splitz_march_kernel reads: (y, x^_0) of the first LBM chunks for the previous rank -- the first rank's MW
         // chunks with their closure terms for the last one --, y of the last LBM chunks for the next rank, (y, p) of the
@@ -559,15 +584,20 @@ __global__ void __launch_bounds__(MW * ML, 4) splitz_ends_kernel(const __grid_co
     }
 }
 
+bool split_circ(const SplitArgs& a, int mode) {
+    return ctx().tune_circ != 0 && a.s1.circ && (mode != MODE_BURGERS || a.s2.circ);
+}
+
 template <int MODE>
 cudaError_t launch_split_ends(const SplitArgs& a, cudaStream_t st) {
     const bool last = (a.t0 + a.Tl == a.T);
     const bool trim = ctx().tune_split_trim != 0;
-    int nfirst = (trim && a.t0 != 0) ? LBM : MW, nlast = last ? LBM + MW : LBM;
+    const bool circ = split_circ(a, MODE);
+    int nfirst = (circ || (trim && a.t0 != 0)) ? LBM : MW, nlast = (last && !circ) ? LBM + MW : LBM;
     int nlist = nfirst + nlast;
     if (nlist >= a.Tl) { nfirst = a.Tl; nlist = a.Tl; }        // the two sets meet: every chunk once
     const dim3 grid((unsigned)(a.nxy / ML), (unsigned)((nlist + MW - 1) / MW), 1);
-    splitz_ends_kernel<MODE><<<grid, MW * ML, 0, st>>>(a, nfirst, nlist, trim);
+    splitz_ends_kernel<MODE><<<grid, MW * ML, 0, st>>>(a, nfirst, nlist, trim, circ);
     return cudaGetLastError();
 }
 
@@ -583,11 +613,13 @@ cudaError_t launch_split_march(const SplitArgs& a, cudaStream_t st) {
     const size_t smem = (size_t)((MODE == MODE_BURGERS) ? 2 : 1) * M_SYS * sizeof(double);
     static bool set = false;
     if (!set) {
-        cudaError_t e = cudaFuncSetAttribute(splitz_march_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(splitz_march_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(splitz_march_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         set = true;
     }
-    splitz_march_kernel<MODE><<<(unsigned)(a.nxy / ML), MW * ML, smem, st>>>(a);
+    if (split_circ(a, MODE)) splitz_march_kernel<MODE, true><<<(unsigned)(a.nxy / ML), MW * ML, smem, st>>>(a);
+    else splitz_march_kernel<MODE, false><<<(unsigned)(a.nxy / ML), MW * ML, smem, st>>>(a);
     return cudaGetLastError();
 }
 
