@@ -145,10 +145,14 @@ static bool build_line2(int mode, const LineArgs& a, const DevPlan& p, const Sys
     b.march_red = ctx().tune_march_red;
     b.march_cfg = ctx().tune_march_cfg;
     b.march_pf = ctx().tune_march_pf;
+    b.march_peel = ctx().tune_march_peel ? 0 : -1;      // -1: never peel (tuning key march_peel = 0)
     // marching panels: periodic directions by default (z: 21.8 -> 14.6 ms for the four Burgers launches at C3, 8.4 -> 5.2 ms for the two
     // derivatives); non-periodic directions (all chunks read coefficient tables) only on request (march = 2) or when the lines
     // are so long that the whole-line kernels are left with 64-byte rows (more than 32 chunks)
-    const bool march_wanted = ctx().tune_march >= 2 || (ctx().tune_march == 1 && (p.periodic || b.T > 32));
+    // ... or, for OPR_Burgers, when only the rounds at the walls read tables (unscaled constant chunks, plan.cu): the marching kernel
+    // then runs constant-only steps in between (y at C3: 15.3 -> 13.9 ms for the four launches)
+    const bool march_wanted = ctx().tune_march >= 2 ||
+                              (ctx().tune_march == 1 && (p.periodic || b.T > 32 || (mode == MODE_BURGERS && march_peelable(mode, b, p.periodic))));
     b.march = (!contig && march_wanted && !b.tma && !b.persist && !b.pair &&
                march_eligible(mode, b, p.periodic, p.need_1der, a.nlines, a.inner)) ? 1 : 0;
     return true;
@@ -468,6 +472,7 @@ int tlab_gpu_set_tuning(const char* key, int value) {
     else if (!std::strcmp(key, "march_red")) ctx().tune_march_red = value;
     else if (!std::strcmp(key, "march_cfg")) ctx().tune_march_cfg = value;
     else if (!std::strcmp(key, "march_pf")) ctx().tune_march_pf = value;
+    else if (!std::strcmp(key, "march_peel")) ctx().tune_march_peel = value;
     else if (!std::strcmp(key, "fuse")) ctx().tune_fuse = value;
     else if (!std::strcmp(key, "overlap")) ctx().tune_overlap = value;
     else if (!std::strcmp(key, "kxsplit")) ctx().tune_kxsplit = value;

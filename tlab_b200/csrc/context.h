@@ -50,6 +50,7 @@ struct Context {
     int tune_lazy_scale = 1;  // RK substep: `hq = hq*kco` is not written by the update but folded into the first accumulation of the next
                               // substep (buoyancy source, OPR_Burgers_X): 8 B/pt less per field and substep, same bits
     int tune_pull_overlap = 1; // kx-split Poisson stage: pulls of p^ and dp^/dy on a second stream, beside the inverse transforms
+    int tune_march_peel = 1;  // marching kernels of non-periodic directions: constant-only steps for the rounds away from the walls
     int tune_circ = 1;        // periodic directions: circulant form of the fast kernels (constant chunks everywhere, wrapping windows)
     int tune_split_trim = 1;  // split-z marching kernels: phase 1 publishes only the chunk ends phase 2 reads
     int tune_split_local = 0; // timing experiment: phase 1 writes its ends into the own block instead of the peers' (results are wrong)

@@ -19,6 +19,7 @@ struct Line2Args {
     int march = 0;                    // strided kernel: marching panels of 32 lines (march.cu)
     int march_cfg = 4;                // marching kernel: resident CTAs per SM it is compiled for (+10: velocity requested before the barriers)
     int march_pf = 0;                 // marching kernel: L2 prefetch of the finishing stage's operands at the start of a step
+    int march_peel = 0;               // marching kernel, non-periodic direction: rounds 1 .. R-2 hold constant chunks only (peeled steps)
     int march_red = 0;                // marching kernel: accumulate with red.global.add.f64 instead of load + store
     int tma_l2 = 0;                   // L2 promotion of the tensor maps (0 none, 1/2/3: 64/128/256 bytes)
     double scale = 0.0;               // input is u + scale * u2 when u2 != nullptr
@@ -60,6 +61,7 @@ cudaError_t launch_lines2(int mode, const Line2Args& a, bool periodic, bool need
 // marching-panel kernels (march.cu)
 bool march_sys_ok(const std::vector<double>& crec, int T, int K0, int K1, bool periodic);
 bool march_eligible(int mode, const Line2Args& a, bool periodic, bool need1, long long nlines, long long inner);
+bool march_peelable(int mode, const Line2Args& a, bool periodic);     // non-periodic: constant-only rounds away from the walls
 cudaError_t launch_march(int mode, const Line2Args& a, bool periodic, bool need1, long long nlines, long long inner, cudaStream_t s);
 
 }  // namespace tlab

@@ -297,8 +297,17 @@ bool march_eligible(int mode, const Line2Args& a, bool periodic, bool need1, lon
     return true;
 }
 
-cudaError_t launch_march(int mode, const Line2Args& a, bool periodic, bool need1, long long nlines, long long inner, cudaStream_t s) {
+// peeled steps: the rounds between the first and the last hold unscaled constant chunks only, in every system of the launch
+bool march_peelable(int mode, const Line2Args& a, bool periodic) {
+    const int R = a.T / MW;
+    auto inner_const = [&](const Sys2& S) { return S.rho != nullptr && S.c_lo <= MW && S.c_hi >= a.T - MW - 1; };
+    return !periodic && R >= 3 && a.march_peel >= 0 && inner_const(a.s1) && (mode != MODE_BURGERS || inner_const(a.s2));
+}
+
+cudaError_t launch_march(int mode, const Line2Args& a_in, bool periodic, bool need1, long long nlines, long long inner, cudaStream_t s) {
     const dim3 grid((unsigned)(inner / ML), (unsigned)(nlines / inner), 1);
+    Line2Args a = a_in;
+    a.march_peel = march_peelable(mode, a, periodic) ? 1 : 0;
     if (mode == MODE_P1) {
         return periodic ? launch_march_k<MODE_P1, true, false>(a, grid, s) : launch_march_k<MODE_P1, false, false>(a, grid, s);
     }

@@ -289,6 +289,14 @@ void build_sys2(DevPlan& p, Sys2& s2, const std::vector<double>& alpha, const st
         fprintf(stderr, "[sys2] n=%d T=%d periodic=%d Wf=%d Wb=%d const_chunks=%d K0=%d K1=%d ca=%g cd=%g cg=%g Af=%g Rb=%g\n", n, T,
                 (int)periodic, window(Af, true), window(Rb, false), nc, s2.K0, s2.K1, s2.ca, s2.cd, s2.cg, Af[T / 2], Rb[T / 2]);
     }
+    {
+        // longest run of constant chunks
+        int best = 0, lo = 0;
+        for (int t = 0; t < T; t++) {
+            if (!isc[t]) { lo = t + 1; continue; }
+            if (t - lo + 1 > best) { best = t - lo + 1; s2.c_lo = lo; s2.c_hi = t; }
+        }
+    }
     if (unscaled) {
         int nc = 0;
         for (int t = 0; t < T; t++) nc += isc[t];

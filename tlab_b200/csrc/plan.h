@@ -66,6 +66,7 @@ struct Sys2 {
     int circ = 0;
     double cwf[LB2], cwb[LB2];
     const double* rho = nullptr;     // item (t, j) at ((t>>3)*CHUNK + j)*8 + (t&7)
+    int c_lo = 0, c_hi = -1;         // chunks c_lo .. c_hi are all constant chunks (non-periodic: everything but the chunks at the walls)
     double jscale = 1.0;             // factor of the solution (the diffusivity of a Burgers system): scales the Jacobian correction
     int ok = 0;                      // 0: look-back window too long for the fast kernels
     int march_ok = 0;                // 1: a window of 3 chunks suffices (dropped weights < 2^-64) and the closure chunks fit one round
