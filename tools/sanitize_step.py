@@ -18,14 +18,17 @@ def main():
     L = tl.load()
     variants = [("default", {}), ("march=2", {"march": 2}), ("march_red", {"march": 2, "march_red": 1}),
                 ("split_emulate=2", {"split_emulate": 2}), ("fast=0", {"fast": 0}), ("tma=1", {"tma": 1, "march": 0}),
-                ("lazy_scale=0", {"lazy_scale": 0}), ("fuse=1", {"fuse": 1})]
+                ("lazy_scale=0", {"lazy_scale": 0}), ("fuse=1", {"fuse": 1}),
+                # lines long enough for the circulant form in x and z (8 chunks) and for the peeled marching steps in y (3 rounds)
+                ("circ_peel", {"shape": (128, 192, 128)}), ("split_circ", {"shape": (128, 64, 256), "split_emulate": 2})]
     only = sys.argv[1:] or None
-    nx, ny, nz = 32, 128, 192
-    x, y, z = grid_periodic(nx), grid_tanh(ny), grid_periodic(nz)
     D, N = GD.DNS_BCS_DIRICHLET, GD.DNS_BCS_NEUMANN
     for name, tune in variants:
-        if only and name not in only:
+        if (only and name not in only) or (not only and "shape" in tune):
             continue
+        tune = dict(tune)
+        nx, ny, nz = tune.pop("shape", (32, 128, 192))
+        x, y, z = grid_periodic(nx), grid_tanh(ny), grid_periodic(nz)
         for k, v in tune.items():
             tl.check(L.tlab_gpu_set_tuning(k.encode(), v))
         g = [opr.FdmPlan(x, True, True, name="x"), opr.FdmPlan(y, False, False, name="y"), opr.FdmPlan(z, True, True, name="z")]
