@@ -80,3 +80,18 @@ def test_broken_header_is_rejected(tmp_path):
     with pytest.raises(tio.TlabIOError) as e:
         tio.read_fields(name, 2, 2, 2, 1)
     assert e.value.code == tio.DNS_ERROR_RECLEN
+
+
+def test_slab_writes_need_no_ordering_between_ranks(tmp_path):
+    """Slab-wise IO_Write_Fields: the header rank may come last (or find a stale, longer file) -- the file is the same."""
+    from tlab_b200 import io
+    rng = np.random.default_rng(5)
+    nx, ny, nz = 8, 5, 12
+    a = rng.standard_normal((nz, ny, nx))
+    ref, out = str(tmp_path / "ref"), str(tmp_path / "out")
+    io.write_fields(ref, 7, [a], params=[0.5, 1e-3])
+    with open(io.field_name(out, 1), "wb") as f:
+        f.write(b"\xff" * (3 * a.nbytes))                     # a stale longer file
+    for koff in (8, 4, 0):                                      # last slab first, header rank last
+        io.write_fields(out, 7, [a[koff:koff + 4]], params=[0.5, 1e-3], koff=koff, nz_total=nz)
+    assert open(io.field_name(out, 1), "rb").read() == open(io.field_name(ref, 1), "rb").read()

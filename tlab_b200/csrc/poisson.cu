@@ -1521,6 +1521,8 @@ int Poisson::solve(double* p, double* c1, double* c2, const double* hb, const do
         KxTab ta, tb;
         const Trp::PeerTab* pa = T.find(cpa);
         const Trp::PeerTab* pb = T.find(cpb);
+        // the registry is emptied when a later registration finds that not every rank can map peer memory (trp.cu)
+        if (!pa || !pb) return fail(TLAB_ERR_OPTION, "OPR_Poisson: the peer mappings of the kx-split exchange are gone; re-initialise the elliptic solver");
         for (int q = 0; q < 8; q++) { ta.p[q] = (double2*)pa->p[q]; tb.p[q] = (double2*)pb->p[q]; }
         for (int q = 0; q < 9; q++) { ta.kx0[q] = kx0[q]; tb.kx0[q] = kx0[q]; }
         const unsigned ctas = (unsigned)std::min<long long>(((long long)ny * nz + KXR - 1) / KXR, T.p2p_ctas * 4);

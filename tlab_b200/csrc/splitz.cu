@@ -703,6 +703,9 @@ int run_split(SplitZ& z, int mode, tlab_plan_s* g, int is, const double* u, cons
     a.rhs1 = p.rhs1[0]; a.rhs2 = p.rhs2;
     a.s1 = p.sys1[0];
     if (mode == MODE_BURGERS) a.s2 = p.sys2[g->burgers_first + is];
+    // the registry is emptied when a later registration finds that not every rank can map peer memory (trp.cu)
+    if (z.emulate <= 1 && !trp().find(z.block[par][0]))
+        return fail(TLAB_ERR_OPTION, "split-z operators: the peer mappings of the exchange blocks are gone; re-create the DNS handle");
     const int nv = z.emulate > 1 ? z.P : 1;          // slabs handled by this process
     const long long slab = (long long)z.kmax * z.nxy;
     auto blk = [&](int r) -> double* {

@@ -121,12 +121,16 @@ def write_fields(fname, nt, fields, params=(), koff=0, nz_total=None):
         nzt = nzl if nz_total is None else int(nz_total)
         p = params[min(i, len(params) - 1)] if per_field else params
         name = field_name(fname, i + 1)
-        if koff == 0:
-            with open(name, "wb") as f:
-                offset = write_header(f, nx, ny, nzt, nt, p)
-                f.truncate(offset + nx * ny * nzt * SIZEOFREAL)
+        # Every rank opens the file create-if-missing and WITHOUT truncation, and every byte of it is written by exactly one
+        # rank (the header by the rank with koff = 0, each slab by its owner), so the ranks need no ordering among themselves
+        # (the reference puts an MPI_BARRIER between its header write and the MPI-IO data write; src/io/io_fields.f90).
+        # A stale longer file is cut to size by the header rank.
         offset = 5 * SIZEOFINT + len(np.ravel(p)) * SIZEOFREAL
-        with open(name, "r+b") as f:
+        fd = os.open(name, os.O_RDWR | os.O_CREAT, 0o644)
+        with os.fdopen(fd, "r+b") as f:
+            if koff == 0:
+                assert write_header(f, nx, ny, nzt, nt, p) == offset
+                f.truncate(offset + nx * ny * nzt * SIZEOFREAL)
             f.seek(offset + koff * ny * nx * SIZEOFREAL)
             f.write(a.tobytes())
 
