@@ -178,6 +178,33 @@ def test_tuning_variants_give_the_same_step(cuda, tune):
             tl.check(L.tlab_gpu_set_tuning(k.encode(), v))
 
 
+@pytest.mark.parametrize("tune", [{"fuse": 1}, {"persist": 1, "march": 0}, {"tma": 1, "march": 0}, {"pair": 1, "march": 0}, {"march": 0},
+                                  {"march": 2}, {"march": 2, "march_peel": 0}, {"circ": 0}, {"fast": 0}, {"lines_x": 8}, {"lines_yz": 8, "march": 0}])
+def test_tuning_variants_on_lines_long_enough_for_the_circulant_form(cuda, tune):
+    """The same on 128 x 192 x 128: x and z lines of 8 chunks (circulant form in every whole-line variant: fused launch,
+    cp.async staging, TMA tiles, CTA pairs, other tilings; and its closure-form fallback circ = 0), y lines of 12 chunks
+    (unscaled constant chunks; marching kernel with and without the peeled constant-only steps)."""
+    from tlab_b200 import lib as tl
+    L = tl.load()
+    defaults = {"fuse": 0, "persist": 0, "tma": 0, "pair": 0, "march": 1, "march_peel": 1, "circ": 1, "fast": 1, "lines_x": 0, "lines_yz": 0}
+    try:
+        for k, v in tune.items():
+            tl.check(L.tlab_gpu_set_tuning(k.encode(), v))
+        o, g = _pair(128, 192, 128, "tanh")
+        if "ref" not in _LONG_REF:                 # the oracle's step once for all variants (it is the slow part)
+            o.runge_kutta(1e-3)
+            _LONG_REF["ref"] = [q.copy() for q in o.q] + [o.s[0].copy()]
+        g.runge_kutta(1e-3)
+        for name, ref in zip(("q1", "q2", "q3", "s1"), _LONG_REF["ref"]):
+            assert rel_l2(g.get(name), ref) <= 1e-11
+    finally:
+        for k, v in defaults.items():
+            tl.check(L.tlab_gpu_set_tuning(k.encode(), v))
+
+
+_LONG_REF = {}
+
+
 @pytest.mark.parametrize("shape,lines", [((16, 64, 128), 0), ((16, 32, 1024), 0), ((16, 32, 1024), 4), ((16, 512, 16), 4),
                                          ((16, 512, 16), 8)])
 def test_step_through_the_tma_kernels(cuda, shape, lines):
