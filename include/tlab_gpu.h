@@ -91,8 +91,23 @@ int tlab_gpu_prefetch(const void* ptr, size_t bytes, int to_device);
 int tlab_gpu_upload(void* dst_device, const void* src_host, size_t bytes);
 int tlab_gpu_download(void* dst_host, const void* src_device, size_t bytes);
 int tlab_gpu_copy(void* dst_device, const void* src_device, size_t bytes);
-/* "lines_x", "lines_yz": lines per CTA of the general line kernels (0 = automatic); "fast": 1/0 use the fast line
- * kernels where the geometry allows (default 1); "pf_dist": their L2 prefetch distance in tiles (-1 automatic, 0 off) */
+/* Tuning keys (all optional; the defaults are what bench.py measures; every variant is an alternative schedule of the same
+ * arithmetic and is tested against the oracle, tests/test_dns_gpu.py):
+ *   "lines_x", "lines_yz"   lines per CTA of the line kernels (0 = automatic)
+ *   "fast"                  1/0: the fast line kernels (lines2.cu, march.cu) where the geometry allows (default 1)
+ *   "pf_dist"               their L2 prefetch distance in tiles (-1 automatic, 0 off)
+ *   "circ"                  1/0: periodic directions in circulant form (default 1) / with the rank-one closure of TRIDPFS
+ *   "march"                 marching-panel kernels: 1 = periodic directions, lines longer than 32 chunks and OPR_Burgers along
+ *                           non-periodic directions whose interior chunks are constant (default), 2 = wherever eligible, 0 = off
+ *   "march_peel"            1/0: constant-only steps for the interior rounds of a non-periodic march (default 1)
+ *   "march_cfg", "march_red", "march_pf"   register budget / red.global.add accumulation / L2 prefetch of the marching kernels
+ *   "fuse", "pf_next", "persist", "pair", "tma", "tma_l2", "neu_compact", "fuse_update", "lazy_scale"   see DESIGN.md section 4
+ *   "splitz"                1/0: z operators of a z-split domain on the slabs (default 1) / through K-transposes
+ *   "split_trim", "split_emulate", "split_local"   phase 1 publishes only what phase 2 reads (default 1); virtual slabs on one
+ *                           GPU (tests); timing experiment (wrong results)
+ *   "poisson_split", "poisson_il", "poisson_minb", "pull_overlap"   Poisson stage: kx-split exchange, table interleave, CTAs per
+ *                           SM of the y solves, two-stream way back
+ * Unknown keys return TLAB_ERR_OPTION. */
 int tlab_gpu_set_tuning(const char* key, int value);
 /* "tma": 1/0 run the y/z line operators as persistent CTAs fed and drained by the TMA unit (default 0: measured slower on rows
  * of 32-128 bytes; falls back to the LSU kernels when a geometry is not eligible).
