@@ -178,3 +178,41 @@ def test_unscaled_constant_chunks_reproduce_tridss(kind, n, second):
             xsol[i0:i0 + C] = xh[i0:i0 + C] + Q[i0:i0 + C] * A[t] + R[i0:i0 + C] * Bx
         Bx = xsol[i0]
     assert np.abs(xsol - ref).max() <= 1e-13 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("second", [False, True])
+@pytest.mark.parametrize("n,P", [(256, 2), (1024, 4), (1024, 8), (2048, 8)])
+def test_circulant_form_split_over_ranks(n, P, second):
+    """What splitz_ends_kernel / splitz_march_kernel<CIRC> exchange (csrc/splitz.cu): a rank that owns Tl consecutive chunks of a
+    periodic line needs, beyond its own data, the forward ends y of the previous rank's last 3 chunks and (y, x^_0) of the next
+    rank's first 3 chunks -- rank P-1 and rank 0 are neighbours like any other pair -- and reproduces TRIDPSS on its chunks."""
+    from oracle import fdm
+    LBM = 3
+    plan = fdm.Plan(grid_periodic(n), True, True)
+    der = plan.der2 if second else plan.der1
+    a, d, g, s = _factors(plan, second, True)
+    mid = slice(n // 4, n - n // 4)
+    ca, cd, cg = a[mid].mean(), d[mid].mean(), g[mid].mean()
+    rho = (1.0 / s) / np.mean(1.0 / s[mid])
+    f = np.random.default_rng(11).standard_normal(n)
+    ref = f.copy()
+    fdm.tridpss(*[der.lu[1:, k].copy() for k in range(1, 6)], ref)
+    T, Tl = n // C, n // C // P
+    Q, R = _const_chunk_tables(ca, cd, cg)
+    wf, wb = (ca ** C) ** np.arange(LBM), (cg ** C) ** np.arange(LBM)
+    assert abs((ca ** C) ** LBM) < 2.0 ** -56 and abs((cg ** C) ** LBM) < 2.0 ** -56        # the dropped fourth term
+    # phase 1 on every rank: zero-inflow sweeps of its first and last LBM chunks, ends published to the neighbours
+    xh_all, ye_all = _local(f, ca, cd, cg)           # (a rank only ever reads its own chunks and the published ends of these)
+    out = np.zeros(n)
+    for r in range(P):
+        t0 = r * Tl
+        prev_y = [ye_all[(t0 - 1 - k) % T] for k in range(LBM)]                  # from rank r-1: its last LBM chunks
+        next_y = [ye_all[(t0 + Tl + k) % T] for k in range(LBM)]                  # from rank r+1: its first LBM chunks
+        next_x0 = [xh_all[((t0 + Tl + k) % T) * C] for k in range(LBM)]
+        ye = np.concatenate([prev_y[::-1], ye_all[t0:t0 + Tl], next_y])          # index LBM + local chunk
+        A = np.array([sum(wf[k] * ye[LBM + t - 1 - k] for k in range(LBM)) for t in range(Tl + LBM)])
+        z = np.concatenate([xh_all[t0 * C:(t0 + Tl) * C:C], next_x0]) + Q[0] * A  # chunk starts, own and beyond the slab
+        B = np.array([sum(wb[k] * z[t + 1 + k] for k in range(LBM)) for t in range(Tl)])
+        x = xh_all[t0 * C:(t0 + Tl) * C].reshape(Tl, C) + np.outer(A[:Tl], Q) + np.outer(B, R)
+        out[t0 * C:(t0 + Tl) * C] = x.reshape(-1) * rho[t0 * C:(t0 + Tl) * C]
+    assert np.abs(out - ref).max() <= 2e-14 * np.abs(ref).max()
