@@ -45,3 +45,25 @@ def rel_l2(a, b):
     b = np.asarray(b, dtype=np.float64).ravel()
     den = np.linalg.norm(b)
     return np.linalg.norm(a - b) / (den if den > 0 else 1.0)
+
+
+def dense_direct2(der, n):
+    """A2 (tridiagonal + wall extensions) and B2 (pentadiagonal, MatMul_5d column conventions) of the direct second derivative."""
+    L, R = der.lhs, der.rhs
+    A, B = np.zeros((n, n)), np.zeros((n, n))
+    for i in range(1, n + 1):
+        if i > 1:
+            A[i - 1, i - 2] = L[i, 1]
+        A[i - 1, i - 1] = L[i, 2]
+        if i < n:
+            A[i - 1, i] = L[i, 3]
+    A[0, 2] = L[1, 1]                       # extended stencil of the wall rows (fdm_comx_direct.f90: third lhs coefficient)
+    A[n - 1, n - 3] = L[n, 3]
+    for i in range(3, n - 1):
+        for k in range(1, 6):
+            B[i - 1, i - 3 + k - 1] = R[i, k]
+    B[0, 0:3] = R[1, 3:6]; B[0, 3] = R[1, 1]
+    B[1, 0:4] = R[2, 2:6]
+    B[n - 2, n - 4:n] = R[n - 1, 1:5]
+    B[n - 1, n - 3:n] = R[n, 1:4]; B[n - 1, n - 4] = R[n, 5]
+    return A, B

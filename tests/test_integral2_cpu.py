@@ -10,29 +10,7 @@ its result must satisfy, computed independently of it with dense matrices of the
 import numpy as np
 import pytest
 
-from common import grid_periodic, grid_tanh, grid_stretched
-
-
-def _dense(der, n):
-    """A2 (tridiagonal + wall extensions) and B2 (pentadiagonal, MatMul_5d column conventions) of the direct second derivative."""
-    L, R = der.lhs, der.rhs
-    A, B = np.zeros((n, n)), np.zeros((n, n))
-    for i in range(1, n + 1):
-        if i > 1:
-            A[i - 1, i - 2] = L[i, 1]
-        A[i - 1, i - 1] = L[i, 2]
-        if i < n:
-            A[i - 1, i] = L[i, 3]
-    A[0, 2] = L[1, 1]                       # extended stencil of the wall rows (fdm_comx_direct.f90: third lhs coefficient)
-    A[n - 1, n - 3] = L[n, 3]
-    for i in range(3, n - 1):
-        for k in range(1, 6):
-            B[i - 1, i - 3 + k - 1] = R[i, k]
-    B[0, 0:3] = R[1, 3:6]; B[0, 3] = R[1, 1]
-    B[1, 0:4] = R[2, 2:6]
-    B[n - 2, n - 4:n] = R[n - 1, 1:5]
-    B[n - 1, n - 3:n] = R[n, 1:4]; B[n - 1, n - 4] = R[n, 5]
-    return A, B
+from common import grid_periodic, grid_tanh, grid_stretched, dense_direct2 as _dense
 
 
 @pytest.fixture(scope="module")
@@ -135,3 +113,32 @@ def test_direct_poisson_solver():
     assert np.abs(p - a - shift).max() <= 2e-4 * np.abs(a).max()
     assert abs(p[:, 0, :].mean()) <= 1e-12
     assert np.abs(dpdy - day).max() <= 2e-3 * np.abs(day).max()
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_direct_second_derivative_is_exact_for_polynomials_on_a_random_grid(seed):
+    """An independent pin of oracle/fdm_direct.py (FDM_C2N6_Direct, fdm_comx_direct.f90:305-412; the reference holds no golden
+    for it): on an arbitrary non-uniform grid the compact relation A2 p'' = B2 p must hold EXACTLY for polynomials up to degree 6
+    in the interior rows and up to degree 4 in the two rows at either wall (coef_c2n3_biased / coef_c2n4) -- and must fail beyond
+    (so the test is not vacuous).  Any wrong coefficient breaks the exactness."""
+    from oracle import fdm
+    rng = np.random.default_rng(seed)
+    n = 24
+    x = np.cumsum(0.5 + rng.random(n))
+    x = (x - x[0]) / (x[-1] - x[0])
+    plan = fdm.Plan(x, False, False, mode2=fdm.FDM_COM6_DIRECT)
+    A, B = _dense(plan.der2, n)
+    xc = x - 0.5
+    for k in range(9):
+        p = xc ** k
+        pp = k * (k - 1) * xc ** (k - 2) if k >= 2 else 0.0 * xc
+        r = np.abs(A @ pp - B @ p) / (np.abs(A) @ np.abs(pp) + np.abs(B) @ np.abs(p))
+        wall = np.r_[r[:2], r[-2:]]
+        if k <= 4:
+            assert wall.max() <= 1e-14, (k, wall)
+        if k <= 6:
+            assert r[2:-2].max() <= 1e-14, (k, r[2:-2].max())
+        if k == 5:
+            assert wall.min() > 1e-9          # third / fourth-order wall closures
+        if k == 8:
+            assert r[3:-3].max() > 1e-4       # sixth-order interior scheme
