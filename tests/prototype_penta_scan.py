@@ -13,7 +13,7 @@ cannot be truncated to a window -- this script measures that, and checks that th
 solves the reference's own factored systems (oracle.integral.int1_initialize on the tanh grid of C3) for the range of
 eigenvalues of C3 and both boundary types, and compares with PENTADSS.
 
-    python tools/prototype_penta_scan.py
+    python tests/prototype_penta_scan.py
 """
 import os
 import sys
