@@ -6,7 +6,7 @@ Follows /root/reference/src:
   fdm/fdm_integral.f90     FDM_Int1_CreateSystem (:91-214), FDM_Int1_Initialize (:58-87),
                            FDM_Int1_Solve (:219-314)
   operators/opr_odes.f90   OPR_ODE2_Factorize_DN_Sing (:37-96), _NN_Sing (:165-183),
-                           _NN (:265-386), _DD (:391-478), _DD_Sing (:188-260)
+                           _NN (:265-386), _DD (:391-478), _DD_Sing (:188-260); the DD pair is ORACLE ONLY (the CUDA path solves BCS_NN)
 
 Storage: fdmi.lhs(n+1, 5+1), fdmi.rhs(n+1, 3+1) 1-based padded;
 rhs_b(1:5, 0:7) as [6][8]; rhs_t(0:4, 8) as [5][9].
@@ -308,4 +308,86 @@ def ode2_factorize_nn(fdmi, rhsi_b, rhsi_t, f, bcs):
     i = 0
     u[i] = u[i] + fn * u1[i] + v[0] * sp[i] + u[nx - 1] * ep[i]
     v[i] = v[i] + lam * u[i]
+    return u, v
+
+
+def ode2_factorize_dd_sing(fdmi, f, bcs):
+    """opr_odes.f90:188-260 (Dirichlet / Dirichlet, lambda = 0).  f(n, nlines, M) (modified), bcs(2, nlines, M) -> u, v."""
+    nx = fdmi[BCS_MIN].lhs.shape[0] - 1
+    M = f.shape[2]
+    u = np.zeros_like(f)
+    v = np.zeros_like(f)
+    # v^(0) in v' = f, v_1 given (0 for now, to be found later on)
+    f[nx - 1] = 0.0
+    v[0] = 0.0
+    int1_solve(fdmi[BCS_MIN], fdmi[BCS_MIN].rhs, f, v)
+    # v^(1)
+    f1 = np.zeros((nx, 1, M))
+    f1[nx - 1] = 1.0
+    v1 = np.zeros((nx, 1, M))
+    int1_solve(fdmi[BCS_MIN], fdmi[BCS_MIN].rhs, f1, v1)
+    # u^(0) in u' = v, u_n given
+    u[nx - 1] = bcs[1]
+    du0_n = int1_solve(fdmi[BCS_MAX], fdmi[BCS_MAX].rhs, v, u, want_du=True)
+    # u^(1)
+    u1 = np.zeros((nx, 1, M))
+    du1_n = int1_solve(fdmi[BCS_MAX], fdmi[BCS_MAX].rhs, v1, u1, want_du=True)
+    # s^(+): the node displacements x(:) - x_n
+    f1[:] = 1.0
+    sp = np.zeros((nx, 1, M))
+    int1_solve(fdmi[BCS_MAX], fdmi[BCS_MAX].rhs, f1, sp)
+    # constraint
+    fn = 1.0 / (du1_n[0] - v1[nx - 1, 0])
+    du0_n = (v[nx - 1] - du0_n) * fn
+    # contribution from v_1 to satisfy the bc at the bottom
+    dummy = 1.0 / sp[0, 0]
+    v[0] = (bcs[0] - (u[0] + du0_n * u1[0, 0])) * dummy
+    u[0] = bcs[0]
+    for i in range(1, nx):
+        u[i] = u[i] + du0_n * u1[i, 0] + v[0] * sp[i, 0]
+        v[i] = v[i] + du0_n * v1[i, 0] + v[0]
+    return u, v
+
+
+def ode2_factorize_dd(fdmi, rhsi_b, rhsi_t, f, bcs):
+    """opr_odes.f90:391-478 (Dirichlet / Dirichlet).  f(n, nlines, M) (modified), bcs(2, nlines, M) -> u, v."""
+    lam = fdmi[BCS_MIN].lam
+    nx = fdmi[BCS_MIN].lhs.shape[0] - 1
+    M = f.shape[2]
+    u = np.zeros_like(f)
+    v = np.zeros_like(f)
+    # v^(0) in v' + lambda v = f, v_1 given (0 for now, to be found later on)
+    f[nx - 1] = 0.0
+    v[0] = 0.0
+    int1_solve(fdmi[BCS_MIN], rhsi_b, f, v)
+    # v^(1) and e^(-)
+    w1 = np.zeros((nx, 2, M))
+    w2 = np.zeros((nx, 2, M))
+    w1[nx - 1, 0] = 1.0      # f1(1, nx)
+    w2[0, 0] = 0.0           # v1(1)
+    w2[0, 1] = 1.0           # em(1)
+    int1_solve(fdmi[BCS_MIN], rhsi_b, w1, w2)
+    v1, em = w2[:, 0].copy(), w2[:, 1].copy()
+    # u^(0) in u' - lambda u = v, u_n given
+    u[nx - 1] = bcs[1]
+    du0_n = int1_solve(fdmi[BCS_MAX], rhsi_t, v, u, want_du=True)
+    # u^(1) and s^(+): forcing (v1, em), both zero at the top
+    w1[nx - 1, 0] = 0.0      # u1(nx)
+    w1[nx - 1, 1] = 0.0      # sp(nx)
+    der_bcs = int1_solve(fdmi[BCS_MAX], rhsi_t, w2, w1, want_du=True)
+    u1, sp = w1[:, 0], w1[:, 1]
+    du1_n, dsp_n = der_bcs[0], der_bcs[1]
+    # constraint and bottom boundary condition
+    aa = du1_n - v1[nx - 1]
+    bb = dsp_n - em[nx - 1]
+    dummy = 1.0 / (aa * sp[0] - bb * u1[0])
+    t = lam * bcs[1] - du0_n + v[nx - 1]
+    v0 = (aa * (bcs[0] - u[0]) - u1[0] * t) * dummy          # q1
+    fn = (sp[0] * t - bb * (bcs[0] - u[0])) * dummy
+    v[0] = v0
+    for i in range(nx - 1, 0, -1):
+        u[i] = u[i] + fn * u1[i] + v[0] * sp[i]
+        v[i] = v[i] + fn * v1[i] + v[0] * em[i] + lam * u[i]
+    u[0] = bcs[0]
+    v[0] = v[0] + lam * u[0]
     return u, v

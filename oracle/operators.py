@@ -19,7 +19,7 @@ import numpy as np
 
 from . import fdm
 from . import integral as I
-from .fdm import BCS_NN, BCS_ND, BCS_DN, BCS_MIN, BCS_MAX
+from .fdm import BCS_DD, BCS_NN, BCS_ND, BCS_DN, BCS_MIN, BCS_MAX
 
 OPR_P1, OPR_P2, OPR_P2_P1 = 1, 2, 3
 OPR_B_SELF, OPR_B_U_IN = 0, 1
@@ -133,9 +133,9 @@ class Elliptic:
 
 
 def opr_poisson(ell, p, bcs_hb, bcs_ht, ibc=BCS_NN):
-    """OPR_Poisson_FourierXZ_Factorize (opr_elliptic.f90:263-364), BCS_NN.
-    p(nz, ny, nx) forcing; bcs_hb, bcs_ht (nz, nx).  Returns (p, dpdy)."""
-    assert ibc == BCS_NN
+    """OPR_Poisson_FourierXZ_Factorize (opr_elliptic.f90:263-364), BCS_NN (wall-normal derivatives given) or BCS_DD (values
+    given).  p(nz, ny, nx) forcing; bcs_hb, bcs_ht (nz, nx).  Returns (p, dpdy)."""
+    assert ibc in (BCS_NN, BCS_DD)
     nz, ny, nx = p.shape
     p = p.copy()
     p[:, 0, :] = bcs_hb
@@ -165,7 +165,12 @@ def opr_poisson(ell, p, bcs_hb, bcs_ht, ibc=BCS_NN):
         bcs = np.zeros((2, 2, M))
         bcs[0] = f[0]
         bcs[1] = f[ny - 1]
-        if singular:
+        if ibc == BCS_DD:
+            if singular:
+                u, v = I.ode2_factorize_dd_sing(fi, f, bcs)
+            else:
+                u, v = I.ode2_factorize_dd(fi, fi[BCS_MIN].rhs, fi[BCS_MAX].rhs, f, bcs)
+        elif singular:
             u, v = I.ode2_factorize_nn_sing(fi, f, bcs)
         else:
             u, v = I.ode2_factorize_nn(fi, fi[BCS_MIN].rhs, fi[BCS_MAX].rhs, f, bcs)

@@ -222,3 +222,58 @@ def test_rk_step_is_divergence_free_and_matches_tables():
     bcs = [[0, 0], [0, 0]]
     div = sum(O.opr_partial(i, O.OPR_P1, bcs, g[i], o.q[i]) for i in range(3))
     assert np.abs(div[:, 1:-1, :]).max() < 1e-12       # "zero divergence down to round-off" (opr_elliptic.f90:109)
+
+
+def test_ode_solvers_with_dirichlet_data():
+    """OPR_ODE2_Factorize_DD / _DD_Sing (opr_odes.f90:188-260, 391-478; vintegral.f90's recipe): analytic solutions, linearity across
+    lines, and -- to round-off -- the first-order systems they are built from: v = delta u + ..., i.e. the pair (u, v) returned
+    satisfies u' = v and v' - lambda^2 u = f in the discrete sense of FDM_Int1 away from the walls (checked through the NN solver:
+    feeding the wall derivatives of the DD solution to OPR_ODE2_Factorize_NN returns the same u).  ORACLE ONLY."""
+    from oracle import fdm, integral as I
+    n = 129
+    y = grid_stretched(n, 1.0, 0.2)
+    g = fdm.Plan(y, False, False)
+    uex = np.cos(3 * y) + y ** 2
+    vex = -3 * np.sin(3 * y) + 2 * y
+    for lam2 in (0.0, 4.0, 400.0):
+        lam = np.sqrt(lam2)
+        fi = {1: I.int1_initialize(g.der1, lam, 1), 2: I.int1_initialize(g.der1, -lam, 2)}
+        fex = -9 * np.cos(3 * y) + 2 - lam2 * uex
+        f = np.zeros((n, 2, 1))
+        f[:, 0, 0], f[:, 1, 0] = fex, -2 * fex
+        bcs = np.zeros((2, 2, 1))
+        bcs[0, :, 0] = [uex[0], -2 * uex[0]]
+        bcs[1, :, 0] = [uex[-1], -2 * uex[-1]]
+        if lam2 == 0.0:
+            u, v = I.ode2_factorize_dd_sing(fi, f.copy(), bcs)
+        else:
+            u, v = I.ode2_factorize_dd(fi, fi[1].rhs, fi[2].rhs, f.copy(), bcs)
+        assert np.abs(u[:, 0, 0] - uex).max() < 1e-6
+        assert np.abs(u[:, 1, 0] + 2 * uex).max() < 2e-6          # linearity across lines
+        assert np.abs(v[:, 0, 0] - vex).max() < 1e-5
+        assert u[0, 0, 0] == uex[0] and abs(u[-1, 0, 0] - uex[-1]) <= 1e-13 * abs(uex[-1]) + 1e-15
+        if lam2 > 0.0:
+            # the same discrete solution through the Neumann solver, fed with the wall derivatives the DD solver returned
+            b2 = np.zeros((2, 2, 1))
+            b2[0], b2[1] = v[0], v[-1]
+            u2, v2 = I.ode2_factorize_nn(fi, fi[1].rhs, fi[2].rhs, f.copy(), b2)
+            assert np.abs(u2 - u).max() <= 1e-9 * np.abs(u).max()
+            assert np.abs(v2 - v).max() <= 1e-9 * np.abs(v).max()
+
+
+def test_poisson_round_trip_with_dirichlet_data():
+    """vpoisson.f90:212-241, the DD branch: OPR_Poisson with the wall values of a given field inverts div(grad) built from delta-delta
+    operators to round-off.  ORACLE ONLY (the CUDA path takes BCS_NN)."""
+    from oracle import fdm, operators as O
+    nx, ny, nz = 16, 33, 16
+    x, y, z = grid_periodic(nx), grid_tanh(ny), grid_periodic(nz)
+    g = [fdm.Plan(x, True, True), fdm.Plan(y, False, False), fdm.Plan(z, True, True)]
+    a = smooth_field((nz, ny, nx), (x, y, z), seed=22)
+    bcs = [[0, 0], [0, 0]]
+
+    def d(i, f):
+        return O.opr_partial(i, O.OPR_P1, bcs, g[i], f)
+    f = d(0, d(0, a)) + d(1, d(1, a)) + d(2, d(2, a))
+    p, dpdy = O.opr_poisson(O.Elliptic(g), f, a[:, 0, :], a[:, -1, :], ibc=fdm.BCS_DD)
+    assert rel_l2(p, a) < 1e-11
+    assert rel_l2(dpdy, d(1, a)) < 1e-10
